@@ -1,0 +1,523 @@
+// oracle/ref_harness.cu — headless driver around the UNMODIFIED reference renderer.
+//
+// TEST / BASELINE INFRASTRUCTURE ONLY.  Nothing in the product library (mort_b200/csrc) includes,
+// links or executes this file.  It exists to (1) pin parity: dump the reference's scenes, cameras,
+// primary-ray hits and images as golden fixtures; (2) be the baseline arm (`bench.py --impl
+// reference`): the reference's own renderKernel rebuilt for sm_100a, timed as the reference times
+// itself (CUDA events around the launch, /root/reference/mort.cu:96-114).
+//
+// How the reference gets in: `#include "mort.cu"` pulls the reference translation unit in where it
+// lies (-I/root/reference), byte for byte.  Only the platform headers it names (<Windows.h>,
+// gpu_anim.h, cpu_bitmap.h, gl_helper.h; mort.cu:5-10) resolve to the headless stand-ins under
+// oracle/stubs/, and its `main` is renamed so that ours can drive the same objects:
+//   scene functions            mort.cu:129-631   (called unchanged)
+//   Camera::initialize         camera.cuh:47-84  (called unchanged)
+//   world::toDevice            world.cuh:98-102  (called unchanged)
+//   setup_rng / renderKernel   rng.cuh:8-15 / mort.cu:44-47, launched exactly as mort.cu:695-709,106
+// Harness-side settings that the reference lacks (documented in SURVEY.md App. A-Q14/Q15): a padded
+// curandState allocation (setup_rng has no bounds check) and a larger device malloc heap (the
+// reference `new`s a cosine_pdf per diffuse bounce per resident thread).
+//
+// No reference source is copied into this repository; the build output goes to oracle/_ref/.
+
+#include <assert.h>
+#include <emmintrin.h>
+#include <limits.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <cuda_runtime_api.h>
+#include <curand.h>
+#include <curand_kernel.h>
+#include <math_constants.h>
+
+#include "mort_scene_format.h"
+
+// The reference keeps texture fields private (textures.cuh:31-35,64-71,150-154,206-213); the dump
+// needs to read them.  Access specifiers do not change layout.
+#define private public
+#define main mort_reference_windows_main
+#include "mort.cu"
+#undef main
+#undef private
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(3); } } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// scene dump (include/mort_scene_format.h)
+// ------------------------------------------------------------------------------------------------
+static void v3(float* d, const vec3& v) { d[0] = v.x(); d[1] = v.y(); d[2] = v.z(); }
+static void bb(float* d, const aabb& b) {
+    d[0] = b.x.imin; d[1] = b.x.imax; d[2] = b.y.imin; d[3] = b.y.imax; d[4] = b.z.imin; d[5] = b.z.imax;
+}
+static uint32_t fnv1a(const unsigned char* p, size_t n) {
+    uint32_t h = 2166136261u;
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 16777619u; }
+    return h;
+}
+static int bvh_nodes(const bvh& b) {
+    int n = 1;
+    for (int i = 0; i < n && i < MAX_BVH_NODES; i++)
+        if (b.is_internal_node[i]) {
+            n = std::max(n, b.left_children_idxs[i] + 1);
+            n = std::max(n, b.right_children_idxs[i] + 1);
+        }
+    return n;
+}
+template <class T> static void put(FILE* f, const T& v) { fwrite(&v, sizeof(T), 1, f); }
+
+static void fill_camera(mscn_camera& c, const Camera& cam) {
+    memset(&c, 0, sizeof(c));
+    c.aspect_ratio = cam.aspect_ratio; c.image_width = cam.image_width; c.image_height = cam.image_height;
+    c.samples_per_pixel = cam.samples_per_pixel; c.pixel_samples_scale = cam.pixel_samples_scale;
+    c.sqrt_spp = cam.sqrt_spp; c.recip_sqrt_spp = cam.recip_sqrt_spp; c.bounce_limit = cam.bounce_limit;
+    c.vfov = cam.vfov; v3(c.background, cam.background);
+    c.light_obj_type = cam.light_obj_type; c.light_obj_idx = cam.light_obj_type == -1 ? 0 : cam.light_obj_idx;
+    v3(c.center, cam.center); v3(c.pixel00_loc, cam.pixel00_loc);
+    v3(c.pixel_delta_u, cam.pixel_delta_u); v3(c.pixel_delta_v, cam.pixel_delta_v);
+    v3(c.lookfrom, cam.lookfrom); v3(c.lookat, cam.lookat); v3(c.vup, cam.vup);
+    v3(c.v, cam.v); v3(c.u, cam.u); v3(c.w, cam.w);
+    c.defocus_angle = cam.defocus_angle; c.focus_dist = cam.focus_dist;
+    v3(c.defocus_disk_u, cam.defocus_disk_u); v3(c.defocus_disk_v, cam.defocus_disk_v);
+}
+
+static void dump_scene(const char* path, const world& w, const Camera& cam, const char* image_rgb_out) {
+    FILE* f = fopen(path, "wb");
+    if (!f) { perror(path); exit(2); }
+    const world_objects& o = w.objs; const world_materials& m = w.mats; const world_textures& t = w.texs;
+    mscn_header h; memset(&h, 0, sizeof(h));
+    h.magic = MSCN_MAGIC; h.version = MSCN_VERSION;
+    h.n_sphere = o.num_spheres; h.n_quad = o.num_quads; h.n_translate = o.num_translates;
+    h.n_rotate_y = o.num_rotate_y; h.n_medium = o.num_constant_medium; h.n_list = o.num_hittable_list;
+    h.n_bvh = o.num_bvh;
+    h.n_lambertian = m.num_lambertians; h.n_metal = m.num_metals; h.n_dielectric = m.num_dielectrics;
+    h.n_diffuse_light = m.num_diffuse_lights; h.n_isotropic = m.num_isotropics;
+    h.n_solid = t.num_solid_colors; h.n_checker = t.num_checker_textures; h.n_image = t.num_image_textures;
+    h.n_noise = t.num_noise_textures; h.bvh_mode = w.bvh_mode ? 1 : 0;
+    put(f, h);
+    for (int i = 0; i < o.num_spheres; i++) {
+        const sphere& s = o.host_sphere[i]; mscn_sphere d; memset(&d, 0, sizeof(d));
+        v3(d.center, s.center1); d.radius = s.radius; d.moves = s.moves ? 1 : 0;
+        if (s.moves) v3(d.center_vec, s.center_vec);   // uninitialised in the reference when !moves
+        d.mat_type = s.mat_type; d.mat_idx = s.mat_idx; d.skip = s.skip ? 1 : 0; bb(d.bbox, s.bbox);
+        put(f, d);
+    }
+    for (int i = 0; i < o.num_quads; i++) {
+        const quad& q = o.host_quad[i]; mscn_quad d; memset(&d, 0, sizeof(d));
+        v3(d.Q, q.Q); v3(d.u, q.u); v3(d.v, q.v); v3(d.normal, q.normal); v3(d.w, q.w);
+        d.D = q.D; d.area = q.area; d.mat_type = q.mat_type; d.mat_idx = q.mat_idx; d.skip = q.skip ? 1 : 0;
+        bb(d.bbox, q.bbox); put(f, d);
+    }
+    for (int i = 0; i < o.num_translates; i++) {
+        const translate& s = o.host_translate[i]; mscn_translate d; memset(&d, 0, sizeof(d));
+        d.obj_type = s.obj_type; d.obj_idx = s.obj_idx; v3(d.offset, s.offset); d.skip = s.skip ? 1 : 0; put(f, d);
+    }
+    for (int i = 0; i < o.num_rotate_y; i++) {
+        const rotate_y& s = o.host_rotate_y[i]; mscn_rotate_y d; memset(&d, 0, sizeof(d));
+        d.obj_type = s.obj_type; d.obj_idx = s.obj_idx; d.sin_theta = s.sin_theta; d.cos_theta = s.cos_theta;
+        d.skip = s.skip ? 1 : 0; put(f, d);
+    }
+    for (int i = 0; i < o.num_constant_medium; i++) {
+        const constant_medium& s = o.host_constant_medium[i]; mscn_medium d; memset(&d, 0, sizeof(d));
+        d.obj_type = s.obj_type; d.obj_idx = s.obj_idx; d.neg_inv_density = s.neg_inv_density;
+        d.mat_type = s.mat_type; d.mat_idx = s.mat_idx; d.skip = s.skip ? 1 : 0; put(f, d);
+    }
+    for (int i = 0; i < o.num_hittable_list; i++) {
+        const hittable_list& s = o.host_hittable_list[i];
+        int32_t skip = s.skip ? 1 : 0, num = s.num_objs; put(f, skip); put(f, num);
+        for (int k = 0; k < num; k++) { int32_t a = s.obj_types[k], b = s.obj_idxs[k]; put(f, a); put(f, b); }
+    }
+    for (int i = 0; i < o.num_bvh; i++) {
+        const bvh& s = o.host_bvh[i];
+        int32_t skip = s.skip ? 1 : 0, n = bvh_nodes(s); put(f, skip); put(f, n);
+        for (int k = 0; k < n; k++) {
+            mscn_bvh_node d; memset(&d, 0, sizeof(d));
+            d.left_type = s.left_children_types[k]; d.left_idx = s.left_children_idxs[k];
+            d.right_type = s.right_children_types[k]; d.right_idx = s.right_children_idxs[k];
+            d.is_internal = s.is_internal_node[k] ? 1 : 0; bb(d.bbox, s.bounding_boxes[k]); put(f, d);
+        }
+    }
+    for (int i = 0; i < m.num_lambertians; i++) { mscn_lambertian d = { m.host_lambertian[i].texType, m.host_lambertian[i].texIdx }; put(f, d); }
+    for (int i = 0; i < m.num_metals; i++) { mscn_metal d; v3(d.albedo, m.host_metal[i].albedo); d.fuzz = m.host_metal[i].fuzz; put(f, d); }
+    for (int i = 0; i < m.num_dielectrics; i++) { mscn_dielectric d; d.ior = m.host_dielectric[i].ior; d.inv_ior = m.host_dielectric[i].inv_ior; v3(d.albedo, m.host_dielectric[i].albedo); put(f, d); }
+    for (int i = 0; i < m.num_diffuse_lights; i++) { mscn_diffuse_light d = { m.host_diffuse_light[i].texType, m.host_diffuse_light[i].texIdx }; put(f, d); }
+    for (int i = 0; i < m.num_isotropics; i++) { mscn_isotropic d = { m.host_isotropic[i].texType, m.host_isotropic[i].texIdx }; put(f, d); }
+    for (int i = 0; i < t.num_solid_colors; i++) { mscn_solid d; v3(d.color, t.host_solid_color[i].color_value); put(f, d); }
+    for (int i = 0; i < t.num_checker_textures; i++) {
+        const checker_texture& c = t.host_checker_texture[i];
+        mscn_checker d = { c.inv_scale, c.evenTextureType, c.evenTextureIdx, c.oddTextureType, c.oddTextureIdx }; put(f, d);
+    }
+    for (int i = 0; i < t.num_image_textures; i++) {
+        const image_texture& c = t.host_image_texture[i];
+        mscn_image d; d.width = c.width; d.height = c.height; d.fnv1a = 0;
+        // The only image any scene names is imgs/earthmap.jpg (mort.cu:293,580); decode it again with the
+        // reference's vendored stb_image (img_loader.h:41) to fingerprint / export the texels it uploaded.
+        img_loader img("imgs/earthmap.jpg");
+        if (img.width() == c.width && img.height() == c.height && img.raw_data()) {
+            size_t nb = (size_t)c.width * c.height * 3;
+            d.fnv1a = fnv1a(img.raw_data(), nb);
+            if (image_rgb_out) {
+                FILE* g = fopen(image_rgb_out, "wb");
+                if (g) { fprintf(g, "P6\n%d %d\n255\n", c.width, c.height); fwrite(img.raw_data(), 1, nb, g); fclose(g); }
+            }
+        }
+        put(f, d);
+    }
+    for (int i = 0; i < t.num_noise_textures; i++) {
+        const noise_texture& c = t.host_noise_texture[i];
+        mscn_noise* d = (mscn_noise*)calloc(1, sizeof(mscn_noise));
+        d->scale = c.scale;
+        for (int k = 0; k < MORT_PERLIN_POINTS; k++) {
+            v3(d->ranvec[k], c.ranvec[k]); d->perm_x[k] = c.perm_x[k]; d->perm_y[k] = c.perm_y[k]; d->perm_z[k] = c.perm_z[k];
+        }
+        fwrite(d, sizeof(mscn_noise), 1, f); free(d);
+    }
+    mscn_camera c; fill_camera(c, cam); put(f, c);
+    fclose(f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// primary-hit parity: world::hit (media disabled) + brute-force primitive identification
+// ------------------------------------------------------------------------------------------------
+struct LeafDesc { int type, idx, top_type, top_idx, nops; int op_kind[4], op_idx[4]; };
+
+static void collect(std::vector<LeafDesc>& out, const world_objects& o, int type, int idx, LeafDesc chain, int depth = 0) {
+    if (depth > 8) return;
+    switch (type) {
+    case OBJ_SPHERE: case OBJ_QUAD: chain.type = type; chain.idx = idx; out.push_back(chain); break;
+    case OBJ_TRANSLATE:
+        if (chain.nops < 4) { chain.op_kind[chain.nops] = OBJ_TRANSLATE; chain.op_idx[chain.nops++] = idx; }
+        collect(out, o, o.host_translate[idx].obj_type, o.host_translate[idx].obj_idx, chain, depth + 1); break;
+    case OBJ_ROTATE_Y:
+        if (chain.nops < 4) { chain.op_kind[chain.nops] = OBJ_ROTATE_Y; chain.op_idx[chain.nops++] = idx; }
+        collect(out, o, o.host_rotate_y[idx].obj_type, o.host_rotate_y[idx].obj_idx, chain, depth + 1); break;
+    case OBJ_HITTABLE_LIST:
+        for (int k = 0; k < o.host_hittable_list[idx].num_objs; k++)
+            collect(out, o, o.host_hittable_list[idx].obj_types[k], o.host_hittable_list[idx].obj_idxs[k], chain, depth + 1);
+        break;
+    default: break;   // media are probed separately; a BVH cannot be a child in the reference (hitDispatch has no case 7)
+    }
+}
+
+// Leaves in the order world::hit visits them (world.cuh:110-168), so "last bit-equal t wins" reproduces
+// the reference's tie rule.
+static std::vector<LeafDesc> enumerate_leaves(const world& w) {
+    std::vector<LeafDesc> out; const world_objects& o = w.objs;
+    LeafDesc c; memset(&c, 0, sizeof(c));
+    for (int b = 0; b < o.num_bvh; b++) {
+        if (o.host_bvh[b].skip) continue;
+        const bvh& B = o.host_bvh[b]; int n = bvh_nodes(B);
+        c.top_type = OBJ_BVH; c.top_idx = b;
+        for (int k = 0; k < n; k++) if (!B.is_internal_node[k]) {
+            collect(out, o, B.left_children_types[k], B.left_children_idxs[k], c);
+            if (B.right_children_types[k] != B.left_children_types[k] || B.right_children_idxs[k] != B.left_children_idxs[k])
+                collect(out, o, B.right_children_types[k], B.right_children_idxs[k], c);
+        }
+    }
+    if (w.bvh_mode) return out;
+    for (int i = 0; i < o.num_spheres; i++) if (!o.host_sphere[i].skip) { c.top_type = OBJ_SPHERE; c.top_idx = i; collect(out, o, OBJ_SPHERE, i, c); }
+    for (int i = 0; i < o.num_quads; i++) if (!o.host_quad[i].skip) { c.top_type = OBJ_QUAD; c.top_idx = i; collect(out, o, OBJ_QUAD, i, c); }
+    for (int i = 0; i < o.num_translates; i++) if (!o.host_translate[i].skip) { c.top_type = OBJ_TRANSLATE; c.top_idx = i; collect(out, o, OBJ_TRANSLATE, i, c); }
+    for (int i = 0; i < o.num_rotate_y; i++) if (!o.host_rotate_y[i].skip) { c.top_type = OBJ_ROTATE_Y; c.top_idx = i; collect(out, o, OBJ_ROTATE_Y, i, c); }
+    for (int i = 0; i < o.num_hittable_list; i++) if (!o.host_hittable_list[i].skip) { c.top_type = OBJ_HITTABLE_LIST; c.top_idx = i; collect(out, o, OBJ_HITTABLE_LIST, i, c); }
+    return out;
+}
+
+__global__ void trace_kernel(world w_nomedia, int n_medium, const float* rays, int n, const LeafDesc* leaves, int n_leaves,
+                             mhit_record* out, mhit_medium_probe* probes, curandState* states) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = rays + 7 * (size_t)i;
+    ray r(point3(q[0], q[1], q[2]), vec3(q[3], q[4], q[5]), q[6]);
+
+    hit_record rec;
+    bool h = w_nomedia.hit(r, 0.001, INFINITY, rec, states, 0);   // same literals as camera.cuh:97
+
+    mhit_record o; memset(&o, 0, sizeof(o));
+    o.hit = h ? 1 : 0; o.leaf_type = o.leaf_idx = o.top_type = o.top_idx = -1;
+    if (h) {
+        o.t = rec.t; o.mat_type = rec.mat_type; o.mat_idx = rec.mat_idx; o.front_face = rec.front_face ? 1 : 0;
+        o.p[0] = rec.p.x(); o.p[1] = rec.p.y(); o.p[2] = rec.p.z();
+        o.normal[0] = rec.normal.x(); o.normal[1] = rec.normal.y(); o.normal[2] = rec.normal.z();
+        o.u = rec.u; o.v = rec.v;
+        int best = -1, last_exact = -1, n_exact = 0; float best_dt = CUDART_INF_F;
+        for (int l = 0; l < n_leaves; l++) {
+            LeafDesc L = leaves[l];
+            ray rr = r;
+            for (int k = 0; k < L.nops; k++) {
+                if (L.op_kind[k] == OBJ_TRANSLATE) {
+                    rr = ray(rr.origin() - dev_translate[L.op_idx[k]].offset, rr.direction(), rr.time());
+                } else {
+                    float s = dev_rotate_y[L.op_idx[k]].sin_theta, c = dev_rotate_y[L.op_idx[k]].cos_theta;
+                    point3 og = rr.origin(); vec3 dr = rr.direction();
+                    og[0] = c * rr.origin()[0] - s * rr.origin()[2];
+                    og[2] = s * rr.origin()[0] + c * rr.origin()[2];
+                    dr[0] = c * rr.direction()[0] - s * rr.direction()[2];
+                    dr[2] = s * rr.direction()[0] + c * rr.direction()[2];
+                    rr = ray(og, dr, rr.time());
+                }
+            }
+            hit_record tmp; bool hh;
+            if (L.type == OBJ_SPHERE) hh = dev_sphere[L.idx].hit(rr, 0.001, INFINITY, tmp);
+            else hh = dev_quad[L.idx].hit(rr, 0.001, INFINITY, tmp);
+            if (!hh) continue;
+            if (tmp.t == rec.t) { n_exact++; last_exact = l; }
+            float dt = fabsf(tmp.t - rec.t);
+            if (dt < best_dt) { best_dt = dt; best = l; }
+        }
+        int pick = last_exact >= 0 ? last_exact : best;
+        if (pick >= 0) {
+            o.leaf_type = leaves[pick].type; o.leaf_idx = leaves[pick].idx;
+            o.top_type = leaves[pick].top_type; o.top_idx = leaves[pick].top_idx;
+        }
+        if (last_exact < 0) o.flags |= 1;
+        if (n_exact > 1) o.flags |= 2;
+    }
+    out[i] = o;
+
+    // boundary probes of every constant_medium, exactly the two calls of objects.cuh:400-406
+    for (int m = 0; m < n_medium; m++) {
+        mhit_medium_probe p; p.hit1 = p.hit2 = 0; p.t1 = p.t2 = 0.f;
+        hit_record rec1, rec2;
+        if (hitDispatch(dev_constant_medium[m].obj_type, dev_constant_medium[m].obj_idx, r, -CUDART_INF_F, CUDART_INF_F, rec1, states, 0)) {
+            p.hit1 = 1; p.t1 = rec1.t;
+            if (hitDispatch(dev_constant_medium[m].obj_type, dev_constant_medium[m].obj_idx, r, rec1.t + 0.0001, CUDART_INF_F, rec2, states, 0)) {
+                p.hit2 = 1; p.t2 = rec2.t;
+            }
+        }
+        probes[(size_t)i * n_medium + m] = p;
+    }
+}
+
+// float accumulation of exactly the loop of Camera::render (camera.cuh:187-192), without the
+// NaN flush / gamma / quantisation of camera.cuh:194-207: xyz = sum over samples whose colour is
+// finite-or-inf in all channels, w = number of samples that produced a NaN in any channel.
+__global__ void hdr_kernel(Camera cam, float4* out, curandState* states, world data) {
+    int x = threadIdx.x + blockIdx.x * blockDim.x;
+    int y = threadIdx.y + blockIdx.y * blockDim.y;
+    int offset = x + y * cam.image_width;
+    if (x >= cam.image_width || y >= cam.image_height) return;
+    float sx = 0, sy = 0, sz = 0; int nan_n = 0;
+    for (int s_j = 0; s_j < cam.sqrt_spp; s_j++)
+        for (int s_i = 0; s_i < cam.sqrt_spp; s_i++) {
+            ray r = cam.get_ray(x, y, states, offset, s_i, s_j);
+            color c = cam.ray_color(r, states, offset, x, y, data);
+            if (c[0] != c[0] || c[1] != c[1] || c[2] != c[2]) nan_n++;
+            else { sx += c[0]; sy += c[1]; sz += c[2]; }
+        }
+    out[offset] = make_float4(sx, sy, sz, (float)nan_n);
+}
+
+// ------------------------------------------------------------------------------------------------
+static uint64_t sm64(uint64_t& s) { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+static float u01(uint64_t& s) { return (float)(sm64(s) >> 40) * (1.0f / 16777216.0f); }
+
+static void write_img(const char* path, int w, int h, int c, int dtype, const void* data, size_t bytes) {
+    FILE* f = fopen(path, "wb"); if (!f) { perror(path); exit(2); }
+    uint32_t hd[5] = { 0x474D494Du /* MIMG */, (uint32_t)w, (uint32_t)h, (uint32_t)c, (uint32_t)dtype };
+    fwrite(hd, 4, 5, f); fwrite(data, 1, bytes, f); fclose(f);
+}
+
+static void usage() {
+    fprintf(stderr,
+        "mort_ref --scene N [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
+        "         [--dump-scene out.mscn] [--dump-image-rgb out.ppm] [--img8 out.mimg] [--hdr out.mimg]\n"
+        "         [--trace-grid GW out.mhit] [--trace-random N SEED out.mhit] [--trace-file in.rays out.mhit]\n");
+}
+
+int main(int argc, char** argv) {
+    int scene = 0, width = 0, spp = 0, depth = 0, frames = 0, grid_w = 0, rnd_n = 0, host_only = 0;
+    float aspect = 0; unsigned long seed = 69420; uint64_t rnd_seed = 1;
+    const char *dump = 0, *dump_rgb = 0, *img8 = 0, *hdr = 0, *grid_out = 0, *rnd_out = 0, *file_in = 0, *file_out = 0;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto nx = [&]() { if (i + 1 >= argc) { usage(); exit(1); } return argv[++i]; };
+        if (a == "--scene") scene = atoi(nx()); else if (a == "--width") width = atoi(nx());
+        else if (a == "--aspect") aspect = (float)atof(nx()); else if (a == "--spp") spp = atoi(nx());
+        else if (a == "--depth") depth = atoi(nx()); else if (a == "--seed") seed = strtoul(nx(), 0, 10);
+        else if (a == "--frames") frames = atoi(nx()); else if (a == "--dump-scene") dump = nx();
+        else if (a == "--dump-image-rgb") dump_rgb = nx(); else if (a == "--img8") img8 = nx();
+        else if (a == "--hdr") hdr = nx();
+        else if (a == "--host-only") host_only = 1;   // dump the host-side scene and stop before any CUDA call (no GPU needed)
+        else if (a == "--trace-grid") { grid_w = atoi(nx()); grid_out = nx(); }
+        else if (a == "--trace-random") { rnd_n = atoi(nx()); rnd_seed = strtoull(nx(), 0, 10); rnd_out = nx(); }
+        else if (a == "--trace-file") { file_in = nx(); file_out = nx(); }
+        else { usage(); return 1; }
+    }
+    if (scene < 1) { usage(); return 1; }
+
+    Camera cam; world data;
+    switch (scene) {              // same dispatch as mort.cu:649-689
+        case 1: random_spheres(data, cam); break;
+        case 2: two_spheres(data, cam); break;
+        case 3: earth(data, cam); break;
+        case 4: two_perlin_spheres(data, cam); break;
+        case 5: quads(data, cam); break;
+        case 6: cornell_box(data, cam); break;
+        case 7: cornell_smoke(data, cam); break;
+        case 8: final_scene(data, cam, 800, 1000, 40); break;
+        case 9: final_scene(data, cam, 400, 250, 4); break;
+        case 10: out_of_order_spheres(data, cam, 35); break;
+        default: break;           // empty world, like the reference
+    }
+    if (width > 0) cam.image_width = width;
+    if (aspect > 0) cam.aspect_ratio = aspect;
+    if (spp > 0) cam.samples_per_pixel = spp;
+    if (depth > 0) cam.bounce_limit = depth;
+    cam.initialize();
+    if (host_only) { if (dump) dump_scene(dump, data, cam, dump_rgb); return 0; }
+    data.toDevice();
+
+    if (dump) dump_scene(dump, data, cam, dump_rgb);
+
+    const int W = cam.image_width, H = cam.image_height;
+    dim3 threads(16, 16), blocks((unsigned)ceil((float)W / 16.0), (unsigned)ceil((float)H / 16.0));
+    CK(cudaDeviceSetLimit(cudaLimitStackSize, 8192));                       // mort.cu:703
+    CK(cudaDeviceSetLimit(cudaLimitMallocHeapSize, (size_t)1 << 30));       // harness-side (A-Q15)
+
+    curandState* dev_states;
+    size_t n_states = (size_t)blocks.y * 16 * W + 16 * 16 + 16;            // padded (A-Q14)
+    CK(cudaMalloc((void**)&dev_states, n_states * sizeof(curandState)));
+    setup_rng<<<blocks, threads>>>(dev_states, seed, W);                     // mort.cu:709
+    CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+
+    size_t n_rec = (size_t)cam.bounce_limit * W * H;                         // mort.cu:712-725
+    CK(cudaMalloc((void**)&cam.recursionAttenuation, n_rec * sizeof(color)));
+    CK(cudaMalloc((void**)&cam.recursionEmission, n_rec * sizeof(color)));
+    CK(cudaMalloc((void**)&cam.recursionScatteringPdf, n_rec * sizeof(float)));
+    CK(cudaMalloc((void**)&cam.recursionPdf, n_rec * sizeof(float)));
+
+    printf("{\"harness\":\"mort_ref\",\"scene\":%d,\"width\":%d,\"height\":%d,\"spp\":%d,\"sqrt_spp\":%d,\"depth\":%d,"
+           "\"n_sphere\":%d,\"n_quad\":%d,\"n_translate\":%d,\"n_rotate_y\":%d,\"n_medium\":%d,\"n_list\":%d,\"n_bvh\":%d,"
+           "\"light\":[%d,%d],\"seed\":%lu}\n",
+           scene, W, H, cam.samples_per_pixel, cam.sqrt_spp, cam.bounce_limit, data.objs.num_spheres, data.objs.num_quads,
+           data.objs.num_translates, data.objs.num_rotate_y, data.objs.num_constant_medium, data.objs.num_hittable_list,
+           data.objs.num_bvh, cam.light_obj_type, cam.light_obj_type == -1 ? 0 : cam.light_obj_idx, seed);
+
+    // ---------------- timed frames: renderKernel exactly as mort.cu:96-114 ----------------
+    if (frames > 0 || img8) {
+        uchar4* dev_img; CK(cudaMalloc((void**)&dev_img, (size_t)W * H * sizeof(uchar4)));
+        CK(cudaMemset(dev_img, 0, (size_t)W * H * sizeof(uchar4)));
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        int nf = frames > 0 ? frames : 1;
+        std::vector<float> ms;
+        for (int fr = 0; fr < nf; fr++) {
+            CK(cudaEventRecord(e0, 0));
+            renderKernel<<<blocks, threads>>>(cam, dev_img, dev_states, data);
+            CK(cudaEventRecord(e1, 0)); CK(cudaEventSynchronize(e1));
+            CK(cudaGetLastError());
+            float t; CK(cudaEventElapsedTime(&t, e0, e1)); ms.push_back(t);
+        }
+        double samples = (double)W * H * cam.sqrt_spp * cam.sqrt_spp;
+        std::vector<float> timed(ms.begin() + (ms.size() > 1 ? 1 : 0), ms.end());   // frame 0 = warm-up when nf > 1
+        std::vector<float> srt = timed; std::sort(srt.begin(), srt.end());
+        double med = srt[srt.size() / 2], sum = 0; for (float v : timed) sum += v;
+        printf("{\"timing\":\"renderKernel\",\"scene\":%d,\"width\":%d,\"height\":%d,\"spp_eff\":%d,\"depth\":%d,\"frames_timed\":%zu,"
+               "\"ms_first\":%.3f,\"ms_median\":%.3f,\"ms_mean\":%.3f,\"samples_per_frame\":%.0f,\"msamples_per_s\":%.4f}\n",
+               scene, W, H, cam.sqrt_spp * cam.sqrt_spp, cam.bounce_limit, timed.size(), ms[0], med, sum / timed.size(),
+               samples, samples / (med * 1e3));
+        if (img8) {
+            std::vector<uchar4> hst((size_t)W * H);
+            CK(cudaMemcpy(hst.data(), dev_img, hst.size() * sizeof(uchar4), cudaMemcpyDeviceToHost));
+            write_img(img8, W, H, 4, 0, hst.data(), hst.size() * sizeof(uchar4));   // rows bottom-up, as the reference
+        }
+        CK(cudaFree(dev_img));
+    }
+
+    if (hdr) {
+        float4* dev_hdr; CK(cudaMalloc((void**)&dev_hdr, (size_t)W * H * sizeof(float4)));
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, 0));
+        hdr_kernel<<<blocks, threads>>>(cam, dev_hdr, dev_states, data);
+        CK(cudaEventRecord(e1, 0)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+        float t; CK(cudaEventElapsedTime(&t, e0, e1));
+        printf("{\"timing\":\"hdr_kernel\",\"scene\":%d,\"ms\":%.3f}\n", scene, t);
+        std::vector<float4> hst((size_t)W * H);
+        CK(cudaMemcpy(hst.data(), dev_hdr, hst.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        write_img(hdr, W, H, 4, 1, hst.data(), hst.size() * sizeof(float4));
+        CK(cudaFree(dev_hdr));
+    }
+
+    // ---------------- primary-hit dumps ----------------
+    for (int mode = 0; mode < 3; mode++) {
+        const char* outp = mode == 0 ? grid_out : mode == 1 ? rnd_out : file_out;
+        if (!outp) continue;
+        std::vector<float> rays;
+        if (mode == 0) {
+            // pixel-centre rays of a grid_w-wide image through this camera (camera.cuh:213-216 with offset 0), time 0.5
+            Camera g = cam; g.image_width = grid_w; g.initialize();
+            for (int j = 0; j < g.image_height; j++) for (int i = 0; i < g.image_width; i++) {
+                vec3 ps = g.pixel00_loc + ((float)i * g.pixel_delta_u) + ((float)j * g.pixel_delta_v);
+                vec3 d = ps - g.center;
+                float r7[7] = { g.center.x(), g.center.y(), g.center.z(), d.x(), d.y(), d.z(), 0.5f };
+                rays.insert(rays.end(), r7, r7 + 7);
+            }
+        } else if (mode == 1) {
+            // incoherent rays: origins uniform in the (10 % padded) bounds of all finite-size primitives,
+            // un-normalised directions (secondary rays are un-normalised in the reference), time in [0,1)
+            float lo[3] = { 1e30f, 1e30f, 1e30f }, hi[3] = { -1e30f, -1e30f, -1e30f };
+            auto grow = [&](const aabb& b) { float v[6]; bb(v, b); for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], v[2 * a]); hi[a] = std::max(hi[a], v[2 * a + 1]); } };
+            for (int i = 0; i < data.objs.num_spheres; i++) if (data.objs.host_sphere[i].radius < 900) grow(data.objs.host_sphere[i].bbox);
+            for (int i = 0; i < data.objs.num_quads; i++) grow(data.objs.host_quad[i].bbox);
+            if (lo[0] > hi[0]) for (int a = 0; a < 3; a++) { lo[a] = -10; hi[a] = 10; }
+            for (int a = 0; a < 3; a++) { float e = 0.1f * (hi[a] - lo[a]) + 0.5f; lo[a] -= e; hi[a] += e; }
+            uint64_t s = rnd_seed;
+            for (int i = 0; i < rnd_n; i++) {
+                float o[3], d[3], l2;
+                for (int a = 0; a < 3; a++) o[a] = lo[a] + (hi[a] - lo[a]) * u01(s);
+                do { for (int a = 0; a < 3; a++) d[a] = 2.f * u01(s) - 1.f; l2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]; } while (l2 >= 1.f || l2 < 1e-4f);
+                float sc = (0.5f + 1.5f * u01(s)) / sqrtf(l2);
+                float r7[7] = { o[0], o[1], o[2], d[0] * sc, d[1] * sc, d[2] * sc, u01(s) };
+                rays.insert(rays.end(), r7, r7 + 7);
+            }
+        } else {
+            FILE* f = fopen(file_in, "rb"); if (!f) { perror(file_in); return 2; }
+            fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+            rays.resize(sz / 4); if (fread(rays.data(), 4, rays.size(), f) != rays.size()) return 2; fclose(f);
+        }
+        int n = (int)(rays.size() / 7);
+        std::vector<LeafDesc> leaves = enumerate_leaves(data);
+        int nm = data.objs.num_constant_medium;
+        world nomedia = data; nomedia.objs.num_constant_medium = 0;
+        float* d_rays; LeafDesc* d_leaves; mhit_record* d_out; mhit_medium_probe* d_pr;
+        CK(cudaMalloc((void**)&d_rays, rays.size() * 4 + 4)); CK(cudaMemcpy(d_rays, rays.data(), rays.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&d_leaves, leaves.size() * sizeof(LeafDesc) + 4)); CK(cudaMemcpy(d_leaves, leaves.data(), leaves.size() * sizeof(LeafDesc), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&d_out, (size_t)n * sizeof(mhit_record) + 4));
+        CK(cudaMalloc((void**)&d_pr, (size_t)n * std::max(nm, 1) * sizeof(mhit_medium_probe)));
+        trace_kernel<<<(n + 127) / 128, 128>>>(nomedia, nm, d_rays, n, d_leaves, (int)leaves.size(), d_out, d_pr, dev_states);
+        CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+        std::vector<mhit_record> out(n); std::vector<mhit_medium_probe> pr((size_t)n * nm);
+        CK(cudaMemcpy(out.data(), d_out, (size_t)n * sizeof(mhit_record), cudaMemcpyDeviceToHost));
+        if (nm) CK(cudaMemcpy(pr.data(), d_pr, pr.size() * sizeof(mhit_medium_probe), cudaMemcpyDeviceToHost));
+        FILE* f = fopen(outp, "wb"); if (!f) { perror(outp); return 2; }
+        uint32_t hd[4] = { MHIT_MAGIC, (uint32_t)n, (uint32_t)nm, (uint32_t)leaves.size() };
+        fwrite(hd, 4, 4, f); fwrite(rays.data(), 4, rays.size(), f);
+        fwrite(out.data(), sizeof(mhit_record), n, f);
+        if (nm) fwrite(pr.data(), sizeof(mhit_medium_probe), pr.size(), f);
+        fclose(f);
+        int nh = 0, ninexact = 0, ntie = 0;
+        for (auto& r : out) { nh += r.hit; ninexact += (r.hit && (r.flags & 1)); ntie += (r.hit && (r.flags & 2)); }
+        printf("{\"trace\":\"%s\",\"scene\":%d,\"rays\":%d,\"hits\":%d,\"leaves\":%zu,\"inexact_t\":%d,\"equal_t_ties\":%d}\n",
+               mode == 0 ? "grid" : mode == 1 ? "random" : "file", scene, n, nh, leaves.size(), ninexact, ntie);
+        cudaFree(d_rays); cudaFree(d_leaves); cudaFree(d_out); cudaFree(d_pr);
+    }
+    return 0;
+}
