@@ -1,0 +1,143 @@
+/* mort_b200.h — C ABI of libmort_b200.so, the B200-native drop-in for the render path of lgleznah/mort.
+ *
+ * The reference has no FFI / plugin boundary: it is one translation unit whose observable surface is
+ *   (1) the scene-builder calls scene code makes          /root/reference/world.cuh:27-102, object / material /
+ *                                                          texture constructors (cited per function below)
+ *   (2) the Camera's public fields + initialize()         /root/reference/camera.cuh:12-84
+ *   (3) one render call per frame that fills an RGBA8      /root/reference/mort.cu:44-47,99-106;
+ *       bottom-up image                                    /root/reference/camera.cuh:178-208
+ *   (4) `mort <scene 1-10>`                                /root/reference/mort.cu:633-689
+ * Each entry point below replaces the piece of that surface it cites.  Plain pointers and sizes only; every
+ * call returns 0 on success or a negative mort_status, never exits the process (the reference exit()s on
+ * CUDA errors, /root/reference/include/book.h:21-30) and never falls back to the CPU: without a CUDA
+ * device mort_create fails.  A context is single-threaded, owns all device memory it allocates, and the
+ * caller owns every buffer it passes in.
+ *
+ * Handles are the reference's: (type tag, array slot) pairs (tags in include/mort_scene_format.h).
+ */
+#ifndef MORT_B200_H
+#define MORT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#include "mort_scene_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mort_ctx mort_ctx;
+typedef struct { int32_t type, idx; } mort_handle;
+
+enum mort_status {
+    MORT_OK = 0, MORT_ERR_ARG = -1, MORT_ERR_CUDA = -2, MORT_ERR_SCENE = -3, MORT_ERR_STATE = -4, MORT_ERR_IO = -5
+};
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+/* replaces main()'s implicit device 0 + cudaDeviceSetLimit (mort.cu:695-709) */
+int mort_create(int cuda_device, mort_ctx** out);
+int mort_destroy(mort_ctx* ctx);
+const char* mort_last_error(const mort_ctx* ctx);
+/* launches go to this cudaStream_t (default: the context's own stream).  Lets a host framework time or
+ * order the kernels on its current stream. */
+int mort_set_stream(mort_ctx* ctx, void* cuda_stream);
+
+/* ---- scenes ------------------------------------------------------------------------------------------- */
+/* the switch of mort.cu:649-689: scene_id 1..10 = the shipped scenes, anything else = empty world */
+int mort_build_scene(mort_ctx* ctx, int scene_id, const char* asset_dir);
+/* BASELINE.json config 4: scene-1 recipe over cells [-G,G)^2 (no reference counterpart: objects.cuh:746 caps at 1100) */
+int mort_build_sphere_field(mort_ctx* ctx, int G, uint64_t seed, int camera_kind);
+int mort_load_scene(mort_ctx* ctx, const char* mscn_path, const char* asset_dir);
+int mort_dump_scene(mort_ctx* ctx, const char* mscn_path);
+int mort_clear_scene(mort_ctx* ctx);                                        /* world::clear, world.cuh:92-96 */
+
+/* textures.cuh:20,42,79,164 + world.cuh:76-90 */
+int mort_add_solid(mort_ctx* ctx, float r, float g, float b, mort_handle* out);
+int mort_add_checker(mort_ctx* ctx, float scale, mort_handle even, mort_handle odd, mort_handle* out);
+int mort_add_image(mort_ctx* ctx, const uint8_t* rgb8_rows_top_down, int width, int height, mort_handle* out);
+int mort_add_noise(mort_ctx* ctx, float scale, mort_handle* out);           /* draws from the context's host rand() stream */
+/* materials.cuh:36,71,104-105,149,180 + world.cuh:56-74 */
+int mort_add_lambertian(mort_ctx* ctx, mort_handle tex, mort_handle* out);
+int mort_add_metal(mort_ctx* ctx, float r, float g, float b, float fuzz, mort_handle* out);
+int mort_add_dielectric(mort_ctx* ctx, float ior, mort_handle* out);
+int mort_add_diffuse_light(mort_ctx* ctx, mort_handle tex, mort_handle* out);
+int mort_add_isotropic(mort_ctx* ctx, mort_handle tex, mort_handle* out);
+/* objects.cuh:38,46,170,258,296,384,459-469,529 + world.cuh:27-54; skip = "reachable only through a parent" */
+int mort_add_sphere(mort_ctx* ctx, const float center[3], float radius, mort_handle mat, int skip, mort_handle* out);
+int mort_add_moving_sphere(mort_ctx* ctx, const float center0[3], const float center1[3], float radius, mort_handle mat, int skip, mort_handle* out);
+int mort_add_quad(mort_ctx* ctx, const float Q[3], const float u[3], const float v[3], mort_handle mat, int skip, mort_handle* out);
+int mort_add_translate(mort_ctx* ctx, mort_handle obj, const float offset[3], int skip, mort_handle* out);
+int mort_add_rotate_y(mort_ctx* ctx, mort_handle obj, float degrees, int skip, mort_handle* out);
+int mort_add_constant_medium(mort_ctx* ctx, mort_handle boundary, float density, mort_handle mat, int skip, mort_handle* out);
+int mort_add_list(mort_ctx* ctx, int skip, mort_handle* out);
+int mort_list_add(mort_ctx* ctx, mort_handle list, mort_handle obj);
+int mort_add_bvh(mort_ctx* ctx, mort_handle list, int skip, mort_handle* out);   /* marks the world bvh_mode (world.cuh:51-54) */
+int mort_add_box(mort_ctx* ctx, const float a[3], const float b[3], mort_handle mat);                                 /* utils.h:51-67 */
+int mort_add_rotated_box(mort_ctx* ctx, const float size[3], const float translation[3], float degrees, mort_handle mat, mort_handle* out);   /* utils.h:69-96 */
+/* rand() of the context's host stream (glibc TYPE_3, unseeded) for scene code that draws like mort.cu does */
+int mort_host_rand(mort_ctx* ctx);
+
+/* ---- camera (camera.cuh:12-84) ------------------------------------------------------------------------ */
+typedef struct {
+    float aspect_ratio; int32_t image_width, samples_per_pixel, bounce_limit, vfov;
+    float background[3]; float lookfrom[3], lookat[3], vup[3]; float defocus_angle, focus_dist;
+    int32_t light_obj_type, light_obj_idx;      /* light_obj_type = -1: no light sampling (mort.cu:215) */
+} mort_camera_desc;
+int mort_get_camera(mort_ctx* ctx, mort_camera_desc* out);
+int mort_set_camera(mort_ctx* ctx, const mort_camera_desc* desc);           /* runs Camera::initialize */
+/* the overrides BASELINE.json's configs need: <= 0 keeps the scene's value */
+int mort_override_camera(mort_ctx* ctx, int image_width, float aspect_ratio, int samples_per_pixel, int bounce_limit);
+int mort_get_camera_record(mort_ctx* ctx, mscn_camera* out);               /* every derived field, for parity checks */
+
+/* ---- commit = world::toDevice (world.cuh:98-102): flatten, SAH-build the 4-wide BVH, upload ------------ */
+int mort_commit(mort_ctx* ctx);
+
+/* ---- render (renderKernel, mort.cu:44-47,99-106; Camera::render, camera.cuh:178-208) ------------------- */
+enum { MORT_MODE_MEGAKERNEL = 0, MORT_MODE_WAVEFRONT = 1 };
+typedef struct {
+    uint32_t seed, frame;          /* Philox key; the reference's seed is 69420 (mort.cu:707) */
+    int32_t mode;                  /* MORT_MODE_* */
+    int32_t sample_mod, sample_rem;/* sample-split across GPUs: this call renders strata rows s_j % mod == rem (1,0 = all) */
+    int32_t stage_nodes;           /* BVH nodes staged in shared memory: -1 auto, 0 none, N first N (breadth-first) */
+    int32_t threads_per_block;     /* 0 = default */
+    int32_t blocks_per_sm;         /* 0 = default */
+    int32_t wavefront_paths;       /* paths in flight for the wavefront mode, 0 = default */
+    int32_t reserved[7];
+} mort_render_opts;
+void mort_default_render_opts(mort_render_opts* o);
+
+/* Accumulation image: W*H float4, rows bottom-up like the reference's frame (camera.cuh:70-78):
+ * xyz = sum of the sample colours (IEEE: a NaN sample poisons the channel exactly as in camera.cuh:190-198),
+ * w = number of samples that contained a NaN. */
+/* Device-resident frame: d_accum is a device pointer owned by the caller (e.g. a torch tensor). */
+int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts, void* d_accum);
+/* Tone pipeline of camera.cuh:194-207 on device: mean over n_samples, NaN flush, gamma 2, quantise to RGBA8
+ * (w=255).  d_rgba8 is a device pointer to W*H*4 bytes. */
+int mort_tonemap_device(mort_ctx* ctx, const void* d_accum, int samples_per_pixel_total, void* d_rgba8);
+/* Host-buffer frame (the reference-facing call): renders, tone-maps and copies back.  rgba8_out: W*H*4 bytes,
+ * bottom-up (may be NULL); accum_out: W*H*4 floats (may be NULL). */
+int mort_render(mort_ctx* ctx, const mort_render_opts* opts, uint8_t* rgba8_out, float* accum_out);
+
+/* ---- parity hook: closest hit of arbitrary rays (world::hit with the medium loop disabled) -------------- */
+enum { MORT_TRACE_BVH = 0, MORT_TRACE_BRUTE_FORCE = 1 };
+/* rays7: n x {ox,oy,oz,dx,dy,dz,time} (host).  out: n records (host).  probes: n * n_medium (host) or NULL. */
+int mort_trace(mort_ctx* ctx, const float* rays7, int n, mhit_record* out, mhit_medium_probe* probes, int flags);
+
+/* ---- stats -------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t width, height, sqrt_spp, bounce_limit;
+    int32_t n_leaves, n_spheres, n_quads, n_nodes, bvh_depth, n_media, n_instances, n_materials, n_textures;
+    double sah_cost, build_ms, upload_ms;
+    double last_render_ms;             /* CUDA-event time of the render kernels of the last mort_render* call */
+    uint64_t last_segments;            /* path segments (top-level closest-hit queries) of that call */
+    uint64_t last_samples;             /* camera paths of that call */
+    uint64_t last_kernel_launches;     /* kernels launched by that call */
+    int32_t sm_count, staged_nodes, threads_per_block, blocks_per_sm;
+    int32_t regs_per_thread, reserved0;
+    uint64_t device_bytes;
+} mort_stats;
+int mort_get_stats(mort_ctx* ctx, mort_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

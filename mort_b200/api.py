@@ -1,0 +1,291 @@
+"""ctypes host layer over libmort_b200.so (include/mort_b200.h).
+
+Mirrors the reference's scene-builder / camera / render surface (world.cuh:27-102, camera.cuh:12-84,
+mort.cu:633-689) one call per C-ABI entry.  There is no CPU rendering path: if the CUDA library is missing
+or no CUDA device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import formats as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmort_b200.so")
+ASSET_DIR = os.path.join(_HERE, "assets")
+
+MODE_MEGAKERNEL, MODE_WAVEFRONT = 0, 1
+TRACE_BVH, TRACE_BRUTE_FORCE = 0, 1
+
+
+class MortError(RuntimeError):
+    pass
+
+
+class Handle(C.Structure):
+    _fields_ = [("type", C.c_int32), ("idx", C.c_int32)]
+
+    def __iter__(self):
+        return iter((self.type, self.idx))
+
+    def __repr__(self):
+        return f"Handle({self.type},{self.idx})"
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [("aspect_ratio", C.c_float), ("image_width", C.c_int32), ("samples_per_pixel", C.c_int32),
+                ("bounce_limit", C.c_int32), ("vfov", C.c_int32), ("background", C.c_float * 3),
+                ("lookfrom", C.c_float * 3), ("lookat", C.c_float * 3), ("vup", C.c_float * 3),
+                ("defocus_angle", C.c_float), ("focus_dist", C.c_float),
+                ("light_obj_type", C.c_int32), ("light_obj_idx", C.c_int32)]
+
+
+class RenderOpts(C.Structure):
+    _fields_ = [("seed", C.c_uint32), ("frame", C.c_uint32), ("mode", C.c_int32), ("sample_mod", C.c_int32),
+                ("sample_rem", C.c_int32), ("stage_nodes", C.c_int32), ("threads_per_block", C.c_int32),
+                ("blocks_per_sm", C.c_int32), ("wavefront_paths", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("sqrt_spp", C.c_int32), ("bounce_limit", C.c_int32),
+                ("n_leaves", C.c_int32), ("n_spheres", C.c_int32), ("n_quads", C.c_int32), ("n_nodes", C.c_int32),
+                ("bvh_depth", C.c_int32), ("n_media", C.c_int32), ("n_instances", C.c_int32), ("n_materials", C.c_int32),
+                ("n_textures", C.c_int32),
+                ("sah_cost", C.c_double), ("build_ms", C.c_double), ("upload_ms", C.c_double), ("last_render_ms", C.c_double),
+                ("last_segments", C.c_uint64), ("last_samples", C.c_uint64), ("last_kernel_launches", C.c_uint64),
+                ("sm_count", C.c_int32), ("staged_nodes", C.c_int32), ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32),
+                ("regs_per_thread", C.c_int32), ("reserved0", C.c_int32), ("device_bytes", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/mort_b200.h declares (tests/test_abi.py checks the library exports all of them)
+ABI_SYMBOLS = [
+    "mort_create", "mort_destroy", "mort_last_error", "mort_set_stream",
+    "mort_build_scene", "mort_build_sphere_field", "mort_load_scene", "mort_dump_scene", "mort_clear_scene",
+    "mort_add_solid", "mort_add_checker", "mort_add_image", "mort_add_noise",
+    "mort_add_lambertian", "mort_add_metal", "mort_add_dielectric", "mort_add_diffuse_light", "mort_add_isotropic",
+    "mort_add_sphere", "mort_add_moving_sphere", "mort_add_quad", "mort_add_translate", "mort_add_rotate_y",
+    "mort_add_constant_medium", "mort_add_list", "mort_list_add", "mort_add_bvh", "mort_add_box", "mort_add_rotated_box",
+    "mort_host_rand",
+    "mort_get_camera", "mort_set_camera", "mort_override_camera", "mort_get_camera_record",
+    "mort_commit", "mort_default_render_opts", "mort_render_device", "mort_tonemap_device", "mort_render",
+    "mort_trace", "mort_get_stats",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libmort_b200.so; raises MortError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MortError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(mort_b200 has no CPU rendering path)")
+    L = C.CDLL(LIB_PATH)
+    P, H, I, Fl = C.c_void_p, Handle, C.c_int, C.c_float
+    HP, F3 = C.POINTER(Handle), C.POINTER(C.c_float)
+    sig = {
+        "mort_create": [I, C.POINTER(P)], "mort_destroy": [P], "mort_set_stream": [P, P],
+        "mort_build_scene": [P, I, C.c_char_p], "mort_build_sphere_field": [P, I, C.c_uint64, I],
+        "mort_load_scene": [P, C.c_char_p, C.c_char_p], "mort_dump_scene": [P, C.c_char_p], "mort_clear_scene": [P],
+        "mort_add_solid": [P, Fl, Fl, Fl, HP], "mort_add_checker": [P, Fl, H, H, HP], "mort_add_image": [P, P, I, I, HP],
+        "mort_add_noise": [P, Fl, HP], "mort_add_lambertian": [P, H, HP], "mort_add_metal": [P, Fl, Fl, Fl, Fl, HP],
+        "mort_add_dielectric": [P, Fl, HP], "mort_add_diffuse_light": [P, H, HP], "mort_add_isotropic": [P, H, HP],
+        "mort_add_sphere": [P, F3, Fl, H, I, HP], "mort_add_moving_sphere": [P, F3, F3, Fl, H, I, HP],
+        "mort_add_quad": [P, F3, F3, F3, H, I, HP], "mort_add_translate": [P, H, F3, I, HP], "mort_add_rotate_y": [P, H, Fl, I, HP],
+        "mort_add_constant_medium": [P, H, Fl, H, I, HP], "mort_add_list": [P, I, HP], "mort_list_add": [P, H, H],
+        "mort_add_bvh": [P, H, I, HP], "mort_add_box": [P, F3, F3, H], "mort_add_rotated_box": [P, F3, F3, Fl, H, HP],
+        "mort_host_rand": [P],
+        "mort_get_camera": [P, C.POINTER(CameraDesc)], "mort_set_camera": [P, C.POINTER(CameraDesc)],
+        "mort_override_camera": [P, I, Fl, I, I], "mort_get_camera_record": [P, P],
+        "mort_commit": [P], "mort_default_render_opts": [C.POINTER(RenderOpts)],
+        "mort_render_device": [P, C.POINTER(RenderOpts), P], "mort_tonemap_device": [P, P, I, P],
+        "mort_render": [P, C.POINTER(RenderOpts), P, P], "mort_trace": [P, P, I, P, P, I], "mort_get_stats": [P, C.POINTER(Stats)],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = None if name == "mort_default_render_opts" else C.c_int
+    L.mort_last_error.argtypes = [P]
+    L.mort_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+@dataclass
+class Frame:
+    """One rendered frame: `accum` (H, W, 4) float32 rows bottom-up — xyz = sum of sample colours, w = #NaN
+    samples — and `rgba8` (H, W, 4) uint8 exactly as the reference's frame buffer (camera.cuh:194-207)."""
+    accum: np.ndarray | None
+    rgba8: np.ndarray | None
+    stats: dict
+
+
+class Renderer:
+    """Owns one mort_ctx on one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.mort_create(int(device), C.byref(h))
+        if rc != 0 or not h:
+            raise MortError(f"mort_create(device={device}) failed with {rc}: a CUDA device is required (no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    # -- plumbing --
+    def _ck(self, rc):
+        if rc != 0:
+            raise MortError(f"{self._L.mort_last_error(self._h).decode()} (status {rc})")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mort_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self._L.mort_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    # -- scenes --
+    def build_scene(self, scene_id: int, asset_dir: str = ASSET_DIR):
+        self._ck(self._L.mort_build_scene(self._h, int(scene_id), asset_dir.encode()))
+        return self
+
+    def build_sphere_field(self, G: int, seed: int = 69420, camera_kind: int = 0):
+        self._ck(self._L.mort_build_sphere_field(self._h, int(G), int(seed), int(camera_kind)))
+        return self
+
+    def load_scene(self, path, asset_dir: str = ASSET_DIR):
+        self._ck(self._L.mort_load_scene(self._h, str(path).encode(), asset_dir.encode()))
+        return self
+
+    def dump_scene(self, path):
+        self._ck(self._L.mort_dump_scene(self._h, str(path).encode()))
+
+    def clear_scene(self):
+        self._ck(self._L.mort_clear_scene(self._h))
+
+    def _add(self, fn, *args):
+        out = Handle()
+        self._ck(fn(self._h, *args, C.byref(out)))
+        return out
+
+    def add_solid(self, r, g, b): return self._add(self._L.mort_add_solid, r, g, b)
+    def add_checker(self, scale, even, odd): return self._add(self._L.mort_add_checker, scale, even, odd)
+    def add_image(self, rgb: np.ndarray):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        return self._add(self._L.mort_add_image, rgb.ctypes.data, rgb.shape[1], rgb.shape[0])
+    def add_noise(self, scale): return self._add(self._L.mort_add_noise, scale)
+    def add_lambertian(self, tex): return self._add(self._L.mort_add_lambertian, tex)
+    def add_metal(self, r, g, b, fuzz): return self._add(self._L.mort_add_metal, r, g, b, fuzz)
+    def add_dielectric(self, ior): return self._add(self._L.mort_add_dielectric, ior)
+    def add_diffuse_light(self, tex): return self._add(self._L.mort_add_diffuse_light, tex)
+    def add_isotropic(self, tex): return self._add(self._L.mort_add_isotropic, tex)
+    def add_sphere(self, c, r, mat, skip=False): return self._add(self._L.mort_add_sphere, _f3(c), r, mat, int(skip))
+    def add_moving_sphere(self, c0, c1, r, mat, skip=False): return self._add(self._L.mort_add_moving_sphere, _f3(c0), _f3(c1), r, mat, int(skip))
+    def add_quad(self, Q, u, v, mat, skip=False): return self._add(self._L.mort_add_quad, _f3(Q), _f3(u), _f3(v), mat, int(skip))
+    def add_translate(self, obj, offset, skip=False): return self._add(self._L.mort_add_translate, obj, _f3(offset), int(skip))
+    def add_rotate_y(self, obj, degrees, skip=False): return self._add(self._L.mort_add_rotate_y, obj, degrees, int(skip))
+    def add_constant_medium(self, boundary, density, mat, skip=False): return self._add(self._L.mort_add_constant_medium, boundary, density, mat, int(skip))
+    def add_list(self, skip=False): return self._add(self._L.mort_add_list, int(skip))
+    def list_add(self, lst, obj): self._ck(self._L.mort_list_add(self._h, lst, obj))
+    def add_bvh(self, lst, skip=False): return self._add(self._L.mort_add_bvh, lst, int(skip))
+    def add_box(self, a, b, mat): self._ck(self._L.mort_add_box(self._h, _f3(a), _f3(b), mat))
+    def add_rotated_box(self, size, translation, degrees, mat): return self._add(self._L.mort_add_rotated_box, _f3(size), _f3(translation), degrees, mat)
+    def host_rand(self): return self._L.mort_host_rand(self._h)
+
+    # -- camera --
+    def get_camera(self) -> CameraDesc:
+        d = CameraDesc()
+        self._ck(self._L.mort_get_camera(self._h, C.byref(d)))
+        return d
+
+    def set_camera(self, desc: CameraDesc):
+        self._ck(self._L.mort_set_camera(self._h, C.byref(desc)))
+
+    def override_camera(self, width=0, aspect=0.0, spp=0, depth=0):
+        self._ck(self._L.mort_override_camera(self._h, int(width), float(aspect), int(spp), int(depth)))
+        return self
+
+    def camera_record(self):
+        c = np.zeros(1, dtype=F.camera_dt)
+        self._ck(self._L.mort_get_camera_record(self._h, c.ctypes.data))
+        return c[0]
+
+    def commit(self):
+        self._ck(self._L.mort_commit(self._h))
+        return self
+
+    # -- render --
+    def opts(self, **kw) -> RenderOpts:
+        o = RenderOpts()
+        self._L.mort_default_render_opts(C.byref(o))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    @property
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self._L.mort_get_stats(self._h, C.byref(s)))
+        return s.asdict()
+
+    def render(self, want_rgba8=True, want_accum=True, **opts) -> Frame:
+        """Host-buffer frame (mort_render): kernels + tone map + device->host copies."""
+        st = self.stats
+        H, W = st["height"], st["width"]
+        rgba = np.empty((H, W, 4), dtype=np.uint8) if want_rgba8 else None
+        acc = np.empty((H, W, 4), dtype=np.float32) if want_accum else None
+        o = self.opts(**opts)
+        self._ck(self._L.mort_render(self._h, C.byref(o), rgba.ctypes.data if rgba is not None else None,
+                                     acc.ctypes.data if acc is not None else None))
+        return Frame(acc, rgba, self.stats)
+
+    def render_into(self, host_rgba8_ptr: int, host_accum_ptr: int = 0, **opts):
+        o = self.opts(**opts)
+        self._ck(self._L.mort_render(self._h, C.byref(o), C.c_void_p(host_rgba8_ptr) if host_rgba8_ptr else None,
+                                     C.c_void_p(host_accum_ptr) if host_accum_ptr else None))
+
+    def render_device(self, d_accum_ptr: int, **opts):
+        """Device-resident frame into a caller-owned float4 buffer (e.g. a torch tensor's data_ptr())."""
+        o = self.opts(**opts)
+        self._ck(self._L.mort_render_device(self._h, C.byref(o), C.c_void_p(d_accum_ptr)))
+
+    def tonemap_device(self, d_accum_ptr: int, samples_per_pixel_total: int, d_rgba8_ptr: int):
+        self._ck(self._L.mort_tonemap_device(self._h, C.c_void_p(d_accum_ptr), int(samples_per_pixel_total), C.c_void_p(d_rgba8_ptr)))
+
+    # -- parity hook --
+    def trace(self, rays: np.ndarray, brute_force=False, want_probes=True):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 7)
+        n = rays.shape[0]
+        nm = self.stats["n_media"]
+        out = np.zeros(n, dtype=F.hit_dt)
+        probes = np.zeros((n, nm), dtype=F.probe_dt)
+        self._ck(self._L.mort_trace(self._h, rays.ctypes.data, n, out.ctypes.data,
+                                    probes.ctypes.data if (nm and want_probes) else None,
+                                    TRACE_BRUTE_FORCE if brute_force else TRACE_BVH))
+        return out, probes

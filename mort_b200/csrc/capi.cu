@@ -1,0 +1,376 @@
+// capi.cu — the C ABI of include/mort_b200.h: context, scene building, commit (flatten + SAH build +
+// upload), render / trace launches, statistics.  No CPU rendering path exists: every entry that produces
+// pixels or hits requires the CUDA device the context was created on.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "flatten.hpp"
+#include "mort_b200.h"
+#include "render.hpp"
+#include "scene.hpp"
+
+using namespace mort;
+
+namespace {
+
+struct DeviceArena {                 // every device allocation of one committed scene
+    std::vector<void*> ptrs; size_t bytes = 0;
+    template <class T> cudaError_t upload(const std::vector<T>& v, const T** out) {
+        *out = nullptr;
+        if (v.empty()) return cudaSuccess;
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, v.size() * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(p); bytes += v.size() * sizeof(T);
+        e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+        *out = reinterpret_cast<const T*>(p);
+        return e;
+    }
+    void release() { for (void* p : ptrs) cudaFree(p); ptrs.clear(); bytes = 0; }
+};
+
+}  // namespace
+
+struct mort_ctx {
+    int device = 0;
+    cudaDeviceProp prop;
+    Scene scene;
+    HostRng rng;
+    FlatScene flat;
+    bool committed = false;
+    DeviceArena arena;
+    DeviceScene dscene;
+    int32_t* d_mat_offsets = nullptr;
+    unsigned long long* d_counters = nullptr;     // [0] segments [1] samples
+    unsigned int* d_work = nullptr;
+    float4* d_accum = nullptr; size_t accum_pixels = 0;
+    uint8_t* d_rgba = nullptr; size_t rgba_pixels = 0;
+    WavefrontBuffers* wave = nullptr; int wave_paths = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    mort_stats stats;
+    double upload_ms = 0;
+};
+
+#define CTX_CHECK(c) do { if (!(c)) return MORT_ERR_ARG; } while (0)
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MORT_ERR_CUDA; } } while (0)
+
+static int fail(mort_ctx* ctx, int code, const std::string& m) { ctx->err = m; return code; }
+static Handle H(mort_handle h) { return Handle{h.type, h.idx}; }
+static void put(mort_handle* out, Handle h) { if (out) { out->type = h.type; out->idx = h.idx; } }
+static V3 v3(const float* p) { return V3(p[0], p[1], p[2]); }
+static void invalidate(mort_ctx* ctx) { ctx->committed = false; }
+
+extern "C" {
+
+int mort_create(int cuda_device, mort_ctx** out) {
+    if (!out) return MORT_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || cuda_device < 0 || cuda_device >= n) return MORT_ERR_CUDA;   // no CPU fallback
+    if (cudaSetDevice(cuda_device) != cudaSuccess) return MORT_ERR_CUDA;
+    mort_ctx* ctx = new mort_ctx();
+    ctx->device = cuda_device;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    memset(&ctx->dscene, 0, sizeof(ctx->dscene));
+    if (cudaGetDeviceProperties(&ctx->prop, cuda_device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_work, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_mat_offsets, 8 * sizeof(int32_t)) != cudaSuccess) {
+        delete ctx; return MORT_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return MORT_OK;
+}
+
+int mort_destroy(mort_ctx* ctx) {
+    CTX_CHECK(ctx);
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->arena.release();
+    wavefront_free(ctx->wave);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_mat_offsets); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgba);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return MORT_OK;
+}
+
+const char* mort_last_error(const mort_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mort_set_stream(mort_ctx* ctx, void* s) { CTX_CHECK(ctx); ctx->stream = s ? reinterpret_cast<cudaStream_t>(s) : ctx->own_stream; return MORT_OK; }
+
+// ---- scenes ---------------------------------------------------------------------------------------------
+int mort_build_scene(mort_ctx* ctx, int scene_id, const char* asset_dir) {
+    CTX_CHECK(ctx); invalidate(ctx);
+    if (!build_reference_scene(ctx->scene, scene_id, asset_dir ? asset_dir : ".")) return fail(ctx, MORT_ERR_SCENE, ctx->scene.error);
+    return MORT_OK;
+}
+int mort_build_sphere_field(mort_ctx* ctx, int G, uint64_t seed, int camera_kind) {
+    CTX_CHECK(ctx); invalidate(ctx);
+    if (!build_sphere_field(ctx->scene, G, seed, camera_kind)) return fail(ctx, MORT_ERR_SCENE, ctx->scene.error);
+    return MORT_OK;
+}
+int mort_load_scene(mort_ctx* ctx, const char* path, const char* asset_dir) {
+    CTX_CHECK(ctx && path); invalidate(ctx);
+    std::string e;
+    if (!ctx->scene.load(path, &e)) return fail(ctx, MORT_ERR_IO, e);
+    if (!ctx->scene.images.empty()) {
+        ImageRec im;
+        if (!asset_dir || !load_ppm(std::string(asset_dir) + "/earthmap.ppm", im)) return fail(ctx, MORT_ERR_IO, "scene names an image texture but earthmap.ppm was not found");
+        for (ImageRec& r : ctx->scene.images) if (r.width == im.width && r.height == im.height) r.rgb = im.rgb;
+    }
+    return MORT_OK;
+}
+int mort_dump_scene(mort_ctx* ctx, const char* path) { CTX_CHECK(ctx && path); return ctx->scene.dump(path) ? MORT_OK : fail(ctx, MORT_ERR_IO, std::string("cannot write ") + path); }
+int mort_clear_scene(mort_ctx* ctx) { CTX_CHECK(ctx); invalidate(ctx); ctx->scene.clear(); ctx->rng.reseed(1); return MORT_OK; }
+
+int mort_add_solid(mort_ctx* ctx, float r, float g, float b, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_solid(V3(r, g, b))); return MORT_OK; }
+int mort_add_checker(mort_ctx* ctx, float scale, mort_handle even, mort_handle odd, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_checker(scale, H(even), H(odd))); return MORT_OK; }
+int mort_add_image(mort_ctx* ctx, const uint8_t* rgb, int w, int h, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_image(rgb, w, h)); return MORT_OK; }
+int mort_add_noise(mort_ctx* ctx, float scale, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_noise(scale, ctx->rng)); return MORT_OK; }
+int mort_add_lambertian(mort_ctx* ctx, mort_handle tex, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_lambertian(H(tex))); return MORT_OK; }
+int mort_add_metal(mort_ctx* ctx, float r, float g, float b, float fuzz, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_metal(V3(r, g, b), fuzz)); return MORT_OK; }
+int mort_add_dielectric(mort_ctx* ctx, float ior, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_dielectric(ior)); return MORT_OK; }
+int mort_add_diffuse_light(mort_ctx* ctx, mort_handle tex, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_diffuse_light(H(tex))); return MORT_OK; }
+int mort_add_isotropic(mort_ctx* ctx, mort_handle tex, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_isotropic(H(tex))); return MORT_OK; }
+int mort_add_sphere(mort_ctx* ctx, const float c[3], float r, mort_handle mat, int skip, mort_handle* out) { CTX_CHECK(ctx && c); invalidate(ctx); put(out, ctx->scene.add_sphere(v3(c), r, H(mat), skip != 0)); return MORT_OK; }
+int mort_add_moving_sphere(mort_ctx* ctx, const float c0[3], const float c1[3], float r, mort_handle mat, int skip, mort_handle* out) { CTX_CHECK(ctx && c0 && c1); invalidate(ctx); put(out, ctx->scene.add_moving_sphere(v3(c0), v3(c1), r, H(mat), skip != 0)); return MORT_OK; }
+int mort_add_quad(mort_ctx* ctx, const float Q[3], const float u[3], const float v[3], mort_handle mat, int skip, mort_handle* out) { CTX_CHECK(ctx && Q && u && v); invalidate(ctx); put(out, ctx->scene.add_quad(v3(Q), v3(u), v3(v), H(mat), skip != 0)); return MORT_OK; }
+int mort_add_translate(mort_ctx* ctx, mort_handle obj, const float off[3], int skip, mort_handle* out) { CTX_CHECK(ctx && off); invalidate(ctx); put(out, ctx->scene.add_translate(H(obj), v3(off), skip != 0)); return MORT_OK; }
+int mort_add_rotate_y(mort_ctx* ctx, mort_handle obj, float deg, int skip, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_rotate_y(H(obj), deg, skip != 0)); return MORT_OK; }
+int mort_add_constant_medium(mort_ctx* ctx, mort_handle b, float density, mort_handle mat, int skip, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_constant_medium(H(b), density, H(mat), skip != 0)); return MORT_OK; }
+int mort_add_list(mort_ctx* ctx, int skip, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_list(skip != 0)); return MORT_OK; }
+int mort_list_add(mort_ctx* ctx, mort_handle list, mort_handle obj) { CTX_CHECK(ctx); invalidate(ctx); return ctx->scene.list_add(H(list), H(obj)) == 0 ? MORT_OK : fail(ctx, MORT_ERR_ARG, "mort_list_add: not a list handle"); }
+int mort_add_bvh(mort_ctx* ctx, mort_handle list, int skip, mort_handle* out) { CTX_CHECK(ctx); invalidate(ctx); put(out, ctx->scene.add_bvh(H(list), skip != 0)); return MORT_OK; }
+int mort_add_box(mort_ctx* ctx, const float a[3], const float b[3], mort_handle mat) { CTX_CHECK(ctx && a && b); invalidate(ctx); ctx->scene.box(v3(a), v3(b), H(mat)); return MORT_OK; }
+int mort_add_rotated_box(mort_ctx* ctx, const float size[3], const float tr[3], float deg, mort_handle mat, mort_handle* out) { CTX_CHECK(ctx && size && tr); invalidate(ctx); put(out, ctx->scene.rotated_box(v3(size), v3(tr), deg, H(mat))); return MORT_OK; }
+int mort_host_rand(mort_ctx* ctx) { return ctx ? ctx->rng.next() : 0; }
+
+// ---- camera ---------------------------------------------------------------------------------------------
+int mort_get_camera(mort_ctx* ctx, mort_camera_desc* o) {
+    CTX_CHECK(ctx && o);
+    const Camera& c = ctx->scene.cam;
+    o->aspect_ratio = c.aspect_ratio; o->image_width = c.image_width; o->samples_per_pixel = c.samples_per_pixel; o->bounce_limit = c.bounce_limit; o->vfov = c.vfov;
+    o->background[0] = c.background.x; o->background[1] = c.background.y; o->background[2] = c.background.z;
+    o->lookfrom[0] = c.lookfrom.x; o->lookfrom[1] = c.lookfrom.y; o->lookfrom[2] = c.lookfrom.z;
+    o->lookat[0] = c.lookat.x; o->lookat[1] = c.lookat.y; o->lookat[2] = c.lookat.z;
+    o->vup[0] = c.vup.x; o->vup[1] = c.vup.y; o->vup[2] = c.vup.z;
+    o->defocus_angle = c.defocus_angle; o->focus_dist = c.focus_dist; o->light_obj_type = c.light_obj_type; o->light_obj_idx = c.light_obj_idx;
+    return MORT_OK;
+}
+int mort_set_camera(mort_ctx* ctx, const mort_camera_desc* d) {
+    CTX_CHECK(ctx && d); invalidate(ctx);
+    if (d->image_width < 1 || !(d->aspect_ratio > 0) || d->samples_per_pixel < 1 || d->bounce_limit < 0) return fail(ctx, MORT_ERR_ARG, "mort_set_camera: bad width / aspect / spp / depth");
+    Camera& c = ctx->scene.cam;
+    c.aspect_ratio = d->aspect_ratio; c.image_width = d->image_width; c.samples_per_pixel = d->samples_per_pixel; c.bounce_limit = d->bounce_limit; c.vfov = d->vfov;
+    c.background = v3(d->background); c.lookfrom = v3(d->lookfrom); c.lookat = v3(d->lookat); c.vup = v3(d->vup);
+    c.defocus_angle = d->defocus_angle; c.focus_dist = d->focus_dist; c.light_obj_type = d->light_obj_type; c.light_obj_idx = d->light_obj_idx;
+    c.initialize();
+    return MORT_OK;
+}
+int mort_override_camera(mort_ctx* ctx, int w, float aspect, int spp, int depth) {
+    CTX_CHECK(ctx);
+    Camera& c = ctx->scene.cam;
+    if (w > 0) c.image_width = w;
+    if (aspect > 0) c.aspect_ratio = aspect;
+    if (spp > 0) c.samples_per_pixel = spp;
+    if (depth > 0) c.bounce_limit = depth;
+    c.initialize();
+    if (ctx->committed) camera_params(c, ctx->flat.cam);       // geometry untouched: no rebuild needed
+    return MORT_OK;
+}
+int mort_get_camera_record(mort_ctx* ctx, mscn_camera* out) { CTX_CHECK(ctx && out); ctx->scene.cam.to_record(*out); return MORT_OK; }
+
+// ---- commit ---------------------------------------------------------------------------------------------
+int mort_commit(mort_ctx* ctx) {
+    CTX_CHECK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    std::string e;
+    if (!flatten_scene(ctx->scene, ctx->flat, &e)) return fail(ctx, MORT_ERR_SCENE, e);
+    auto t0 = std::chrono::steady_clock::now();
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->arena.release();
+    DeviceScene d; memset(&d, 0, sizeof(d));
+    const FlatScene& f = ctx->flat;
+    CU(ctx->arena.upload(f.nodes, &d.nodes)); d.n_nodes = (int)f.nodes.size();
+    CU(ctx->arena.upload(f.spheres, &d.spheres)); CU(ctx->arena.upload(f.sphere_info, &d.sphere_info)); d.n_spheres = (int)f.spheres.size();
+    CU(ctx->arena.upload(f.quads, &d.quads)); d.n_quads = (int)f.quads.size();
+    CU(ctx->arena.upload(f.instances, &d.instances)); d.n_instances = (int)f.instances.size();
+    CU(ctx->arena.upload(f.materials, &d.materials)); d.n_materials = (int)f.materials.size();
+    CU(ctx->arena.upload(f.textures, &d.textures)); d.n_textures = (int)f.textures.size();
+    std::vector<ImageDesc> imgs;
+    for (const ImageRec& im : ctx->scene.images) {
+        ImageDesc I; I.texels = nullptr; I.width = im.width; I.height = im.height; I.cols = im.width * 3;
+        if (!im.rgb.empty()) CU(ctx->arena.upload(im.rgb, &I.texels));
+        imgs.push_back(I);
+    }
+    CU(ctx->arena.upload(imgs, &d.images)); d.n_images = (int)imgs.size();
+    CU(ctx->arena.upload(f.noises, &d.noises)); d.n_noises = (int)f.noises.size();
+    CU(ctx->arena.upload(f.media, &d.media)); d.n_media = (int)f.media.size();
+    CU(ctx->arena.upload(f.boundary, &d.boundary)); d.n_boundary = (int)f.boundary.size();
+    CU(ctx->arena.upload(f.lights, &d.lights)); d.n_lights = (int)f.lights.size(); d.light_kind = f.light_kind;
+    d.post_media_order = f.post_media_order; d.two_pass = f.two_pass; d.empty = f.empty;
+    ctx->dscene = d;
+    const Scene& s = ctx->scene;
+    int32_t off[8] = {0, 0, (int32_t)s.lambertians.size(), 0, 0, 0, 0, 0};
+    off[3] = off[2] + (int32_t)s.metals.size(); off[4] = off[3] + (int32_t)s.dielectrics.size(); off[5] = off[4] + (int32_t)s.lights.size();
+    CU(cudaMemcpy(ctx->d_mat_offsets, off, sizeof(off), cudaMemcpyHostToDevice));
+    ctx->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->committed = true;
+    return MORT_OK;
+}
+
+// ---- render ---------------------------------------------------------------------------------------------
+void mort_default_render_opts(mort_render_opts* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->seed = 69420; o->frame = 0; o->mode = MORT_MODE_MEGAKERNEL; o->sample_mod = 1; o->sample_rem = 0; o->stage_nodes = -1;
+}
+
+static int ensure_accum(mort_ctx* ctx, size_t npix) {
+    if (ctx->accum_pixels < npix) {
+        cudaFree(ctx->d_accum); ctx->d_accum = nullptr; ctx->accum_pixels = 0;
+        CU(cudaMalloc(&ctx->d_accum, npix * sizeof(float4))); ctx->accum_pixels = npix;
+    }
+    if (ctx->rgba_pixels < npix) {
+        cudaFree(ctx->d_rgba); ctx->d_rgba = nullptr; ctx->rgba_pixels = 0;
+        CU(cudaMalloc(&ctx->d_rgba, npix * 4)); ctx->rgba_pixels = npix;
+    }
+    return MORT_OK;
+}
+
+int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_accum) {
+    CTX_CHECK(ctx && d_accum);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "mort_render: scene not committed (call mort_commit)");
+    mort_render_opts o; if (opts_in) o = *opts_in; else mort_default_render_opts(&o);
+    CU(cudaSetDevice(ctx->device));
+    const CameraParams& cam = ctx->flat.cam;
+    if (o.sample_mod < 1 || o.sample_rem < 0 || o.sample_rem >= o.sample_mod) return fail(ctx, MORT_ERR_ARG, "mort_render: bad sample split");
+    FrameParams p; memset(&p, 0, sizeof(p));
+    p.sc = ctx->dscene; p.cam = cam; p.seed = o.seed; p.frame = o.frame; p.sj_mod = o.sample_mod; p.sj_rem = o.sample_rem;
+    p.n_rows = cam.sqrt_spp > o.sample_rem ? (cam.sqrt_spp - o.sample_rem + o.sample_mod - 1) / o.sample_mod : 0;
+    p.n_subset = p.n_rows * cam.sqrt_spp;
+    p.n_pixels = cam.width * cam.height;
+    int G = 1; while (G < 32 && G < p.n_subset) G <<= 1;
+    p.lanes_per_pixel = G;
+    p.accum = reinterpret_cast<float4*>(d_accum);
+    p.counters = ctx->d_counters; p.work_counter = ctx->d_work;
+
+    const int threads = o.threads_per_block > 0 ? (o.threads_per_block + 31) / 32 * 32 : 128;
+    if (threads > 128) return fail(ctx, MORT_ERR_ARG, "mort_render: at most 128 threads per block");
+    // staging: auto = every node if the whole tree fits in 96 KB per block, else none (decided by the ncu
+    // comparison in profiles/)
+    int n_staged = o.stage_nodes;
+    const int max_stage = (int)((ctx->prop.sharedMemPerBlockOptin > 2048 ? ctx->prop.sharedMemPerBlockOptin - 2048 : 0) / sizeof(Bvh4Node));
+    if (n_staged < 0) n_staged = 0;
+    n_staged = std::min(n_staged, std::min(max_stage, (int)ctx->flat.nodes.size()));
+    p.n_staged = n_staged;
+
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
+    uint64_t launches = 0;
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (o.mode == MORT_MODE_MEGAKERNEL) {
+        int occ = 0, regs = 0;
+        CU(mega_query(threads, n_staged, &occ, &regs));
+        if (occ < 1) return fail(ctx, MORT_ERR_CUDA, "megakernel does not fit on an SM with this configuration");
+        int bps = o.blocks_per_sm > 0 ? std::min(o.blocks_per_sm, occ) : occ;
+        LaunchShape sh; sh.threads = threads; sh.blocks = bps * ctx->prop.multiProcessorCount; sh.smem_bytes = n_staged * (int)sizeof(Bvh4Node);
+        CU(mega_launch(p, sh, ctx->stream));
+        launches = 1;
+        ctx->stats.threads_per_block = threads; ctx->stats.blocks_per_sm = bps; ctx->stats.regs_per_thread = regs; ctx->stats.staged_nodes = n_staged;
+    } else if (o.mode == MORT_MODE_WAVEFRONT) {
+        int n_paths = o.wavefront_paths > 0 ? o.wavefront_paths : 1 << 21;
+        if (!ctx->wave || ctx->wave_paths != n_paths) {
+            wavefront_free(ctx->wave); ctx->wave = nullptr;
+            CU(wavefront_alloc(&ctx->wave, n_paths)); ctx->wave_paths = n_paths;
+        }
+        CU(wavefront_render(p, ctx->wave, n_paths, ctx->prop.multiProcessorCount, ctx->stream, &launches));
+        ctx->stats.threads_per_block = 256; ctx->stats.blocks_per_sm = 0; ctx->stats.staged_nodes = 0;
+    } else return fail(ctx, MORT_ERR_ARG, "mort_render: unknown mode");
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    unsigned long long cnt[2] = {0, 0};
+    CU(cudaMemcpyAsync(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.last_render_ms = ms; ctx->stats.last_segments = cnt[0]; ctx->stats.last_samples = cnt[1]; ctx->stats.last_kernel_launches = launches;
+    return MORT_OK;
+}
+
+int mort_tonemap_device(mort_ctx* ctx, const void* d_accum, int spp_total, void* d_rgba8) {
+    CTX_CHECK(ctx && d_accum && d_rgba8);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "scene not committed");
+    if (spp_total < 1) return fail(ctx, MORT_ERR_ARG, "mort_tonemap_device: samples_per_pixel_total < 1");
+    const CameraParams& cam = ctx->flat.cam;
+    float scale = (float)(1.0 / (double)spp_total);                       // camera.cuh:52 for the full sample set
+    CU(tonemap_launch(reinterpret_cast<const float4*>(d_accum), cam.width * cam.height, scale, reinterpret_cast<uint8_t*>(d_rgba8), ctx->stream));
+    ctx->stats.last_kernel_launches += 1;
+    return MORT_OK;
+}
+
+int mort_render(mort_ctx* ctx, const mort_render_opts* opts, uint8_t* rgba8_out, float* accum_out) {
+    CTX_CHECK(ctx);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "mort_render: scene not committed (call mort_commit)");
+    const CameraParams& cam = ctx->flat.cam;
+    size_t npix = (size_t)cam.width * cam.height;
+    int rc = ensure_accum(ctx, npix);
+    if (rc != MORT_OK) return rc;
+    rc = mort_render_device(ctx, opts, ctx->d_accum);
+    if (rc != MORT_OK) return rc;
+    if (rgba8_out) {
+        rc = mort_tonemap_device(ctx, ctx->d_accum, cam.sqrt_spp * cam.sqrt_spp, ctx->d_rgba);
+        if (rc != MORT_OK) return rc;
+        CU(cudaMemcpyAsync(rgba8_out, ctx->d_rgba, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (accum_out) CU(cudaMemcpyAsync(accum_out, ctx->d_accum, npix * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MORT_OK;
+}
+
+// ---- parity hook ----------------------------------------------------------------------------------------
+int mort_trace(mort_ctx* ctx, const float* rays7, int n, mhit_record* out, mhit_medium_probe* probes, int flags) {
+    CTX_CHECK(ctx && (n == 0 || (rays7 && out)));
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "mort_trace: scene not committed");
+    if (n == 0) return MORT_OK;
+    CU(cudaSetDevice(ctx->device));
+    float* d_rays = nullptr; mhit_record* d_out = nullptr; mhit_medium_probe* d_pr = nullptr;
+    int nm = ctx->dscene.n_media;
+    cudaError_t e = cudaMalloc(&d_rays, (size_t)n * 28);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * sizeof(mhit_record));
+    if (e == cudaSuccess && probes && nm) e = cudaMalloc(&d_pr, (size_t)n * nm * sizeof(mhit_medium_probe));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays7, (size_t)n * 28, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = trace_launch(ctx->dscene, d_rays, n, d_out, d_pr, (flags & MORT_TRACE_BRUTE_FORCE) ? 1 : 0, ctx->d_mat_offsets, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(mhit_record), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && d_pr) e = cudaMemcpyAsync(probes, d_pr, (size_t)n * nm * sizeof(mhit_medium_probe), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_rays); cudaFree(d_out); cudaFree(d_pr);
+    if (e != cudaSuccess) return fail(ctx, MORT_ERR_CUDA, std::string("mort_trace: ") + cudaGetErrorString(e));
+    return MORT_OK;
+}
+
+// ---- stats ----------------------------------------------------------------------------------------------
+int mort_get_stats(mort_ctx* ctx, mort_stats* out) {
+    CTX_CHECK(ctx && out);
+    mort_stats& s = ctx->stats;
+    const Camera& c = ctx->scene.cam;
+    s.width = c.image_width; s.height = c.image_height; s.sqrt_spp = c.sqrt_spp; s.bounce_limit = c.bounce_limit;
+    const FlatScene& f = ctx->flat;
+    s.n_leaves = f.stats.n_leaves; s.n_spheres = (int)f.spheres.size(); s.n_quads = (int)f.quads.size(); s.n_nodes = f.stats.n_nodes; s.bvh_depth = f.stats.max_depth;
+    s.n_media = (int)f.media.size(); s.n_instances = (int)f.instances.size(); s.n_materials = (int)f.materials.size(); s.n_textures = (int)f.textures.size();
+    s.sah_cost = f.stats.sah_cost; s.build_ms = f.stats.build_ms; s.upload_ms = ctx->upload_ms;
+    s.sm_count = ctx->prop.multiProcessorCount; s.device_bytes = ctx->arena.bytes;
+    *out = s;
+    return MORT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// flatten.cpp — Scene (reference-shaped handles) -> FlatScene (device layout) — see flatten.hpp.
+#include "flatten.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+
+namespace mort {
+namespace {
+
+struct Chain { int n = 0; int kind[3]; int idx[3]; bool overflow = false;
+    bool operator<(const Chain& o) const {
+        if (n != o.n) return n < o.n;
+        for (int i = 0; i < n; i++) { if (kind[i] != o.kind[i]) return kind[i] < o.kind[i]; if (idx[i] != o.idx[i]) return idx[i] < o.idx[i]; }
+        return false;
+    } };
+
+struct Flattener {
+    const Scene& s; FlatScene& out; std::string err;
+    std::map<Chain, int> inst_ids;
+    Flattener(const Scene& sc, FlatScene& o) : s(sc), out(o) {}
+
+    int instance_of(const Chain& c) {
+        if (c.n == 0) return -1;
+        auto it = inst_ids.find(c);
+        if (it != inst_ids.end()) return it->second;
+        Instance I; memset(&I, 0, sizeof(I));
+        I.nops = c.n;
+        for (int k = 0; k < c.n; k++) {
+            if (c.kind[k] == MORT_OBJ_TRANSLATE) {
+                I.kind[k] = INST_OP_TRANSLATE;
+                for (int a = 0; a < 3; a++) I.a[k][a] = s.translates[c.idx[k]].offset[a];
+            } else {
+                I.kind[k] = INST_OP_ROTATE_Y;
+                I.a[k][0] = s.rotates[c.idx[k]].sin_theta; I.a[k][1] = s.rotates[c.idx[k]].cos_theta;
+            }
+        }
+        int id = (int)out.instances.size();
+        out.instances.push_back(I); inst_ids[c] = id;
+        return id;
+    }
+
+    // hitDispatch recursion (objects.cuh:858-887) unrolled into a list of leaves in visit order
+    template <class F> void collect(int type, int idx, Chain c, int depth, F&& emit) {
+        if (depth > 16) { err = "object nesting deeper than 16 levels (cycle?)"; return; }
+        switch (type) {
+            case MORT_OBJ_SPHERE:
+                if (idx < 0 || idx >= (int)s.spheres.size()) { err = "sphere handle out of range"; return; }
+                emit(type, idx, c); break;
+            case MORT_OBJ_QUAD:
+                if (idx < 0 || idx >= (int)s.quads.size()) { err = "quad handle out of range"; return; }
+                emit(type, idx, c); break;
+            case MORT_OBJ_TRANSLATE:
+                if (idx < 0 || idx >= (int)s.translates.size()) { err = "translate handle out of range"; return; }
+                if (c.n >= 3) { err = "more than 3 nested translate/rotate_y wrappers are not supported"; return; }
+                c.kind[c.n] = MORT_OBJ_TRANSLATE; c.idx[c.n++] = idx;
+                collect(s.translates[idx].obj_type, s.translates[idx].obj_idx, c, depth + 1, emit); break;
+            case MORT_OBJ_ROTATE_Y:
+                if (idx < 0 || idx >= (int)s.rotates.size()) { err = "rotate_y handle out of range"; return; }
+                if (c.n >= 3) { err = "more than 3 nested translate/rotate_y wrappers are not supported"; return; }
+                c.kind[c.n] = MORT_OBJ_ROTATE_Y; c.idx[c.n++] = idx;
+                collect(s.rotates[idx].obj_type, s.rotates[idx].obj_idx, c, depth + 1, emit); break;
+            case MORT_OBJ_HITTABLE_LIST:
+                if (idx < 0 || idx >= (int)s.lists.size()) { err = "list handle out of range"; return; }
+                for (const Handle& h : s.lists[idx].items) collect(h.type, h.idx, c, depth + 1, emit);
+                break;
+            case MORT_OBJ_CONSTANT_MEDIUM:
+                err = "constant_medium nested inside another object is not supported (only top-level media)"; return;
+            default: break;       // hitDispatch has no case for a BVH or unknown tags: never hit
+        }
+    }
+
+    // object space -> world space through an instance chain (outermost op first)
+    void to_world(const Chain& c, float p[3]) const {
+        for (int k = c.n - 1; k >= 0; k--) {
+            if (c.kind[k] == MORT_OBJ_TRANSLATE) { for (int a = 0; a < 3; a++) p[a] += s.translates[c.idx[k]].offset[a]; }
+            else {
+                float sn = s.rotates[c.idx[k]].sin_theta, cs = s.rotates[c.idx[k]].cos_theta;
+                float x = cs * p[0] + sn * p[2], z = -sn * p[0] + cs * p[2];
+                p[0] = x; p[2] = z;
+            }
+        }
+    }
+    void leaf_world_box(int type, int idx, const Chain& c, float lo[3], float hi[3]) const {
+        for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; }
+        auto grow = [&](const float* p, float r) { for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], p[a] - r); hi[a] = fmaxf(hi[a], p[a] + r); } };
+        if (type == MORT_OBJ_SPHERE) {
+            const mscn_sphere& sp = s.spheres[idx];
+            float c0[3] = {sp.center[0], sp.center[1], sp.center[2]};
+            float c1[3] = {sp.center[0] + sp.center_vec[0], sp.center[1] + sp.center_vec[1], sp.center[2] + sp.center_vec[2]};
+            to_world(c, c0); grow(c0, fabsf(sp.radius));
+            if (sp.moves) { to_world(c, c1); grow(c1, fabsf(sp.radius)); }
+        } else {
+            const mscn_quad& q = s.quads[idx];
+            for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) {
+                float p[3] = {q.Q[0] + i * q.u[0] + j * q.v[0], q.Q[1] + i * q.u[1] + j * q.v[1], q.Q[2] + i * q.u[2] + j * q.v[2]};
+                to_world(c, p); grow(p, 0.f);
+            }
+        }
+    }
+};
+
+int mat_gid(const Scene& s, int type, int idx) {
+    int off[6] = {0, 0, (int)s.lambertians.size(), 0, 0, 0};
+    off[3] = off[2] + (int)s.metals.size(); off[4] = off[3] + (int)s.dielectrics.size(); off[5] = off[4] + (int)s.lights.size();
+    int cnt[6] = {0, (int)s.lambertians.size(), (int)s.metals.size(), (int)s.dielectrics.size(), (int)s.lights.size(), (int)s.isotropics.size()};
+    if (type < 1 || type > 5 || idx < 0 || idx >= cnt[type]) return -1;   // scatterDispatch falls through: absorbs, no emission
+    return off[type] + idx;
+}
+int tex_gid(const Scene& s, int type, int idx) {
+    int cnt[5] = {0, (int)s.solids.size(), (int)s.checkers.size(), (int)s.images.size(), (int)s.noises.size()};
+    if (type < 1 || type > 4 || idx < 0 || idx >= cnt[type]) return -1;   // valueDispatch's magenta error texture
+    int off = 0;
+    for (int t = 1; t < type; t++) off += cnt[t];
+    return off + idx;
+}
+
+void fill_quad_rows(const mscn_quad& q, float a[5][4]) {
+    a[0][0] = q.normal[0]; a[0][1] = q.normal[1]; a[0][2] = q.normal[2]; a[0][3] = q.D;
+    for (int k = 0; k < 3; k++) { a[1][k] = q.Q[k]; a[2][k] = q.u[k]; a[3][k] = q.v[k]; a[4][k] = q.w[k]; }
+    a[1][3] = a[2][3] = a[3][3] = a[4][3] = 0;
+}
+
+}  // namespace
+
+void camera_params(const Camera& c, CameraParams& o) {
+    memset(&o, 0, sizeof(o));
+    auto p3 = [](float* d, V3 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; };
+    p3(o.center, c.center); p3(o.pixel00, c.pixel00_loc); p3(o.du, c.pixel_delta_u); p3(o.dv, c.pixel_delta_v);
+    p3(o.defocus_u, c.defocus_disk_u); p3(o.defocus_v, c.defocus_disk_v); p3(o.background, c.background);
+    o.defocus_angle = c.defocus_angle; o.recip_sqrt_spp = c.recip_sqrt_spp; o.pixel_samples_scale = c.pixel_samples_scale;
+    o.width = c.image_width; o.height = c.image_height; o.sqrt_spp = c.sqrt_spp; o.bounce_limit = c.bounce_limit;
+}
+
+bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
+    out = FlatScene();
+    Flattener F(s, out);
+    auto fail = [&](const std::string& m) { if (err) *err = m; return false; };
+
+    // ---- materials / textures: one running index each ----
+    for (const auto& m : s.lambertians) { Material d; memset(&d, 0, sizeof(d)); d.type = MORT_MAT_LAMBERTIAN; d.tex_gid = tex_gid(s, m.tex_type, m.tex_idx); out.materials.push_back(d); }
+    for (const auto& m : s.metals) { Material d; memset(&d, 0, sizeof(d)); d.type = MORT_MAT_METAL; d.tex_gid = -1; d.ax = m.albedo[0]; d.ay = m.albedo[1]; d.az = m.albedo[2]; d.p0 = m.fuzz; out.materials.push_back(d); }
+    for (const auto& m : s.dielectrics) { Material d; memset(&d, 0, sizeof(d)); d.type = MORT_MAT_DIELECTRIC; d.tex_gid = -1; d.ax = m.albedo[0]; d.ay = m.albedo[1]; d.az = m.albedo[2]; d.p0 = m.ior; d.p1 = m.inv_ior; out.materials.push_back(d); }
+    for (const auto& m : s.lights) { Material d; memset(&d, 0, sizeof(d)); d.type = MORT_MAT_DIFFUSE_LIGHT; d.tex_gid = tex_gid(s, m.tex_type, m.tex_idx); out.materials.push_back(d); }
+    for (const auto& m : s.isotropics) { Material d; memset(&d, 0, sizeof(d)); d.type = MORT_MAT_ISOTROPIC; d.tex_gid = tex_gid(s, m.tex_type, m.tex_idx); out.materials.push_back(d); }
+    for (const auto& t : s.solids) { Texture d; memset(&d, 0, sizeof(d)); d.type = MORT_TEX_SOLID; d.c0 = t.color[0]; d.c1 = t.color[1]; d.c2 = t.color[2]; out.textures.push_back(d); }
+    for (const auto& t : s.checkers) { Texture d; memset(&d, 0, sizeof(d)); d.type = MORT_TEX_CHECKER; d.c0 = t.inv_scale; d.even_gid = tex_gid(s, t.even_type, t.even_idx); d.odd_gid = tex_gid(s, t.odd_type, t.odd_idx); out.textures.push_back(d); }
+    for (size_t i = 0; i < s.images.size(); i++) { Texture d; memset(&d, 0, sizeof(d)); d.type = MORT_TEX_IMAGE; d.even_gid = (int)i; out.textures.push_back(d); }
+    for (size_t i = 0; i < s.noises.size(); i++) {
+        Texture d; memset(&d, 0, sizeof(d)); d.type = MORT_TEX_NOISE; d.even_gid = (int)i; out.textures.push_back(d);
+        NoiseTables n; memset(&n, 0, sizeof(n));
+        for (int k = 0; k < 256; k++) {
+            for (int a = 0; a < 3; a++) n.ranvec[k][a] = s.noises[i].ranvec[k][a];
+            n.perm_x[k] = (uint8_t)s.noises[i].perm_x[k]; n.perm_y[k] = (uint8_t)s.noises[i].perm_y[k]; n.perm_z[k] = (uint8_t)s.noises[i].perm_z[k];
+        }
+        n.scale = s.noises[i].scale;
+        out.noises.push_back(n);
+    }
+
+    // ---- visible leaves in world::hit order (world.cuh:110-168) ----
+    std::vector<Chain> chains;
+    int top_type = 0, top_idx = 0;
+    auto emit = [&](int type, int idx, const Chain& c) {
+        LeafRef L; L.type = type; L.idx = idx; L.inst = F.instance_of(c); L.order = (int)out.leaves.size(); L.top_type = top_type; L.top_idx = top_idx;
+        out.leaves.push_back(L); chains.push_back(c);
+    };
+    Chain none;
+    for (size_t b = 0; b < s.bvhs.size(); b++) {
+        if (s.bvhs[b].skip || s.bvhs[b].nodes.empty()) continue;
+        top_type = MORT_OBJ_BVH; top_idx = (int)b;
+        // depth-first, left before right: the order bvh::hit (objects.cuh:664-723) tests the leaves in
+        std::vector<int> stack; stack.push_back(0);
+        while (!stack.empty()) {
+            int n = stack.back(); stack.pop_back();
+            if (n < 0 || n >= (int)s.bvhs[b].nodes.size()) return fail("bvh node index out of range");
+            const mscn_bvh_node& nd = s.bvhs[b].nodes[n];
+            if (nd.is_internal) { stack.push_back(nd.right_idx); stack.push_back(nd.left_idx); }
+            else {
+                F.collect(nd.left_type, nd.left_idx, none, 0, emit);
+                if (nd.right_type != nd.left_type || nd.right_idx != nd.left_idx) F.collect(nd.right_type, nd.right_idx, none, 0, emit);
+            }
+        }
+    }
+    if (!s.bvh_mode) {                       // world.cuh:118-120: with a BVH in the world nothing else is visible
+        for (size_t i = 0; i < s.spheres.size(); i++) if (!s.spheres[i].skip) { top_type = MORT_OBJ_SPHERE; top_idx = (int)i; F.collect(MORT_OBJ_SPHERE, (int)i, none, 0, emit); }
+        for (size_t i = 0; i < s.quads.size(); i++) if (!s.quads[i].skip) { top_type = MORT_OBJ_QUAD; top_idx = (int)i; F.collect(MORT_OBJ_QUAD, (int)i, none, 0, emit); }
+        for (size_t i = 0; i < s.translates.size(); i++) if (!s.translates[i].skip) { top_type = MORT_OBJ_TRANSLATE; top_idx = (int)i; F.collect(MORT_OBJ_TRANSLATE, (int)i, none, 0, emit); }
+        for (size_t i = 0; i < s.rotates.size(); i++) if (!s.rotates[i].skip) { top_type = MORT_OBJ_ROTATE_Y; top_idx = (int)i; F.collect(MORT_OBJ_ROTATE_Y, (int)i, none, 0, emit); }
+        out.post_media_order = (int)out.leaves.size();
+        for (size_t i = 0; i < s.lists.size(); i++) if (!s.lists[i].skip) { top_type = MORT_OBJ_HITTABLE_LIST; top_idx = (int)i; F.collect(MORT_OBJ_HITTABLE_LIST, (int)i, none, 0, emit); }
+    } else {
+        out.post_media_order = (int)out.leaves.size();
+    }
+    if (!F.err.empty()) return fail(F.err);
+
+    // ---- media (only reachable at top level, and not at all in bvh_mode) ----
+    if (!s.bvh_mode)
+        for (size_t m = 0; m < s.media.size(); m++) {
+            if (s.media[m].skip) continue;
+            Medium M; memset(&M, 0, sizeof(M));
+            M.neg_inv_density = s.media[m].neg_inv_density; M.mat_gid = mat_gid(s, s.media[m].mat_type, s.media[m].mat_idx);
+            M.first = (int)out.boundary.size(); M.obj_idx = (int)m;
+            auto emit_b = [&](int type, int idx, const Chain& c) {
+                BoundaryPrim B; memset(&B, 0, sizeof(B));
+                B.type = type; B.inst = F.instance_of(c);
+                if (type == MORT_OBJ_SPHERE) {
+                    const mscn_sphere& sp = s.spheres[idx];
+                    B.a[0][0] = sp.center[0]; B.a[0][1] = sp.center[1]; B.a[0][2] = sp.center[2]; B.a[0][3] = sp.radius;
+                    if (sp.moves) { B.a[1][0] = sp.center_vec[0]; B.a[1][1] = sp.center_vec[1]; B.a[1][2] = sp.center_vec[2]; }
+                } else fill_quad_rows(s.quads[idx], B.a);
+                out.boundary.push_back(B);
+            };
+            F.collect(s.media[m].obj_type, s.media[m].obj_idx, none, 0, emit_b);
+            if (!F.err.empty()) return fail(F.err);
+            M.count = (int)out.boundary.size() - M.first;
+            out.media.push_back(M);
+        }
+    out.two_pass = (!out.media.empty() && out.post_media_order < (int)out.leaves.size()) ? 1 : 0;
+    out.empty = out.leaves.empty() ? 1 : 0;
+
+    // ---- light handle (camera.cuh:118-133, objects.cuh:947-979) ----
+    auto light_prim = [&](int type, int idx) {
+        LightPrim L; memset(&L, 0, sizeof(L)); L.kind = LIGHT_INVALID;
+        if (type == MORT_OBJ_SPHERE && idx >= 0 && idx < (int)s.spheres.size()) {
+            L.kind = LIGHT_SPHERE; const mscn_sphere& sp = s.spheres[idx];
+            L.a[0][0] = sp.center[0]; L.a[0][1] = sp.center[1]; L.a[0][2] = sp.center[2]; L.a[0][3] = sp.radius;
+        } else if (type == MORT_OBJ_QUAD && idx >= 0 && idx < (int)s.quads.size()) {
+            L.kind = LIGHT_QUAD; fill_quad_rows(s.quads[idx], L.a); L.area = s.quads[idx].area; L.D = s.quads[idx].D;
+        }
+        return L;
+    };
+    const Camera& cam = s.cam;
+    if (cam.light_obj_type == -1) out.light_kind = LIGHT_NONE;
+    else if (cam.light_obj_type == MORT_OBJ_SPHERE || cam.light_obj_type == MORT_OBJ_QUAD) {
+        LightPrim L = light_prim(cam.light_obj_type, cam.light_obj_idx);
+        out.light_kind = L.kind; out.lights.push_back(L);
+    } else if (cam.light_obj_type == MORT_OBJ_HITTABLE_LIST && cam.light_obj_idx >= 0 && cam.light_obj_idx < (int)s.lists.size()) {
+        out.light_kind = LIGHT_LIST;
+        for (const Handle& h : s.lists[cam.light_obj_idx].items) {
+            if (h.type == MORT_OBJ_HITTABLE_LIST) return fail("nested lists as light handles are not supported");
+            out.lights.push_back(light_prim(h.type, h.idx));
+        }
+        if (out.lights.empty()) return fail("light list is empty");
+    } else out.light_kind = LIGHT_INVALID;   // e.g. scene 7's (4,0): pdf 0, direction (1,0,0)
+
+    // ---- boxes, padding, SAH build ----
+    std::vector<BuildPrim> prims(out.leaves.size());
+    float M = 0;
+    for (int a = 0; a < 3; a++) M = fmaxf(M, fabsf(cam.center[a]));
+    for (size_t i = 0; i < out.leaves.size(); i++) {
+        BuildPrim& p = prims[i];
+        F.leaf_world_box(out.leaves[i].type, out.leaves[i].idx, chains[i], p.lo, p.hi);
+        p.type = out.leaves[i].type; p.ref = (int)i;
+        for (int a = 0; a < 3; a++) { M = fmaxf(M, fabsf(p.lo[a])); M = fmaxf(M, fabsf(p.hi[a])); }
+    }
+    // The slab test runs in float with one FMA per plane; its error is a few ulp of the largest coordinate
+    // in play.  Boxes are padded by 2e-6 * M so the BVH can never cull a hit the exact primitive test accepts
+    // (checked against brute force in tests/test_gpu_trace.py).
+    float pad = 2e-6f * M;
+    for (auto& p : prims) for (int a = 0; a < 3; a++) { p.lo[a] -= pad + 2e-6f * fabsf(p.lo[a]); p.hi[a] += pad + 2e-6f * fabsf(p.hi[a]); }
+    out.stats.pad = pad; out.stats.scene_extent = M; out.stats.n_leaves = (int)out.leaves.size();
+
+    std::vector<int> order;
+    build_bvh4(prims, out.nodes, order, out.stats);
+
+    // ---- emit primitive records in leaf order; rewrite leaf child words to per-type record indices ----
+    std::vector<int> rec_index(order.size());
+    for (size_t i = 0; i < order.size(); i++) {
+        const LeafRef& L = out.leaves[order[i]];
+        if (L.type == MORT_OBJ_SPHERE) {
+            const mscn_sphere& sp = s.spheres[L.idx];
+            SphereGeom g; g.cx = sp.center[0]; g.cy = sp.center[1]; g.cz = sp.center[2]; g.r = sp.radius;
+            g.vx = sp.moves ? sp.center_vec[0] : 0.f; g.vy = sp.moves ? sp.center_vec[1] : 0.f; g.vz = sp.moves ? sp.center_vec[2] : 0.f;
+            g.inst = L.inst;
+            PrimInfo pi; pi.mat_gid = mat_gid(s, sp.mat_type, sp.mat_idx); pi.obj_idx = L.idx; pi.order = L.order; pi.pad = (L.top_type << 24) | (L.top_idx & 0xFFFFFF);
+            rec_index[i] = (int)out.spheres.size();
+            out.spheres.push_back(g); out.sphere_info.push_back(pi);
+        } else {
+            const mscn_quad& q = s.quads[L.idx];
+            QuadRec r; memset(&r, 0, sizeof(r));
+            r.nx = q.normal[0]; r.ny = q.normal[1]; r.nz = q.normal[2]; r.D = q.D;
+            r.Qx = q.Q[0]; r.Qy = q.Q[1]; r.Qz = q.Q[2]; r.inst = L.inst;
+            r.ux = q.u[0]; r.uy = q.u[1]; r.uz = q.u[2]; r.mat_gid = mat_gid(s, q.mat_type, q.mat_idx);
+            r.vx = q.v[0]; r.vy = q.v[1]; r.vz = q.v[2]; r.order = L.order;
+            r.wx = q.w[0]; r.wy = q.w[1]; r.wz = q.w[2]; r.obj_idx = L.idx;
+            r.area = q.area; r.pad[0] = (L.top_type << 24) | (L.top_idx & 0xFFFFFF);
+            rec_index[i] = (int)out.quads.size();
+            out.quads.push_back(r);
+        }
+    }
+    for (Bvh4Node& n : out.nodes)
+        for (int k = 0; k < 4; k++) {
+            uint32_t w = n.child[k];
+            if (w == MORT_CHILD_EMPTY || !(w & MORT_LEAF_BIT)) continue;
+            uint32_t first = w & 0x07FFFFFFu;
+            n.child[k] = (w & ~0x07FFFFFFu) | (uint32_t)rec_index[first];
+        }
+    camera_params(s.cam, out.cam);
+    return true;
+}
+
+}  // namespace mort

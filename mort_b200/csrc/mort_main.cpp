@@ -1,0 +1,62 @@
+// mort_main.cpp — the `mort <scene 1-10>` entry point (mort.cu:633-689), headless: instead of opening a GLUT
+// window and re-rendering forever (gpu_anim.h, out of scope on a headless B200 box) it renders `--frames`
+// frames through the C ABI, prints the reference's "Avg. time per frame" line (mort.cu:116-119) and writes
+// the image as PPM (top-down; the frame itself is bottom-up like the reference's, camera.cuh:70-78).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mort_b200.h"
+
+static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
+                            "            [--mode mega|wave] [--stage N] [--assets DIR] [--out image.ppm] [--device K]\n"); return -1; }
+
+int main(int argc, char** argv) {
+    if (argc < 2) return usage();                       // mort.cu:638-641
+    int scene = atoi(argv[1]);
+    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = -1, mode = MORT_MODE_MEGAKERNEL;
+    float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out;
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i];
+        auto nx = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(-1); } return argv[++i]; };
+        if (a == "--width") width = atoi(nx()); else if (a == "--aspect") aspect = (float)atof(nx());
+        else if (a == "--spp") spp = atoi(nx()); else if (a == "--depth") depth = atoi(nx());
+        else if (a == "--seed") seed = (unsigned)strtoul(nx(), 0, 10); else if (a == "--frames") frames = atoi(nx());
+        else if (a == "--assets") assets = nx(); else if (a == "--out") out = nx(); else if (a == "--device") device = atoi(nx());
+        else if (a == "--stage") stage = atoi(nx());
+        else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : MORT_MODE_MEGAKERNEL; }
+        else return usage();
+    }
+    mort_ctx* ctx = nullptr;
+    if (mort_create(device, &ctx) != MORT_OK) { fprintf(stderr, "mort: no usable CUDA device %d (this renderer has no CPU path)\n", device); return 2; }
+    auto die = [&](const char* what) { fprintf(stderr, "mort: %s: %s\n", what, mort_last_error(ctx)); mort_destroy(ctx); return 3; };
+    if (mort_build_scene(ctx, scene, assets.c_str()) != MORT_OK) return die("scene");
+    if (mort_override_camera(ctx, width, aspect, spp, depth) != MORT_OK) return die("camera");
+    if (mort_commit(ctx) != MORT_OK) return die("commit");
+    mort_stats st; mort_get_stats(ctx, &st);
+    std::vector<uint8_t> img((size_t)st.width * st.height * 4);
+    mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.stage_nodes = stage;
+    double total = 0;
+    for (int f = 0; f < frames; f++) {
+        o.frame = (uint32_t)f;
+        if (mort_render(ctx, &o, img.data(), nullptr) != MORT_OK) return die("render");
+        mort_get_stats(ctx, &st);
+        total += st.last_render_ms;
+        printf("Avg. time per frame: %3.1f ms\n", total / (f + 1));
+    }
+    double samples = (double)st.width * st.height * st.sqrt_spp * st.sqrt_spp;
+    printf("{\"scene\":%d,\"width\":%d,\"height\":%d,\"spp_eff\":%d,\"depth\":%d,\"ms\":%.3f,\"msamples_per_s\":%.3f,\"mrays_per_s\":%.3f,\"nodes\":%d,\"leaves\":%d}\n",
+           scene, st.width, st.height, st.sqrt_spp * st.sqrt_spp, st.bounce_limit, st.last_render_ms, samples / (st.last_render_ms * 1e3),
+           (double)st.last_segments / (st.last_render_ms * 1e3), st.n_nodes, st.n_leaves);
+    if (!out.empty()) {
+        FILE* f = fopen(out.c_str(), "wb");
+        if (!f) { perror(out.c_str()); mort_destroy(ctx); return 4; }
+        fprintf(f, "P6\n%d %d\n255\n", st.width, st.height);
+        for (int y = st.height - 1; y >= 0; y--) for (int x = 0; x < st.width; x++) fwrite(&img[4 * ((size_t)y * st.width + x)], 1, 3, f);
+        fclose(f);
+    }
+    mort_destroy(ctx);
+    return 0;
+}

@@ -1,0 +1,44 @@
+// render.hpp — launch interface between the C ABI (capi.cu) and the CUDA kernels (render.cu, wavefront.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_types.h"
+#include "mort_scene_format.h"
+
+namespace mort {
+
+struct FrameParams {
+    DeviceScene sc;
+    CameraParams cam;
+    uint32_t seed, frame;
+    int32_t sj_mod, sj_rem;         // sample-split: strata rows s_j % sj_mod == sj_rem
+    int32_t n_rows;                 // strata rows this call renders
+    int32_t n_subset;               // samples per pixel this call renders = n_rows * sqrt_spp
+    int32_t lanes_per_pixel;        // power of two <= 32
+    int32_t n_pixels;
+    int32_t n_staged;               // BVH nodes copied to shared memory per block
+    float4* accum;                  // W*H
+    unsigned long long* counters;   // [0] segments, [1] samples
+    unsigned int* work_counter;     // persistent-warp work queue head
+};
+
+struct LaunchShape { int threads, blocks, smem_bytes; };
+
+// megakernel (render.cu)
+cudaError_t mega_query(int threads, int n_staged, int* max_blocks_per_sm, int* regs);
+cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, cudaStream_t st);
+
+// wavefront (wavefront.cu)
+struct WavefrontBuffers;            // opaque SoA queues
+cudaError_t wavefront_alloc(WavefrontBuffers** out, int n_paths);
+void wavefront_free(WavefrontBuffers* b);
+size_t wavefront_bytes(int n_paths);
+cudaError_t wavefront_render(const FrameParams& p, WavefrontBuffers* buf, int n_paths, int sm_count, cudaStream_t st, uint64_t* launches);
+
+// parity hook + tone pipeline (render.cu)
+cudaError_t trace_launch(const DeviceScene& sc, const float* d_rays, int n, mhit_record* d_out, mhit_medium_probe* d_probes,
+                         int brute_force, const int32_t* d_mat_offsets, cudaStream_t st);
+cudaError_t tonemap_launch(const float4* d_accum, int n_pixels, float scale, uint8_t* d_rgba8, cudaStream_t st);
+
+}  // namespace mort

@@ -1,0 +1,732 @@
+// rt_core.cuh — per-ray device code of mort-b200: Philox stream, exact primitive tests, 4-wide BVH
+// traversal, media, record reconstruction, materials / textures / PDFs and one path segment.
+//
+// Everything here is a MORT_HD inline function over plain structs: the CUDA kernels in render.cu are thin
+// schedulers (persistent warps, queues) around them.  The same header also compiles as ordinary C++
+// (tests/hostsim) — a development aid that lets traversal and shading be debugged against the oracle on a
+// machine without a GPU; it is not part of, nor reachable from, libmort_b200.so.
+//
+// Parity-critical arithmetic (anything that decides WHICH primitive a ray hits and at what t) is written
+// with explicit single-rounding intrinsics in the contraction pattern the reference's device code compiles
+// to (SURVEY.md §7 "hard parts"), so nvcc can neither fuse nor reorder it:
+//   sphere::hit objects.cuh:60-88 · quad::hit objects.cuh:190-215 · translate / rotate_y objects.cuh:268-366
+// Shading arithmetic uses ordinary operators.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "device_types.h"
+#include "mort_scene_format.h"
+
+#if defined(__CUDACC__)
+#define MORT_HD __host__ __device__ __forceinline__
+#define MORT_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define MORT_HD inline
+#define MORT_HD_NOINLINE inline
+#endif
+
+namespace mort {
+
+// ---------------------------------------------------------------------------------------------------
+// exact single-rounding ops + vector loads
+// ---------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+MORT_HD float xfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+MORT_HD float xmul(float a, float b) { return __fmul_rn(a, b); }
+MORT_HD float xadd(float a, float b) { return __fadd_rn(a, b); }
+MORT_HD float xsub(float a, float b) { return __fsub_rn(a, b); }
+MORT_HD float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+MORT_HD float xsqrt(float a) { return __fsqrt_rn(a); }
+struct F4 { float x, y, z, w; };
+MORT_HD F4 ld4(const void* p) { float4 v = __ldg(reinterpret_cast<const float4*>(p)); F4 r = {v.x, v.y, v.z, v.w}; return r; }
+MORT_HD uint32_t ldu8(const uint8_t* p) { return __ldg(p); }
+MORT_HD int f2i_bits(float f) { return __float_as_int(f); }
+MORT_HD float i2f_bits(int i) { return __int_as_float(i); }
+#else
+MORT_HD float xfma(float a, float b, float c) { return fmaf(a, b, c); }    // host build uses -ffp-contract=off
+MORT_HD float xmul(float a, float b) { return a * b; }
+MORT_HD float xadd(float a, float b) { return a + b; }
+MORT_HD float xsub(float a, float b) { return a - b; }
+MORT_HD float xdiv(float a, float b) { return a / b; }
+MORT_HD float xsqrt(float a) { return sqrtf(a); }
+struct F4 { float x, y, z, w; };
+MORT_HD F4 ld4(const void* p) { return *reinterpret_cast<const F4*>(p); }
+MORT_HD uint32_t ldu8(const uint8_t* p) { return *p; }
+MORT_HD int f2i_bits(float f) { int i; memcpy(&i, &f, 4); return i; }
+MORT_HD float i2f_bits(int i) { float f; memcpy(&f, &i, 4); return f; }
+#endif
+
+struct f3 { float x, y, z; };
+MORT_HD f3 mk3(float x, float y, float z) { f3 r = {x, y, z}; return r; }
+MORT_HD f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+MORT_HD f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+MORT_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+MORT_HD f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+MORT_HD f3 operator*(float t, f3 a) { return mk3(t * a.x, t * a.y, t * a.z); }
+MORT_HD float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+MORT_HD float len2(f3 a) { return dot3(a, a); }
+MORT_HD f3 cross3(f3 u, f3 v) { return mk3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x); }
+MORT_HD f3 unit3(f3 a) { float r = 1.0f / sqrtf(len2(a)); return r * a; }     // vec3.cuh:133-136: (1/len) * v
+MORT_HD bool isnan3(f3 a) { return a.x != a.x || a.y != a.y || a.z != a.z; }
+// exact forms (reference contraction: e2*f2 fused last, first product fused onto the plain middle one)
+MORT_HD float xdot(f3 a, f3 b) { return xfma(a.z, b.z, xfma(a.x, b.x, xmul(a.y, b.y))); }
+MORT_HD f3 xsub3(f3 a, f3 b) { return mk3(xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)); }
+MORT_HD f3 xadd3(f3 a, f3 b) { return mk3(xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)); }
+MORT_HD f3 xat(f3 o, f3 d, float t) { return mk3(xfma(t, d.x, o.x), xfma(t, d.y, o.y), xfma(t, d.z, o.z)); }
+MORT_HD f3 xcross(f3 u, f3 v) {
+    return mk3(xfma(u.y, v.z, -xmul(u.z, v.y)), xfma(u.z, v.x, -xmul(u.x, v.z)), xfma(u.x, v.y, -xmul(u.y, v.x)));
+}
+
+struct Ray { f3 o, d; float tm; };
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10, canonical stream: key = (seed, frame), counter = (pixel, sample, block, 0);
+// uniforms u = (x >> 8) * 2^-24 consumed in program order (identical to oracle/mort_oracle.c).
+// ---------------------------------------------------------------------------------------------------
+struct Rng { uint32_t k0, k1, pixel, sample, block; uint32_t buf[4]; int have; };
+
+MORT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#if defined(__CUDA_ARCH__)
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+MORT_HD void rng_init(Rng& g, uint32_t seed, uint32_t frame, uint32_t pixel, uint32_t sample) {
+    g.k0 = seed; g.k1 = frame; g.pixel = pixel; g.sample = sample; g.block = 0; g.have = 0;
+}
+MORT_HD float rnd(Rng& g) {
+    if (g.have == 0) { philox4x32_10(g.pixel, g.sample, g.block, 0u, g.k0, g.k1, g.buf); g.block++; g.have = 4; }
+    uint32_t x = g.have == 4 ? g.buf[0] : (g.have == 3 ? g.buf[1] : (g.have == 2 ? g.buf[2] : g.buf[3]));
+    g.have--;
+    return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+MORT_HD float rnd_range(Rng& g, float lo, float hi) { return rnd(g) * (hi - lo) + lo; }          // rng.cuh:25-28
+MORT_HD int rnd_int(Rng& g, int lo, int hi) {                                                    // rng.cuh:30-42
+    float r = 1.0f - rnd(g);
+    r = (float)((double)r * (hi - lo + 0.999999));
+    r += (float)lo;
+    return (int)truncf(r);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// instance transforms (objects.cuh:268-278, 334-366)
+// ---------------------------------------------------------------------------------------------------
+MORT_HD void ray_to_object(const Instance* insts, int inst, f3& o, f3& d) {
+    if (inst < 0) return;
+    const Instance* I = insts + inst;
+    F4 hd = ld4(I);                                       // nops, kind[0..2]
+    int nops = f2i_bits(hd.x);
+    for (int k = 0; k < nops; k++) {
+        int kind = f2i_bits(k == 0 ? hd.y : (k == 1 ? hd.z : hd.w));
+        F4 a = ld4(&I->a[k][0]);
+        if (kind == INST_OP_TRANSLATE) { o = xsub3(o, mk3(a.x, a.y, a.z)); }
+        else {
+            float s = a.x, c = a.y;
+            float ox = xfma(c, o.x, -xmul(s, o.z)), oz = xfma(s, o.x, xmul(c, o.z));
+            float dx = xfma(c, d.x, -xmul(s, d.z)), dz = xfma(s, d.x, xmul(c, d.z));
+            o.x = ox; o.z = oz; d.x = dx; d.z = dz;
+        }
+    }
+}
+MORT_HD void record_to_world(const Instance* insts, int inst, f3& p, f3& n) {
+    if (inst < 0) return;
+    const Instance* I = insts + inst;
+    F4 hd = ld4(I);
+    int nops = f2i_bits(hd.x);
+    for (int k = nops - 1; k >= 0; k--) {
+        int kind = f2i_bits(k == 0 ? hd.y : (k == 1 ? hd.z : hd.w));
+        F4 a = ld4(&I->a[k][0]);
+        if (kind == INST_OP_TRANSLATE) { p = xadd3(p, mk3(a.x, a.y, a.z)); }
+        else {
+            float s = a.x, c = a.y;
+            float px = xfma(c, p.x, xmul(s, p.z)), pz = xfma(c, p.z, -xmul(s, p.x));   // -s*x + c*z compiles as c*z - s*x
+            float nx = xfma(c, n.x, xmul(s, n.z)), nz = xfma(c, n.z, -xmul(s, n.x));
+            p.x = px; p.z = pz; n.x = nx; n.z = nz;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact primitive tests.  Both return the reference's t for the interval test the reference applies
+// (sphere: reject root < tmin || tmax < root; quad: reject t < tmin || t > tmax) or a negative "miss" flag.
+// ---------------------------------------------------------------------------------------------------
+MORT_HD bool sphere_test(f3 c, float r, f3 vel, f3 o, f3 d, float tm, float tmin, float tmax, float& t_out) {
+    f3 cen = mk3(xfma(tm, vel.x, c.x), xfma(tm, vel.y, c.y), xfma(tm, vel.z, c.z));
+    f3 oc = xsub3(o, cen);
+    float a = xdot(d, d);
+    float half_b = xdot(oc, d);
+    float cc = xfma(-r, r, xdot(oc, oc));
+    float disc = xfma(half_b, half_b, -xmul(a, cc));
+    if (disc < 0) return false;
+    float sq = xsqrt(disc);
+    float root = xdiv(xsub(-half_b, sq), a);
+    if (root < tmin || tmax < root) {
+        root = xdiv(xadd(-half_b, sq), a);
+        if (root < tmin || tmax < root) return false;
+    }
+    t_out = root;
+    return true;
+}
+MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3 d, float tmin, float tmax, float& t_out, float& alpha, float& beta) {
+    f3 n = mk3(nD.x, nD.y, nD.z);
+    float denom = xdot(n, d);
+    if (fabsf(denom) <= 1e-8f) return false;          // == ((double)fabsf(denom) < 1e-8): 1e-8f is the largest float below 1e-8
+    float t = xdiv(xsub(nD.w, xdot(n, o)), denom);
+    if (t < tmin || t > tmax) return false;
+    F4 Q = ld4(rec), U = ld4(rec + 4), Vv = ld4(rec + 8), W = ld4(rec + 12);
+    f3 P = xat(o, d, t);
+    f3 hp = xsub3(P, mk3(Q.x, Q.y, Q.z));
+    f3 w = mk3(W.x, W.y, W.z);
+    float al = xdot(w, xcross(hp, mk3(Vv.x, Vv.y, Vv.z)));
+    float be = xdot(w, xcross(mk3(U.x, U.y, U.z), hp));
+    if ((al < 0) || (al > 1) || (be < 0) || (be > 1)) return false;
+    t_out = t; alpha = al; beta = be;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// closest hit over the 4-wide BVH
+// ---------------------------------------------------------------------------------------------------
+#define MORT_STACK 48
+#define MORT_PRIM_NONE 0xFFFFFFFFu
+
+struct Hit { float t; uint32_t prim; float a, b; };      // prim = leaf-word type bits | record index ; (a,b) = quad alpha/beta
+
+MORT_HD int prim_order(const DeviceScene& sc, uint32_t prim) {
+    uint32_t i = prim & 0x07FFFFFFu;
+    if (prim & MORT_LEAF_QUAD_BIT) { F4 v = ld4(reinterpret_cast<const float*>(sc.quads + i) + 12); return f2i_bits(v.w); }
+    F4 v = ld4(sc.sphere_info + i); return f2i_bits(v.z);
+}
+
+// Candidate acceptance = the reference's sequential rule restated order-independently: nearest t wins; on
+// bit-equal t the primitive the reference visits LATER wins (App. A-Q3).  order_lo/order_hi restrict the
+// candidates to a visit-order window (used only when media and top-level lists coexist).
+MORT_HD void consider(const DeviceScene& sc, Hit& best, float t, uint32_t prim, float a, float b, int order_lo, int order_hi) {
+    if (order_lo > 0 || order_hi < 0x7FFFFFFF) { int o = prim_order(sc, prim); if (o < order_lo || o >= order_hi) return; }
+    if (t == best.t && best.prim != MORT_PRIM_NONE) { if (prim_order(sc, prim) < prim_order(sc, best.prim)) return; }
+    best.t = t; best.prim = prim; best.a = a; best.b = b;
+}
+
+MORT_HD void leaf_intersect(const DeviceScene& sc, uint32_t w, const Ray& r, float tmin, Hit& best, int order_lo, int order_hi) {
+    uint32_t first = w & 0x07FFFFFFu; int count = (int)((w >> 27) & 7u) + 1;
+    if (w & MORT_LEAF_QUAD_BIT) {
+        for (int i = 0; i < count; i++) {
+            const float* q = reinterpret_cast<const float*>(sc.quads + first + i);
+            F4 nD = ld4(q); F4 Qi = ld4(q + 4);
+            f3 o = r.o, d = r.d;
+            ray_to_object(sc.instances, f2i_bits(Qi.w), o, d);
+            float t, al, be;
+            if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be))
+                consider(sc, best, t, MORT_LEAF_BIT | MORT_LEAF_QUAD_BIT | (first + i), al, be, order_lo, order_hi);
+        }
+    } else {
+        for (int i = 0; i < count; i++) {
+            const float* s = reinterpret_cast<const float*>(sc.spheres + first + i);
+            F4 c = ld4(s), v = ld4(s + 4);
+            f3 o = r.o, d = r.d;
+            ray_to_object(sc.instances, f2i_bits(v.w), o, d);
+            float t;
+            if (sphere_test(mk3(c.x, c.y, c.z), c.w, mk3(v.x, v.y, v.z), o, d, r.tm, tmin, best.t, t))
+                consider(sc, best, t, MORT_LEAF_BIT | (first + i), 0.f, 0.f, order_lo, order_hi);
+        }
+    }
+}
+
+MORT_HD float safe_rcp_dir(float d) {
+    // axis-parallel rays: keep the slab arithmetic finite (inf * 0 would make NaN); 1e-20 tilts the ray by
+    // far less than the box padding
+    float a = fabsf(d) < 1e-20f ? (d < 0 ? -1e-20f : 1e-20f) : d;
+    return 1.0f / a;
+}
+
+// kStaged: the first n_staged nodes (breadth-first prefix = top levels) are read from a shared-memory copy,
+// the rest from global memory, through generic 128-bit loads; otherwise every node is a read-only LDG.128.
+template <bool kStaged>
+MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, const Ray& r, float tmin, float tmax, Hit& best,
+                         int order_lo = 0, int order_hi = 0x7FFFFFFF) {
+    best.t = tmax; best.prim = MORT_PRIM_NONE; best.a = best.b = 0.f;
+    if (sc.empty) return false;
+    const float idx = safe_rcp_dir(r.d.x), idy = safe_rcp_dir(r.d.y), idz = safe_rcp_dir(r.d.z);
+    const float oix = r.o.x * idx, oiy = r.o.y * idy, oiz = r.o.z * idz;
+    uint32_t stack_c[MORT_STACK]; float stack_t[MORT_STACK];
+    int sp = 0;
+    uint32_t cur = 0;
+    for (;;) {
+        if (!(cur & MORT_LEAF_BIT)) {
+            F4 lx, ly, lz, hx, hy, hz, chf;
+#if defined(__CUDA_ARCH__)
+            if (kStaged) {
+                // generic 128-bit loads: the pointer may be shared or global
+                const float4* n4 = reinterpret_cast<const float4*>(((int)cur < n_staged ? staged : sc.nodes) + cur);
+                float4 a0 = n4[0], a1 = n4[1], a2 = n4[2], a3 = n4[3], a4 = n4[4], a5 = n4[5], a6 = n4[6];
+                lx = F4{a0.x, a0.y, a0.z, a0.w}; ly = F4{a1.x, a1.y, a1.z, a1.w}; lz = F4{a2.x, a2.y, a2.z, a2.w};
+                hx = F4{a3.x, a3.y, a3.z, a3.w}; hy = F4{a4.x, a4.y, a4.z, a4.w}; hz = F4{a5.x, a5.y, a5.z, a5.w}; chf = F4{a6.x, a6.y, a6.z, a6.w};
+            } else
+#endif
+            {
+                const float* n = reinterpret_cast<const float*>(sc.nodes + cur);
+                lx = ld4(n); ly = ld4(n + 4); lz = ld4(n + 8); hx = ld4(n + 12); hy = ld4(n + 16); hz = ld4(n + 20); chf = ld4(n + 24);
+            }
+            struct { uint32_t x, y, z, w; } ch = {(uint32_t)f2i_bits(chf.x), (uint32_t)f2i_bits(chf.y), (uint32_t)f2i_bits(chf.z), (uint32_t)f2i_bits(chf.w)};
+            (void)staged; (void)n_staged;
+            float tn[4]; uint32_t cw[4] = {ch.x, ch.y, ch.z, ch.w};
+            const float lxa[4] = {lx.x, lx.y, lx.z, lx.w}, lya[4] = {ly.x, ly.y, ly.z, ly.w}, lza[4] = {lz.x, lz.y, lz.z, lz.w};
+            const float hxa[4] = {hx.x, hx.y, hx.z, hx.w}, hya[4] = {hy.x, hy.y, hy.z, hy.w}, hza[4] = {hz.x, hz.y, hz.z, hz.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float t0x = fmaf(lxa[k], idx, -oix), t1x = fmaf(hxa[k], idx, -oix);
+                float t0y = fmaf(lya[k], idy, -oiy), t1y = fmaf(hya[k], idy, -oiy);
+                float t0z = fmaf(lza[k], idz, -oiz), t1z = fmaf(hza[k], idz, -oiz);
+                float tnear = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+                float tfar = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
+                bool h = (tnear <= tfar) && (cw[k] != MORT_CHILD_EMPTY);
+                tn[k] = h ? tnear : INFINITY;
+                if (!h) cw[k] = MORT_CHILD_EMPTY;
+            }
+            // sort the 4 (tn, child) pairs ascending: 5-comparator network
+#define MORT_CSWAP(i, j) { if (tn[j] < tn[i]) { float tt = tn[i]; tn[i] = tn[j]; tn[j] = tt; uint32_t cc = cw[i]; cw[i] = cw[j]; cw[j] = cc; } }
+            MORT_CSWAP(0, 1) MORT_CSWAP(2, 3) MORT_CSWAP(0, 2) MORT_CSWAP(1, 3) MORT_CSWAP(1, 2)
+#undef MORT_CSWAP
+            // misses carry EMPTY + inf and sort to the back; push far-to-near, continue with the nearest
+#pragma unroll
+            for (int k = 3; k >= 1; k--)
+                if (cw[k] != MORT_CHILD_EMPTY && sp < MORT_STACK) { stack_c[sp] = cw[k]; stack_t[sp] = tn[k]; sp++; }
+            if (cw[0] != MORT_CHILD_EMPTY) { cur = cw[0]; continue; }
+        } else {
+            leaf_intersect(sc, cur, r, tmin, best, order_lo, order_hi);
+        }
+        // pop; entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit
+        bool found = false;
+        while (sp > 0) { sp--; if (stack_t[sp] <= best.t) { cur = stack_c[sp]; found = true; break; } }
+        if (!found) break;
+    }
+    return best.prim != MORT_PRIM_NONE;
+}
+
+// brute force over every leaf record (validation only: mort_trace(..., MORT_TRACE_BRUTE_FORCE))
+MORT_HD bool closest_hit_brute(const DeviceScene& sc, const Ray& r, float tmin, float tmax, Hit& best) {
+    best.t = tmax; best.prim = MORT_PRIM_NONE; best.a = best.b = 0.f;
+    for (int i = 0; i < sc.n_spheres; i++) leaf_intersect(sc, MORT_LEAF_BIT | (uint32_t)i, r, tmin, best, 0, 0x7FFFFFFF);
+    for (int i = 0; i < sc.n_quads; i++) leaf_intersect(sc, MORT_LEAF_BIT | MORT_LEAF_QUAD_BIT | (uint32_t)i, r, tmin, best, 0, 0x7FFFFFFF);
+    return best.prim != MORT_PRIM_NONE;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// hit record (hit_record.cuh) reconstructed once for the winning primitive
+// ---------------------------------------------------------------------------------------------------
+struct Record {
+    f3 p, normal; float t, u, v; int mat_gid; bool front_face;
+    int leaf_type, leaf_idx;      // reference (type, slot) of the primitive
+    bool sphere_uv;               // u,v still to be derived from the outward normal (only image textures need them)
+    f3 outward;                   // sphere outward normal in object space (for compute_uv)
+};
+
+MORT_HD void sphere_uv(f3 p, float& u, float& v) {                                   // objects.cuh:101-108
+    float theta = acosf(-p.y);
+    float phi = (float)((double)atan2f(-p.z, p.x) + 3.141592565);
+    u = (float)((double)phi / (2.0 * 3.141592565));
+    v = (float)((double)theta / 3.141592565);
+}
+
+MORT_HD void resolve_hit(const DeviceScene& sc, const Ray& r, const Hit& h, Record& rec) {
+    uint32_t i = h.prim & 0x07FFFFFFu;
+    f3 o = r.o, d = r.d;
+    rec.t = h.t;
+    if (h.prim & MORT_LEAF_QUAD_BIT) {
+        const float* q = reinterpret_cast<const float*>(sc.quads + i);
+        F4 nD = ld4(q), Qi = ld4(q + 4), U = ld4(q + 8), Vv = ld4(q + 12), W = ld4(q + 16);
+        int inst = f2i_bits(Qi.w);
+        ray_to_object(sc.instances, inst, o, d);
+        f3 n = mk3(nD.x, nD.y, nD.z);
+        rec.p = xat(o, d, h.t);
+        rec.front_face = xdot(d, n) < 0;
+        rec.normal = rec.front_face ? n : -n;
+        rec.u = h.a; rec.v = h.b; rec.sphere_uv = false;
+        rec.mat_gid = f2i_bits(U.w); rec.leaf_type = MORT_OBJ_QUAD; rec.leaf_idx = f2i_bits(W.w);
+        (void)Vv;
+        record_to_world(sc.instances, inst, rec.p, rec.normal);
+    } else {
+        const float* s = reinterpret_cast<const float*>(sc.spheres + i);
+        F4 c = ld4(s), v = ld4(s + 4), info = ld4(sc.sphere_info + i);
+        int inst = f2i_bits(v.w);
+        ray_to_object(sc.instances, inst, o, d);
+        f3 cen = mk3(xfma(r.tm, v.x, c.x), xfma(r.tm, v.y, c.y), xfma(r.tm, v.z, c.z));
+        rec.p = xat(o, d, h.t);
+        float rr = xdiv(1.0f, c.w);
+        f3 pc = xsub3(rec.p, cen);
+        f3 outward = mk3(xmul(rr, pc.x), xmul(rr, pc.y), xmul(rr, pc.z));
+        rec.front_face = xdot(d, outward) < 0;
+        rec.normal = rec.front_face ? outward : -outward;
+        rec.outward = outward; rec.sphere_uv = true; rec.u = rec.v = 0.f;
+        rec.mat_gid = f2i_bits(info.x); rec.leaf_type = MORT_OBJ_SPHERE; rec.leaf_idx = f2i_bits(info.y);
+        record_to_world(sc.instances, inst, rec.p, rec.normal);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// constant_medium (objects.cuh:396-434): boundary probes by linear scan in the reference's order
+// ---------------------------------------------------------------------------------------------------
+MORT_HD bool boundary_probe(const DeviceScene& sc, const Medium& m, const Ray& r, float tmin, float tmax, float& t_hit) {
+    bool any = false; float closest = tmax;
+    for (int k = 0; k < m.count; k++) {
+        const BoundaryPrim* B = sc.boundary + m.first + k;
+        F4 hd = ld4(B);
+        f3 o = r.o, d = r.d;
+        ray_to_object(sc.instances, f2i_bits(hd.y), o, d);
+        float t;
+        if (f2i_bits(hd.x) == MORT_OBJ_SPHERE) {
+            F4 c = ld4(&B->a[0][0]), v = ld4(&B->a[1][0]);
+            if (sphere_test(mk3(c.x, c.y, c.z), c.w, mk3(v.x, v.y, v.z), o, d, r.tm, tmin, closest, t)) { any = true; closest = t; }
+        } else {
+            float al, be;
+            if (quad_test(ld4(&B->a[0][0]), &B->a[1][0], o, d, tmin, closest, t, al, be)) { any = true; closest = t; }
+        }
+    }
+    t_hit = closest;
+    return any;
+}
+
+// returns true when the ray scatters inside medium m before `closest`
+MORT_HD bool medium_hit(const DeviceScene& sc, const Medium& m, const Ray& r, float tmin, float tmax, Rng& g, float& t_out) {
+    float t1, t2;
+    if (!boundary_probe(sc, m, r, -INFINITY, INFINITY, t1)) return false;
+    if (!boundary_probe(sc, m, r, (float)((double)t1 + 0.0001), INFINITY, t2)) return false;
+    if (t1 < tmin) t1 = tmin;
+    if (t2 > tmax) t2 = tmax;
+    if (t1 >= t2) return false;
+    if (t1 < 0) t1 = 0;
+    float ray_length = xsqrt(xdot(r.d, r.d));
+    float inside = (t2 - t1) * ray_length;
+    double hit_distance = m.neg_inv_density * (double)logf(rnd(g));
+    if (hit_distance > (double)inside) return false;
+    t_out = (float)((double)t1 + hit_distance / (double)ray_length);
+    return true;
+}
+
+// world::hit (world.cuh:104-171): surfaces, then media clipped to the closest surface, then top-level lists
+template <bool kStaged>
+MORT_HD bool world_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, const Ray& r, Rng& g, Record& rec) {
+    const float tmin = 0.001f;
+    Hit h;
+    bool any;
+    if (!sc.two_pass) any = closest_hit<kStaged>(sc, staged, n_staged, r, tmin, INFINITY, h);
+    else any = closest_hit<kStaged>(sc, staged, n_staged, r, tmin, INFINITY, h, 0, sc.post_media_order);
+    float closest = any ? h.t : INFINITY;
+    int med = -1; float tmed = 0.f;
+    for (int m = 0; m < sc.n_media; m++) {
+        float t;
+        if (medium_hit(sc, sc.media[m], r, tmin, closest, g, t)) { med = m; tmed = t; closest = t; }
+    }
+    if (sc.two_pass) {
+        Hit h2;
+        if (closest_hit<kStaged>(sc, staged, n_staged, r, tmin, closest, h2, sc.post_media_order, 0x7FFFFFFF)) { h = h2; any = true; med = -1; }
+    }
+    if (med >= 0) {
+        rec.t = tmed; rec.p = xat(r.o, r.d, tmed); rec.normal = mk3(1, 0, 0); rec.front_face = true;
+        rec.mat_gid = sc.media[med].mat_gid; rec.u = rec.v = 0.f; rec.sphere_uv = false;
+        rec.leaf_type = MORT_OBJ_CONSTANT_MEDIUM; rec.leaf_idx = sc.media[med].obj_idx;
+        return true;
+    }
+    if (!any) return false;
+    resolve_hit(sc, r, h, rec);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// textures (textures.cuh)
+// ---------------------------------------------------------------------------------------------------
+MORT_HD_NOINLINE float perlin_turb(const NoiseTables* N, f3 p) {                      // textures.cuh:174-196, 232-265
+    double accum = 0.0, weight = 1.0;
+    for (int oct = 0; oct < 7; oct++) {
+        float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+        float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+        u = u * u * (3 - 2 * u); v = v * v * (3 - 2 * v); w = w * w * (3 - 2 * w);
+        int i = (int)fx, j = (int)fy, k = (int)fz;
+        double du = u, dv = v, dw = w;
+        double uu = du * du * (3 - 2 * du), vv = dv * dv * (3 - 2 * dv), ww = dw * dw * (3 - 2 * dw);
+        double acc = 0.0;
+        for (int di = 0; di < 2; di++) for (int dj = 0; dj < 2; dj++) for (int dk = 0; dk < 2; dk++) {
+            int idx = (int)(ldu8(N->perm_x + ((i + di) & 255)) ^ ldu8(N->perm_y + ((j + dj) & 255)) ^ ldu8(N->perm_z + ((k + dk) & 255)));
+            F4 c = ld4(&N->ranvec[idx][0]);
+            f3 wv = mk3((float)(du - di), (float)(dv - dj), (float)(dw - dk));
+            float dt = xfma(c.z, wv.z, xfma(c.x, wv.x, xmul(c.y, wv.y)));
+            acc += (di * uu + (1 - di) * (1 - uu)) * (dj * vv + (1 - dj) * (1 - vv)) * (dk * ww + (1 - dk) * (1 - ww)) * (double)dt;
+        }
+        accum += weight * (double)(float)acc;
+        weight *= 0.5;
+        p = 2.0f * p;
+    }
+    return fabsf((float)accum);
+}
+
+MORT_HD f3 texture_value(const DeviceScene& sc, int gid, Record& rec) {               // textures.cuh:327-349
+    for (int guard = 0; guard < 8; guard++) {
+        if (gid < 0) break;
+        const Texture* T = sc.textures + gid;
+        F4 a = ld4(T), b = ld4(reinterpret_cast<const float*>(T) + 4);
+        int type = f2i_bits(a.x);
+        if (type == MORT_TEX_SOLID) return mk3(a.y, a.z, a.w);
+        if (type == MORT_TEX_CHECKER) {                                               // textures.cuh:52-60
+            float inv = a.y;
+            int xi = (int)floorf(inv * rec.p.x), yi = (int)floorf(inv * rec.p.y), zi = (int)floorf(inv * rec.p.z);
+            bool even = (xi + yi + zi) % 2 == 0;
+            gid = even ? f2i_bits(b.x) : f2i_bits(b.y);
+            continue;
+        }
+        if (rec.sphere_uv) { sphere_uv(rec.outward, rec.u, rec.v); rec.sphere_uv = false; }
+        if (type == MORT_TEX_IMAGE) {                                                 // textures.cuh:129-146
+            const ImageDesc im = sc.images[f2i_bits(b.x)];
+            if (im.height <= 0 || im.texels == nullptr) return mk3(0, 1, 1);
+            float u = rec.u < 0 ? 0 : (rec.u > 1 ? 1 : rec.u);
+            float vc = rec.v < 0 ? 0 : (rec.v > 1 ? 1 : rec.v);
+            float v = (float)(1.0 - (double)vc);
+            int i = (int)(u * im.width), j = (int)(v * im.height);
+            if (j > im.height - 1) j = im.height - 1;
+            if (j < 0) j = 0;
+            int x0 = i * 3; int cmax = im.cols - 1;
+            int xr = x0 < 0 ? 0 : (x0 > cmax ? cmax : x0), xg = x0 + 1 > cmax ? cmax : (x0 + 1 < 0 ? 0 : x0 + 1), xb = x0 + 2 > cmax ? cmax : (x0 + 2 < 0 ? 0 : x0 + 2);
+            const uint8_t* row = im.texels + (size_t)j * im.cols;
+            float sc255 = (float)(1.0 / 255.0);
+            return mk3(sc255 * (float)ldu8(row + xr), sc255 * (float)ldu8(row + xg), sc255 * (float)ldu8(row + xb));
+        }
+        if (type == MORT_TEX_NOISE) {                                                 // textures.cuh:198-202
+            const NoiseTables* N = sc.noises + f2i_bits(b.x);
+            f3 s = N->scale * rec.p;
+            float f = (float)(1.0 + sin((double)s.z + 10.0 * (double)perlin_turb(N, s)));
+            return mk3(0.5f * f, 0.5f * f, 0.5f * f);
+        }
+        break;
+    }
+    if (rec.sphere_uv) { sphere_uv(rec.outward, rec.u, rec.v); rec.sphere_uv = false; }
+    float e = (float)(((int)floorf(rec.u * 1000.0f) % 2) == ((int)floorf(rec.v * 1000.0f) % 2));   // textures.cuh:347-348
+    return mk3(e, 0.f, e);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sampling helpers (vec3.cuh:148-212, onb.cuh:41-50) and light sampling (objects.cuh:110-145, 217-235, 488-504)
+// ---------------------------------------------------------------------------------------------------
+struct Onb { f3 u, v, w; };
+MORT_HD void onb_from_w(Onb& b, f3 w) {
+    f3 uw = unit3(w);
+    f3 a = (fabsf(uw.x) > 0.9f) ? mk3(0, 1, 0) : mk3(1, 0, 0);
+    f3 v = unit3(cross3(uw, a));
+    b.u = cross3(uw, v); b.v = v; b.w = uw;
+}
+MORT_HD f3 onb_local(const Onb& b, f3 a) { return a.x * b.u + a.y * b.v + a.z * b.w; }
+MORT_HD f3 random_unit_vector(Rng& g) {
+    for (;;) {
+        float x = rnd_range(g, -1, 1), y = rnd_range(g, -1, 1), z = rnd_range(g, -1, 1);
+        f3 p = mk3(x, y, z);
+        if (len2(p) >= 1) continue;
+        return unit3(p);
+    }
+}
+MORT_HD f3 random_cosine_direction(Rng& g) {
+    float r1 = rnd(g), r2 = rnd(g);
+    float phi = (float)(2 * 3.1415926 * (double)r1);
+    float sr = sqrtf(r2);
+    return mk3(cosf(phi) * sr, sinf(phi) * sr, sqrtf(1 - r2));
+}
+MORT_HD f3 reflect3(f3 v, f3 n) { return v - (2 * dot3(v, n)) * n; }
+MORT_HD f3 refract3(f3 uv, f3 n, float eta) {
+    float cos_theta = fminf(dot3(-uv, n), 1.0f);
+    f3 perp = eta * (uv + cos_theta * n);
+    f3 par = ((float)(-sqrt(fabs(1.0 - (double)len2(perp))))) * n;
+    return perp + par;
+}
+MORT_HD float reflectance(float cosine, float ref_idx) {
+    float r0 = (1 - ref_idx) / (1 + ref_idx); r0 = r0 * r0;
+    float x = 1 - cosine, x2 = x * x;
+    return r0 + (1 - r0) * (x2 * x2 * x);
+}
+
+MORT_HD float light_prim_pdf(const LightPrim* L, f3 origin, f3 dir) {
+    F4 hd = ld4(L);
+    int kind = f2i_bits(hd.x);
+    if (kind == LIGHT_SPHERE) {                                                       // objects.cuh:110-122
+        F4 c = ld4(&L->a[0][0]);
+        float t;
+        if (!sphere_test(mk3(c.x, c.y, c.z), c.w, mk3(0, 0, 0), origin, dir, 0.f, 0.001f, HUGE_VALF, t)) return 0.f;
+        float cos_theta_max = sqrtf(1 - c.w * c.w / len2(mk3(c.x, c.y, c.z) - origin));
+        float solid_angle = (float)(2 * 3.1415926 * (double)(1 - cos_theta_max));
+        return (float)(1.0 / (double)solid_angle);
+    }
+    if (kind == LIGHT_QUAD) {                                                         // objects.cuh:217-229
+        float t, al, be;
+        F4 nD = ld4(&L->a[0][0]);
+        if (!quad_test(nD, &L->a[1][0], origin, dir, 0.001f, HUGE_VALF, t, al, be)) return 0.f;
+        float d2 = t * t * len2(dir);
+        f3 n = mk3(nD.x, nD.y, nD.z);                  // |dot| is the same for the flipped normal
+        float cosine = fabsf(dot3(dir, n) / sqrtf(len2(dir)));
+        return d2 / (cosine * hd.y);
+    }
+    return 0.f;
+}
+MORT_HD f3 light_prim_random(const LightPrim* L, f3 origin, Rng& g) {
+    F4 hd = ld4(L);
+    int kind = f2i_bits(hd.x);
+    if (kind == LIGHT_SPHERE) {                                                       // objects.cuh:124-145
+        F4 c = ld4(&L->a[0][0]);
+        f3 direction = mk3(c.x, c.y, c.z) - origin;
+        float d2 = len2(direction);
+        Onb uvw; onb_from_w(uvw, direction);
+        float r1 = rnd(g), r2 = rnd(g);
+        float z = 1 + r2 * (sqrtf(1 - c.w * c.w / d2) - 1);
+        float phi = (float)(2 * 3.141592 * (double)r1);
+        float s = sqrtf(1 - z * z);
+        return onb_local(uvw, mk3(cosf(phi) * s, sinf(phi) * s, z));
+    }
+    if (kind == LIGHT_QUAD) {                                                         // objects.cuh:231-235
+        F4 Q = ld4(&L->a[1][0]), U = ld4(&L->a[2][0]), Vv = ld4(&L->a[3][0]);
+        float r1 = rnd(g), r2 = rnd(g);
+        f3 p = mk3(Q.x, Q.y, Q.z) + r1 * mk3(U.x, U.y, U.z) + r2 * mk3(Vv.x, Vv.y, Vv.z);
+        return p - origin;
+    }
+    return mk3(1, 0, 0);
+}
+MORT_HD float light_pdf_value(const DeviceScene& sc, f3 origin, f3 dir) {             // objects.cuh:947-962
+    if (sc.light_kind == LIGHT_SPHERE || sc.light_kind == LIGHT_QUAD) return light_prim_pdf(sc.lights, origin, dir);
+    if (sc.light_kind == LIGHT_LIST) {
+        float weight = (float)(1.0 / (double)(float)sc.n_lights), sum = 0.f;
+        for (int i = 0; i < sc.n_lights; i++) sum += weight * light_prim_pdf(sc.lights + i, origin, dir);
+        return sum;
+    }
+    return 0.f;
+}
+MORT_HD f3 light_random(const DeviceScene& sc, f3 origin, Rng& g) {                   // objects.cuh:964-979
+    if (sc.light_kind == LIGHT_SPHERE || sc.light_kind == LIGHT_QUAD) return light_prim_random(sc.lights, origin, g);
+    if (sc.light_kind == LIGHT_LIST) { int k = rnd_int(g, 0, sc.n_lights - 1); return light_prim_random(sc.lights + k, origin, g); }
+    return mk3(1, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// camera (camera.cuh:210-242) and one path segment (camera.cuh:96-159, forward form)
+// ---------------------------------------------------------------------------------------------------
+MORT_HD void camera_ray(const CameraParams& c, int x, int y, int s_i, int s_j, Rng& g, Ray& r) {
+    double px = (double)(((float)s_i + rnd(g)) * c.recip_sqrt_spp) - 0.5;
+    double py = (double)(((float)s_j + rnd(g)) * c.recip_sqrt_spp) - 0.5;
+    float ox = (float)px, oy = (float)py;
+    float tu = (float)((double)x + (double)ox), tv = (float)((double)y + (double)oy);
+    f3 ps = mk3(xfma(tv, c.dv[0], xfma(tu, c.du[0], c.pixel00[0])), xfma(tv, c.dv[1], xfma(tu, c.du[1], c.pixel00[1])),
+                xfma(tv, c.dv[2], xfma(tu, c.du[2], c.pixel00[2])));
+    f3 origin = mk3(c.center[0], c.center[1], c.center[2]);
+    if (!(c.defocus_angle <= 0)) {
+        float dx, dy;
+        for (;;) { dx = rnd_range(g, -1, 1); dy = rnd_range(g, -1, 1); if (dx * dx + dy * dy < 1) break; }
+        origin = mk3(xfma(dy, c.defocus_v[0], xfma(dx, c.defocus_u[0], c.center[0])), xfma(dy, c.defocus_v[1], xfma(dx, c.defocus_u[1], c.center[1])),
+                     xfma(dy, c.defocus_v[2], xfma(dx, c.defocus_u[2], c.center[2])));
+    }
+    r.o = origin; r.d = xsub3(ps, origin); r.tm = rnd(g);
+}
+
+// Path state.  The reference stores (A, E, spdf, pdf) per bounce and unwinds L = E + A*spdf*L/pdf backwards
+// (camera.cuh:137-173).  Only non-scattering hits emit, so E_i = 0 on every stored bounce and the unwind is
+// exactly  L = (prod_i A_i*spdf_i/pdf_i) * terminal ; the product is carried forward in `thr`.  IEEE
+// inf/NaN propagate through the product the same way they do through the unwind (0*inf, 0/0 -> NaN).
+struct Path { Ray ray; f3 thr; int depth; };
+
+enum { SEG_CONTINUE = 0, SEG_DONE = 1 };
+
+// Advances one segment.  On SEG_DONE `color` is the finished sample (may be NaN/inf, like the reference's).
+// `traced` is set when a closest-hit query was issued (the unit of the Mrays/s metric).
+template <bool kStaged>
+MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const Bvh4Node* staged, int n_staged, Path& P, Rng& g, f3& color, bool& traced) {
+    traced = false;
+    if (P.depth >= cam.bounce_limit) { color = P.thr * mk3(0, 0, 0); return SEG_DONE; }   // camera.cuh:161-163 (0 * inf stays NaN)
+    Record rec;
+    if (isnan3(P.ray.d) || isnan3(P.ray.o)) { color = mk3(NAN, NAN, NAN); return SEG_DONE; }
+    traced = true;
+    if (!world_hit<kStaged>(sc, staged, n_staged, P.ray, g, rec)) {
+        color = P.thr * mk3(cam.background[0], cam.background[1], cam.background[2]);   // camera.cuh:154-158
+        return SEG_DONE;
+    }
+    if (rec.mat_gid < 0) { color = P.thr * mk3(0, 0, 0); return SEG_DONE; }             // dispatchers' default: no scatter, no emission
+    const Material* M = sc.materials + rec.mat_gid;
+    F4 m0 = ld4(M), m1 = ld4(reinterpret_cast<const float*>(M) + 4);
+    int type = f2i_bits(m0.x), tex = f2i_bits(m0.y);
+    if (type == MORT_MAT_DIFFUSE_LIGHT) {                                                 // materials.cuh:151-163
+        f3 e = rec.front_face ? texture_value(sc, tex, rec) : mk3(0, 0, 0);
+        color = P.thr * e;
+        return SEG_DONE;
+    }
+    if (type == MORT_MAT_METAL) {                                                         // materials.cuh:73-84
+        f3 refl = reflect3(P.ray.d, rec.normal);
+        float fuzz = m1.y;
+        refl = unit3(refl) + fuzz * random_unit_vector(g);
+        P.thr = P.thr * mk3(m0.z, m0.w, m1.x);
+        P.ray.o = rec.p; P.ray.d = refl; P.depth++;
+        return SEG_CONTINUE;
+    }
+    if (type == MORT_MAT_DIELECTRIC) {                                                    // materials.cuh:107-130
+        float ratio = rec.front_face ? m1.z : m1.y;
+        f3 ud = unit3(P.ray.d);
+        float cos_theta = fminf(dot3(-ud, rec.normal), 1.0f);
+        float sin_theta = (float)sqrt(1.0 - (double)(cos_theta * cos_theta));
+        bool cant_refract = (ratio * sin_theta) > 1.0f;
+        f3 dir;
+        if (cant_refract || reflectance(cos_theta, ratio) > rnd(g)) dir = reflect3(ud, rec.normal);
+        else dir = refract3(ud, rec.normal, ratio);
+        P.ray.o = rec.p; P.ray.d = dir; P.depth++;       // attenuation (1,1,1)
+        return SEG_CONTINUE;
+    }
+    if (type != MORT_MAT_LAMBERTIAN && type != MORT_MAT_ISOTROPIC) { color = P.thr * mk3(0, 0, 0); return SEG_DONE; }
+
+    // lambertian / isotropic: importance-sampled bounce (camera.cuh:115-140, pdf.cuh)
+    f3 atten = texture_value(sc, tex, rec);
+    const bool cosine = type == MORT_MAT_LAMBERTIAN;
+    Onb uvw;
+    if (cosine) onb_from_w(uvw, rec.normal);
+    f3 dir; float pdf;
+    const float inv4pi = (float)(1 / (4 * 3.1415926));
+    if (sc.light_kind == LIGHT_NONE) {
+        dir = cosine ? onb_local(uvw, random_cosine_direction(g)) : random_unit_vector(g);
+        pdf = cosine ? fmaxf(0.f, (float)((double)dot3(unit3(dir), uvw.w) / 3.1415926)) : inv4pi;
+    } else {
+        if (rnd(g) < 0.5f) dir = light_random(sc, rec.p, g);
+        else dir = cosine ? onb_local(uvw, random_cosine_direction(g)) : random_unit_vector(g);
+        float pm = cosine ? fmaxf(0.f, (float)((double)dot3(unit3(dir), uvw.w) / 3.1415926)) : inv4pi;
+        pdf = (float)(0.5 * (double)light_pdf_value(sc, rec.p, dir) + 0.5 * (double)pm);
+    }
+    float spdf;
+    if (cosine) { float ct = dot3(rec.normal, unit3(dir)); spdf = (ct < 0) ? 0.f : (float)((double)ct / 3.141592565); }   // materials.cuh:51-55
+    else spdf = inv4pi;
+    // (attenuation * scattering_pdf * L) / pdf  with vec/scalar = (1/pdf) * vec  (camera.cuh:172, vec3.cuh:109-112)
+    float rp = 1.0f / pdf;
+    P.thr = rp * ((spdf * atten) * P.thr);
+    P.ray.o = rec.p; P.ray.d = dir; P.depth++;
+    return SEG_CONTINUE;
+}
+
+MORT_HD void path_start(const CameraParams& cam, uint32_t seed, uint32_t frame, int pixel, int s_i, int s_j, Path& P, Rng& g) {
+    int x = pixel % cam.width, y = pixel / cam.width;
+    rng_init(g, seed, frame, (uint32_t)pixel, (uint32_t)(s_j * cam.sqrt_spp + s_i));
+    camera_ray(cam, x, y, s_i, s_j, g, P.ray);
+    P.thr = mk3(1, 1, 1); P.depth = 0;
+}
+
+// Camera::render's tail (camera.cuh:194-207): mean, NaN flush, gamma 2, 8-bit quantisation.
+MORT_HD void tonemap_pixel(float sx, float sy, float sz, float scale, uint8_t out[4]) {
+    float c[3] = {sx * scale, sy * scale, sz * scale};
+    for (int k = 0; k < 3; k++) {
+        float v = c[k];
+        if (v != v) v = 0.0f;
+        v = sqrtf(v);
+        v = v < 0.0f ? 0.0f : (v > 0.999f ? 0.999f : v);
+        out[k] = (uint8_t)(int)(256 * v);
+    }
+    out[3] = 255;
+}
+
+}  // namespace mort

@@ -267,9 +267,9 @@ static int rotate_hit(const oracle_scene* S, const mscn_rotate_y* t, const ray_t
     if (!hit_dispatch(S, t->obj_type, t->obj_idx, &rr, tmin, tmax, rec, g)) return 0;
     v3 p = rec->p, n = rec->normal;
     p.x = fmaf(c, rec->p.x, s * rec->p.z);
-    p.z = fmaf(-s, rec->p.x, c * rec->p.z);
+    p.z = fmaf(c, rec->p.z, -(s * rec->p.x));      /* (-s*x + c*z) is canonicalised to c*z - s*x before contraction */
     n.x = fmaf(c, rec->normal.x, s * rec->normal.z);
-    n.z = fmaf(-s, rec->normal.x, c * rec->normal.z);
+    n.z = fmaf(c, rec->normal.z, -(s * rec->normal.x));
     rec->p = p; rec->normal = n;
     return 1;
 }

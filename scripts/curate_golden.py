@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Curates tests/golden/ from the raw outputs of the reference harness (gpurun_out/ref/, produced on a
+B200 by scripts/gpu_ref_fixtures.sh and scripts/gpu_ref_fixtures2.sh).  Everything written here is an
+output of the UNMODIFIED reference renderer (oracle/ref_harness.cu); nothing is synthesised.
+
+  scene_<n>.mscn            host scene arrays + camera right before world::toDevice (scene 9: camera only)
+  hits_<n>.npz              primary-hit records for a camera grid + incoherent rays (subsampled)
+  small_<n>.npz             96-wide 64-spp frames: 8-bit reference frame, float sums for two seeds
+  conv_<n>.npz              4096-spp (or as noted) float frame, seed A, + noise floor vs seed B
+  reference_timings.jsonl   the harness' own timing lines
+"""
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mort_b200 import formats as F  # noqa: E402
+
+SRC = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/ref"
+DST = "tests/golden"
+os.makedirs(DST, exist_ok=True)
+
+
+def subsample(h, keep=1500):
+    n = len(h["hits"])
+    ties = np.nonzero((h["hits"]["flags"] & 2) != 0)[0]
+    step = max(1, n // keep)
+    idx = np.unique(np.concatenate([np.arange(0, n, step), ties]))
+    return idx
+
+
+for sc in range(1, 11):
+    p = f"{SRC}/scene_{sc}.mscn"
+    if os.path.exists(p):
+        if sc == 9:
+            raw = open(p, "rb").read()
+            raw8 = open(f"{SRC}/scene_8.mscn", "rb").read()
+            assert raw[:-F.camera_dt.itemsize] == raw8[:-F.camera_dt.itemsize], "scene 9 geometry differs from scene 8"
+            open(f"{DST}/camera_9.bin", "wb").write(raw[-F.camera_dt.itemsize:])
+        else:
+            shutil.copy(p, f"{DST}/scene_{sc}.mscn")
+    out = {}
+    for kind in ("grid", "rnd"):
+        p = f"{SRC}/{kind}_{sc}.mhit"
+        if not os.path.exists(p):
+            continue
+        h = F.read_hits(p)
+        idx = subsample(h)
+        out[f"{kind}_rays"] = h["rays"][idx]
+        out[f"{kind}_hits"] = h["hits"][idx]
+        out[f"{kind}_probes"] = h["probes"][idx]
+    if out:
+        np.savez_compressed(f"{DST}/hits_{sc}.npz", **out)
+    small = {}
+    for tag, name in (("small8", "a"), ("smallhdr", "a"), ("smallhdr", "b")):
+        p = f"{SRC}/{tag}_{sc}_{name}.mimg"
+        if os.path.exists(p):
+            img = F.read_mimg(p)
+            small[f"{tag}_{name}"] = img if img.dtype == np.uint8 else img.astype(np.float32)
+    if small:
+        np.savez_compressed(f"{DST}/small_{sc}.npz", **small)
+    pa, pb = f"{SRC}/convhdr_{sc}_a.mimg", f"{SRC}/convhdr_{sc}_b.mimg"
+    if os.path.exists(pa) and os.path.exists(pb):
+        a, b = F.read_mimg(pa), F.read_mimg(pb)
+        meta = json.load(open(f"{SRC}/conv_meta_{sc}.json")) if os.path.exists(f"{SRC}/conv_meta_{sc}.json") else {}
+        spp = meta.get("spp", 4096)
+        ok = (a[..., 3] == 0) & (b[..., 3] == 0) & np.isfinite(a[..., :3]).all(axis=-1) & np.isfinite(b[..., :3]).all(axis=-1)
+        ma, mb = a[..., :3][ok] / spp, b[..., :3][ok] / spp
+        rmse_ab = np.sqrt(((ma - mb) ** 2).mean(axis=0)) if ok.any() else np.zeros(3)
+        lum = lambda m: float((0.2126 * m[:, 0] + 0.7152 * m[:, 1] + 0.0722 * m[:, 2]).mean()) if len(m) else 0.0
+        np.savez_compressed(f"{DST}/conv_{sc}.npz", mean_a=(a[..., :3] / spp).astype(np.float16), nan_a=a[..., 3].astype(np.uint16),
+                            nan_b=b[..., 3].astype(np.uint16), finite_b=np.isfinite(b[..., :3]).all(axis=-1), spp=np.int32(spp), rmse_ab=rmse_ab.astype(np.float64),
+                            lum_a=np.float64(lum(ma)), lum_b=np.float64(lum(mb)),
+                            rgba8_a=F.read_mimg(f"{SRC}/conv8_{sc}_a.mimg") if os.path.exists(f"{SRC}/conv8_{sc}_a.mimg") else np.zeros(0, np.uint8))
+        print(f"scene {sc}: conv {a.shape} spp {spp} rmse_ab {rmse_ab} lum {lum(ma):.5f} {lum(mb):.5f} nan px {int((a[...,3]>0).sum())}")
+if os.path.exists(f"{SRC}/log.jsonl"):
+    lines = [l for l in open(f"{SRC}/log.jsonl") if '"timing"' in l or '"failed"' in l]
+    open(f"{DST}/reference_timings.jsonl", "a").writelines(lines)
+os.system(f"du -sh {DST}")

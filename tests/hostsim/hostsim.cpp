@@ -1,0 +1,104 @@
+// tests/hostsim/hostsim.cpp — DEVELOPMENT AID, test-only.  Compiles mort_b200/csrc/rt_core.cuh as plain
+// C++ and runs the product's flattening + BVH traversal + shading functions serially on the CPU so they
+// can be diffed against the oracle on a machine without a GPU.  It is not linked into libmort_b200.so and
+// no product entry point can reach it; the product itself has no CPU path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "flatten.hpp"
+#include "rt_core.cuh"
+#include "scene.hpp"
+
+using namespace mort;
+
+static DeviceScene make_device_scene(const Scene& s, const FlatScene& f, std::vector<ImageDesc>& imgs) {
+    DeviceScene d; memset(&d, 0, sizeof(d));
+    d.nodes = f.nodes.data(); d.n_nodes = (int)f.nodes.size();
+    d.spheres = f.spheres.data(); d.sphere_info = f.sphere_info.data(); d.n_spheres = (int)f.spheres.size();
+    d.quads = f.quads.data(); d.n_quads = (int)f.quads.size();
+    d.instances = f.instances.data(); d.n_instances = (int)f.instances.size();
+    d.materials = f.materials.data(); d.n_materials = (int)f.materials.size();
+    d.textures = f.textures.data(); d.n_textures = (int)f.textures.size();
+    imgs.clear();
+    for (const ImageRec& im : s.images) { ImageDesc I; I.texels = im.rgb.empty() ? nullptr : im.rgb.data(); I.width = im.width; I.height = im.height; I.cols = im.width * 3; imgs.push_back(I); }
+    d.images = imgs.data(); d.n_images = (int)imgs.size();
+    d.noises = f.noises.data(); d.n_noises = (int)f.noises.size();
+    d.media = f.media.data(); d.n_media = (int)f.media.size();
+    d.boundary = f.boundary.data(); d.n_boundary = (int)f.boundary.size();
+    d.lights = f.lights.data(); d.n_lights = (int)f.lights.size(); d.light_kind = f.light_kind;
+    d.post_media_order = f.post_media_order; d.two_pass = f.two_pass; d.empty = f.empty;
+    return d;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "hostsim <scene 1-10 | file.mscn> <assets> trace in.mhit out.mhit [brute]\n        ... render W SPP DEPTH SEED out.mimg\n"); return 1; }
+    Scene s; std::string assets = argv[2];
+    std::string a1 = argv[1];
+    if (a1.size() > 5 && a1.substr(a1.size() - 5) == ".mscn") {
+        std::string err; if (!s.load(a1, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+        ImageRec im; if (!s.images.empty() && load_ppm(assets + "/earthmap.ppm", im)) { s.images[0].rgb = im.rgb; }
+    } else if (!build_reference_scene(s, atoi(argv[1]), assets)) { fprintf(stderr, "scene: %s\n", s.error.c_str()); return 2; }
+    std::string mode = argv[3];
+    if (mode == "render") {
+        int W = atoi(argv[4]), spp = atoi(argv[5]), depth = atoi(argv[6]);
+        if (W > 0) s.cam.image_width = W;
+        if (spp > 0) s.cam.samples_per_pixel = spp;
+        if (depth > 0) s.cam.bounce_limit = depth;
+        s.cam.initialize();
+    }
+    FlatScene f; std::string err;
+    if (!flatten_scene(s, f, &err)) { fprintf(stderr, "flatten: %s\n", err.c_str()); return 2; }
+    std::vector<ImageDesc> imgs;
+    DeviceScene d = make_device_scene(s, f, imgs);
+    fprintf(stderr, "leaves %d nodes %d (bvh2 %d) depth %d sah %.2f pad %g build %.2f ms two_pass %d media %d lights %d kind %d\n", f.stats.n_leaves, f.stats.n_nodes,
+            f.stats.n_bvh2_nodes, f.stats.max_depth, f.stats.sah_cost, f.stats.pad, f.stats.build_ms, f.two_pass, d.n_media, d.n_lights, d.light_kind);
+    if (mode == "trace") {
+        FILE* fi = fopen(argv[4], "rb"); if (!fi) return 3;
+        uint32_t hd[4]; if (fread(hd, 4, 4, fi) != 4) return 3;
+        int n = (int)hd[1];
+        std::vector<float> rays((size_t)n * 7); if (fread(rays.data(), 4, rays.size(), fi) != rays.size()) return 3; fclose(fi);
+        bool brute = argc > 6 && !strcmp(argv[6], "brute");
+        std::vector<mhit_record> out(n);
+        for (int i = 0; i < n; i++) {
+            const float* q = &rays[7 * (size_t)i];
+            Ray r; r.o = mk3(q[0], q[1], q[2]); r.d = mk3(q[3], q[4], q[5]); r.tm = q[6];
+            Hit h; bool any = brute ? closest_hit_brute(d, r, 0.001f, INFINITY, h) : closest_hit<false>(d, nullptr, 0, r, 0.001f, INFINITY, h);
+            mhit_record o; memset(&o, 0, sizeof(o)); o.hit = any; o.leaf_type = o.leaf_idx = o.top_type = o.top_idx = -1;
+            if (any) {
+                Record rec; resolve_hit(d, r, h, rec);
+                if (rec.sphere_uv) sphere_uv(rec.outward, rec.u, rec.v);
+                o.t = rec.t; o.leaf_type = rec.leaf_type; o.leaf_idx = rec.leaf_idx; o.front_face = rec.front_face;
+                int gid = rec.mat_gid; o.mat_type = gid < 0 ? -1 : f.materials[gid].type;
+                int off = 0; for (int g = 0; g < gid; g++) if (f.materials[g].type != o.mat_type) off = g + 1;
+                o.mat_idx = gid - off;
+                o.p[0] = rec.p.x; o.p[1] = rec.p.y; o.p[2] = rec.p.z; o.normal[0] = rec.normal.x; o.normal[1] = rec.normal.y; o.normal[2] = rec.normal.z;
+                o.u = rec.u; o.v = rec.v;
+            }
+            out[i] = o;
+        }
+        FILE* fo = fopen(argv[5], "wb"); uint32_t oh[4] = {MHIT_MAGIC, (uint32_t)n, 0, (uint32_t)f.stats.n_leaves};
+        fwrite(oh, 4, 4, fo); fwrite(rays.data(), 4, rays.size(), fo); fwrite(out.data(), sizeof(mhit_record), n, fo); fclose(fo);
+    } else if (mode == "render") {
+        uint32_t seed = (uint32_t)strtoul(argv[7], 0, 10);
+        const CameraParams& cam = f.cam;
+        std::vector<float> hdr((size_t)cam.width * cam.height * 4, 0.f);
+        unsigned long long segs = 0;
+        for (int pix = 0; pix < cam.width * cam.height; pix++) {
+            float sx = 0, sy = 0, sz = 0; int nan_n = 0;
+            for (int sj = 0; sj < cam.sqrt_spp; sj++) for (int si = 0; si < cam.sqrt_spp; si++) {
+                Path P; Rng g; f3 col;
+                path_start(cam, seed, 0, pix, si, sj, P, g);
+                for (;;) { bool tr; int st = path_segment<false>(d, cam, nullptr, 0, P, g, col, tr); segs += tr; if (st == SEG_DONE) break; }
+                if (isnan3(col)) nan_n++; else { sx += col.x; sy += col.y; sz += col.z; }
+            }
+            hdr[4 * (size_t)pix] = sx; hdr[4 * (size_t)pix + 1] = sy; hdr[4 * (size_t)pix + 2] = sz; hdr[4 * (size_t)pix + 3] = (float)nan_n;
+        }
+        fprintf(stderr, "segments %llu\n", segs);
+        FILE* fo = fopen(argv[8], "wb"); uint32_t hd[5] = {0x474D494Du, (uint32_t)cam.width, (uint32_t)cam.height, 4, 1};
+        fwrite(hd, 4, 5, fo); fwrite(hdr.data(), 4, hdr.size(), fo); fclose(fo);
+    }
+    return 0;
+}
