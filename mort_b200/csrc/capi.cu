@@ -303,6 +303,7 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     CU(cudaMemcpyAsync(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.reserved0 = (int32_t)sizeof(FrameParams);      // bytes of kernel parameters that go host->device per frame
     ctx->stats.last_render_ms = ms; ctx->stats.last_segments = cnt[0]; ctx->stats.last_samples = cnt[1]; ctx->stats.last_kernel_launches = launches;
     return MORT_OK;
 }

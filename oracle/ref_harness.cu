@@ -344,7 +344,7 @@ static void usage() {
 }
 
 int main(int argc, char** argv) {
-    int scene = 0, width = 0, spp = 0, depth = 0, frames = 0, grid_w = 0, rnd_n = 0, host_only = 0;
+    int scene = 0, width = 0, spp = 0, depth = 0, frames = 0, grid_w = 0, rnd_n = 0, host_only = 0, warmup = -1;
     float aspect = 0; unsigned long seed = 69420; uint64_t rnd_seed = 1;
     const char *dump = 0, *dump_rgb = 0, *img8 = 0, *hdr = 0, *grid_out = 0, *rnd_out = 0, *file_in = 0, *file_out = 0;
     for (int i = 1; i < argc; i++) {
@@ -353,7 +353,7 @@ int main(int argc, char** argv) {
         if (a == "--scene") scene = atoi(nx()); else if (a == "--width") width = atoi(nx());
         else if (a == "--aspect") aspect = (float)atof(nx()); else if (a == "--spp") spp = atoi(nx());
         else if (a == "--depth") depth = atoi(nx()); else if (a == "--seed") seed = strtoul(nx(), 0, 10);
-        else if (a == "--frames") frames = atoi(nx()); else if (a == "--dump-scene") dump = nx();
+        else if (a == "--frames") frames = atoi(nx()); else if (a == "--warmup") warmup = atoi(nx()); else if (a == "--dump-scene") dump = nx();
         else if (a == "--dump-image-rgb") dump_rgb = nx(); else if (a == "--img8") img8 = nx();
         else if (a == "--hdr") hdr = nx();
         else if (a == "--host-only") host_only = 1;   // dump the host-side scene and stop before any CUDA call (no GPU needed)
@@ -418,6 +418,8 @@ int main(int argc, char** argv) {
         CK(cudaMemset(dev_img, 0, (size_t)W * H * sizeof(uchar4)));
         cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         int nf = frames > 0 ? frames : 1;
+        if (warmup < 0) warmup = frames > 1 ? 1 : 0;       // --frames F --warmup W: W untimed launches, then F timed ones
+        nf += warmup;
         std::vector<float> ms;
         for (int fr = 0; fr < nf; fr++) {
             CK(cudaEventRecord(e0, 0));
@@ -427,12 +429,12 @@ int main(int argc, char** argv) {
             float t; CK(cudaEventElapsedTime(&t, e0, e1)); ms.push_back(t);
         }
         double samples = (double)W * H * cam.sqrt_spp * cam.sqrt_spp;
-        std::vector<float> timed(ms.begin() + (ms.size() > 1 ? 1 : 0), ms.end());   // frame 0 = warm-up when nf > 1
+        std::vector<float> timed(ms.begin() + warmup, ms.end());
         std::vector<float> srt = timed; std::sort(srt.begin(), srt.end());
         double med = srt[srt.size() / 2], sum = 0; for (float v : timed) sum += v;
-        printf("{\"timing\":\"renderKernel\",\"scene\":%d,\"width\":%d,\"height\":%d,\"spp_eff\":%d,\"depth\":%d,\"frames_timed\":%zu,"
-               "\"ms_first\":%.3f,\"ms_median\":%.3f,\"ms_mean\":%.3f,\"samples_per_frame\":%.0f,\"msamples_per_s\":%.4f}\n",
-               scene, W, H, cam.sqrt_spp * cam.sqrt_spp, cam.bounce_limit, timed.size(), ms[0], med, sum / timed.size(),
+        printf("{\"timing\":\"renderKernel\",\"scene\":%d,\"width\":%d,\"height\":%d,\"spp_eff\":%d,\"depth\":%d,\"frames_timed\":%zu,\"warmup\":%d,"
+               "\"ms_first\":%.3f,\"ms_median\":%.3f,\"ms_mean\":%.3f,\"ms_total_timed\":%.3f,\"samples_per_frame\":%.0f,\"msamples_per_s\":%.4f}\n",
+               scene, W, H, cam.sqrt_spp * cam.sqrt_spp, cam.bounce_limit, timed.size(), warmup, ms[0], med, sum / timed.size(), sum,
                samples, samples / (med * 1e3));
         if (img8) {
             std::vector<uchar4> hst((size_t)W * H);

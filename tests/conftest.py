@@ -1,0 +1,55 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ASSETS = os.path.join(ROOT, "mort_b200", "assets")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_scene_path(sc, tmpdir=None):
+    """Path of the reference's scene dump; scene 9 is scene 8's arrays + its own camera record."""
+    if sc != 9:
+        return os.path.join(GOLDEN, f"scene_{sc}.mscn")
+    from mort_b200 import formats as F
+    raw8 = open(os.path.join(GOLDEN, "scene_8.mscn"), "rb").read()
+    cam9 = open(os.path.join(GOLDEN, "camera_9.bin"), "rb").read()
+    out = os.path.join(tmpdir or "/tmp", "mort_golden_scene_9.mscn")
+    open(out, "wb").write(raw8[:-F.camera_dt.itemsize] + cam9)
+    return out
+
+
+@pytest.fixture(scope="session")
+def earth():
+    from mort_b200 import formats as F
+    return F.read_ppm(os.path.join(ASSETS, "earthmap.ppm"))
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    """Test-only host build of the product's per-ray code (tests/hostsim)."""
+    out = os.path.join(ROOT, "tests", "hostsim", "hostsim.bin")
+    src = [os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")] + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in
+                                                                      ("scene.cpp", "scenes.cpp", "flatten.cpp", "bvh_build.cpp")]
+    deps = src + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in ("rt_core.cuh", "device_types.h", "flatten.hpp", "scene.hpp")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "mort_b200", "csrc"),
+                               "-I" + os.path.join(ROOT, "include")] + src + ["-o", out])
+    return out
+
+
+def luminance(rgb):
+    return 0.2126 * rgb[..., 0] + 0.7152 * rgb[..., 1] + 0.0722 * rgb[..., 2]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
