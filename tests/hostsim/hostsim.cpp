@@ -37,11 +37,15 @@ int main(int argc, char** argv) {
     if (argc < 4) { fprintf(stderr, "hostsim <scene 1-10 | file.mscn> <assets> trace in.mhit out.mhit [brute]\n        ... render W SPP DEPTH SEED out.mimg\n"); return 1; }
     Scene s; std::string assets = argv[2];
     std::string a1 = argv[1];
-    if (a1.size() > 5 && a1.substr(a1.size() - 5) == ".mscn") {
+    if (a1.rfind("field:", 0) == 0) {
+        if (!build_sphere_field(s, atoi(a1.c_str() + 6), 69420, 0)) { fprintf(stderr, "field: %s\n", s.error.c_str()); return 2; }
+    } else if (a1.size() > 5 && a1.substr(a1.size() - 5) == ".mscn") {
         std::string err; if (!s.load(a1, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
         ImageRec im; if (!s.images.empty() && load_ppm(assets + "/earthmap.ppm", im)) { s.images[0].rgb = im.rgb; }
     } else if (!build_reference_scene(s, atoi(argv[1]), assets)) { fprintf(stderr, "scene: %s\n", s.error.c_str()); return 2; }
     std::string mode = argv[3];
+    if (mode == "dump") { return s.dump(argv[4]) ? 0 : 3; }
+    if (mode == "rand") { HostRng g(1); int n = atoi(argv[4]); for (int i = 0; i < n; i++) fprintf(stderr, "%d\n", g.next()); return 0; }
     if (mode == "render") {
         int W = atoi(argv[4]), spp = atoi(argv[5]), depth = atoi(argv[6]);
         if (W > 0) s.cam.image_width = W;
@@ -55,6 +59,58 @@ int main(int argc, char** argv) {
     DeviceScene d = make_device_scene(s, f, imgs);
     fprintf(stderr, "leaves %d nodes %d (bvh2 %d) depth %d sah %.2f pad %g build %.2f ms two_pass %d media %d lights %d kind %d\n", f.stats.n_leaves, f.stats.n_nodes,
             f.stats.n_bvh2_nodes, f.stats.max_depth, f.stats.sah_cost, f.stats.pad, f.stats.build_ms, f.two_pass, d.n_media, d.n_lights, d.light_kind);
+    if (mode == "checkbvh") {
+        // structural invariants of the 4-wide BVH: each primitive record referenced exactly once, leaves
+        // type-homogeneous by construction of the child word, un-instanced primitives inside their leaf box,
+        // children boxes inside the box their parent holds for them
+        std::vector<int> seen_s(f.spheres.size(), 0), seen_q(f.quads.size(), 0);
+        int bad = 0; size_t visited = 0;
+        struct It { uint32_t node; float lo[3], hi[3]; bool has; };
+        std::vector<It> st; It root; root.node = 0; root.has = false; st.push_back(root);
+        while (!st.empty()) {
+            It it = st.back(); st.pop_back(); visited++;
+            const Bvh4Node& n = f.nodes[it.node];
+            for (int k = 0; k < 4; k++) {
+                uint32_t w = n.child[k];
+                if (w == MORT_CHILD_EMPTY) continue;
+                float lo[3] = {n.lox[k], n.loy[k], n.loz[k]}, hi[3] = {n.hix[k], n.hiy[k], n.hiz[k]};
+                if (it.has) for (int a = 0; a < 3; a++) if (lo[a] < it.lo[a] - 1e-3f || hi[a] > it.hi[a] + 1e-3f) bad++;
+                if (w & MORT_LEAF_BIT) {
+                    uint32_t first = w & 0x07FFFFFFu; int cnt = (int)((w >> 27) & 7u) + 1;
+                    for (int i = 0; i < cnt; i++) {
+                        if (w & MORT_LEAF_QUAD_BIT) {
+                            if (first + i >= f.quads.size()) { bad++; continue; }
+                            seen_q[first + i]++;
+                            const QuadRec& q = f.quads[first + i];
+                            if (q.inst < 0) for (int c = 0; c < 4; c++) {
+                                float p[3] = {q.Qx + (c & 1) * q.ux + (c >> 1) * q.vx, q.Qy + (c & 1) * q.uy + (c >> 1) * q.vy, q.Qz + (c & 1) * q.uz + (c >> 1) * q.vz};
+                                for (int a = 0; a < 3; a++) if (p[a] < lo[a] || p[a] > hi[a]) bad++;
+                            }
+                        } else {
+                            if (first + i >= f.spheres.size()) { bad++; continue; }
+                            seen_s[first + i]++;
+                            const SphereGeom& g = f.spheres[first + i];
+                            if (g.inst < 0) {
+                                float c[3] = {g.cx, g.cy, g.cz}, v[3] = {g.vx, g.vy, g.vz};
+                                for (int a = 0; a < 3; a++) {
+                                    float mn = fminf(c[a], c[a] + v[a]) - fabsf(g.r), mx = fmaxf(c[a], c[a] + v[a]) + fabsf(g.r);
+                                    if (mn < lo[a] || mx > hi[a]) bad++;
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    if (w >= f.nodes.size()) { bad++; continue; }
+                    It c; c.node = w; c.has = true; memcpy(c.lo, lo, 12); memcpy(c.hi, hi, 12); st.push_back(c);
+                }
+            }
+        }
+        for (int v : seen_s) if (v != 1) bad++;
+        for (int v : seen_q) if (v != 1) bad++;
+        if (visited != f.nodes.size()) bad++;
+        fprintf(stderr, bad ? "bvh BAD: %d violations\n" : "bvh ok (%d)\n", bad);
+        return bad ? 4 : 0;
+    }
     if (mode == "trace") {
         FILE* fi = fopen(argv[4], "rb"); if (!fi) return 3;
         uint32_t hd[4]; if (fread(hd, 4, 4, fi) != 4) return 3;

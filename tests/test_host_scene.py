@@ -1,0 +1,74 @@
+"""Host logic of the product on the CPU: scene builder vs the reference's dumps, flattening + SAH wide BVH +
+per-ray code (through the test-only host simulation) vs the reference's hit records and the oracle's frames."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_binding as O
+from conftest import ASSETS, GOLDEN, bits, golden_scene_path
+from mort_b200 import formats as F
+
+SCENES = list(range(1, 11))
+
+
+def run(hostsim, *args):
+    return subprocess.run([hostsim, *map(str, args)], check=True, capture_output=True, text=True).stderr
+
+
+@pytest.mark.parametrize("sc", SCENES)
+def test_scene_dump_is_byte_identical_to_the_reference(hostsim, sc, tmp_path):
+    out = tmp_path / f"s{sc}.mscn"
+    run(hostsim, sc, ASSETS, "dump", out)
+    assert open(out, "rb").read() == open(golden_scene_path(sc, str(tmp_path)), "rb").read()
+
+
+def test_host_rand_is_glibc_rand(hostsim):
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    want = [libc.rand() for _ in range(1000)]
+    got = [int(x) for x in run(hostsim, 0, ASSETS, "rand", 1000).split()]
+    assert got == want
+
+
+@pytest.mark.parametrize("sc", SCENES)
+def test_flatten_bvh_and_traversal_reproduce_reference_hits(hostsim, sc, tmp_path):
+    g = np.load(f"{GOLDEN}/hits_{sc}.npz")
+    for kind in ("grid", "rnd"):
+        fin, fout, fbr = tmp_path / "in.mhit", tmp_path / "out.mhit", tmp_path / "brute.mhit"
+        F.write_hits(fin, g[f"{kind}_rays"], g[f"{kind}_hits"])
+        run(hostsim, sc, ASSETS, "trace", fin, fout)
+        run(hostsim, sc, ASSETS, "trace", fin, fbr, "brute")
+        ref, out, br = g[f"{kind}_hits"], F.read_hits(fout)["hits"], F.read_hits(fbr)["hits"]
+        b = ref["hit"] == 1
+        assert (out["hit"] == ref["hit"]).all() and (bits(out["t"])[b] == bits(ref["t"])[b]).all()
+        for k in ("leaf_type", "leaf_idx", "mat_type", "mat_idx", "front_face"):
+            assert (out[k][b] == ref[k][b]).all(), k
+        assert (bits(out["p"])[b] == bits(ref["p"])[b]).all() and (bits(out["normal"])[b] == bits(ref["normal"])[b]).all()
+        assert (out["hit"] == br["hit"]).all() and (bits(out["t"]) == bits(br["t"])).all() and (out["leaf_idx"] == br["leaf_idx"]).all()
+
+
+@pytest.mark.parametrize("sc,w,spp", [(1, 48, 16), (4, 48, 9), (6, 40, 16), (7, 40, 16), (9, 32, 9)])
+def test_frames_match_oracle_same_stream(hostsim, earth, sc, w, spp, tmp_path):
+    out = tmp_path / "f.mimg"
+    run(hostsim, sc, ASSETS, "render", w, spp, 0, 99, out)
+    mine = F.read_mimg(out)
+    osc = O.OracleScene(golden_scene_path(sc, str(tmp_path)), earth)
+    osc.override(width=w, spp=spp)
+    hdr, _, _ = osc.render(seed=99, want_rgba8=False)
+    assert (mine[..., 3] != hdr[..., 3]).mean() <= 0.003
+    ok = (mine[..., 3] == 0) & (hdr[..., 3] == 0) & np.isfinite(mine[..., :3]).all(-1) & np.isfinite(hdr[..., :3]).all(-1)
+    rel = np.abs(mine[..., :3][ok] - hdr[..., :3][ok]).max(-1) / (np.abs(hdr[..., :3][ok]).max(-1) + 0.16)
+    assert (rel > 1e-3).mean() <= 0.05
+
+
+def test_bvh_builder_invariants(hostsim, tmp_path):
+    """every leaf appears exactly once, children boxes lie inside the node they hang from, leaves are type-homogeneous"""
+    txt = run(hostsim, 8, ASSETS, "checkbvh")
+    assert "bvh ok" in txt, txt
+    txt = run(hostsim, 1, ASSETS, "checkbvh")
+    assert "bvh ok" in txt, txt
+    txt = run(hostsim, "field:40", ASSETS, "checkbvh")
+    assert "bvh ok" in txt, txt

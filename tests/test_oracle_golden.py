@@ -1,0 +1,127 @@
+"""Pins the ORACLE (oracle/mort_oracle.c) to the reference: every fixture under tests/golden/ is an output
+of the unmodified reference renderer executed on a B200 (oracle/ref_harness.cu, scripts/curate_golden.py).
+CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as O
+from conftest import GOLDEN, bits, golden_scene_path, luminance
+from mort_b200 import formats as F
+
+SCENES = list(range(1, 11))
+
+
+def test_philox_known_answers():
+    # SURVEY.md App. D (Random123 KATs)
+    assert [hex(x) for x in O.philox([0] * 4, [0] * 2)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in O.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in O.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0])] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_stream_is_counter_based_and_uniform():
+    a = O.stream_uniforms(69420, 0, 1234, 7, 64)
+    b = O.stream_uniforms(69420, 0, 1234, 7, 64)
+    assert np.array_equal(a, b) and (a >= 0).all() and (a < 1).all()
+    blk = O.philox([1234, 7, 0, 0], [69420, 0])
+    assert np.allclose(a[:4], (blk >> 8).astype(np.float32) / np.float32(16777216.0), rtol=0, atol=0)
+    big = np.concatenate([O.stream_uniforms(1, 0, p, 0, 256) for p in range(64)])
+    assert abs(big.mean() - 0.5) < 0.01 and abs(big.var() - 1 / 12) < 0.005
+
+
+@pytest.mark.parametrize("sc", SCENES)
+def test_primary_hits_bit_exact(sc, earth, tmp_path):
+    g = np.load(f"{GOLDEN}/hits_{sc}.npz")
+    osc = O.OracleScene(golden_scene_path(sc, str(tmp_path)), earth)
+    for kind in ("grid", "rnd"):
+        ref = g[f"{kind}_hits"]
+        out, probes = osc.trace(g[f"{kind}_rays"])
+        b = ref["hit"] == 1
+        assert (out["hit"] == ref["hit"]).all()
+        assert (bits(out["t"])[b] == bits(ref["t"])[b]).all(), "t must match the reference bit for bit"
+        for k in ("leaf_type", "leaf_idx", "top_type", "top_idx", "mat_type", "mat_idx", "front_face"):
+            assert (out[k][b] == ref[k][b]).all(), k
+        assert (bits(out["p"])[b] == bits(ref["p"])[b]).all() and (bits(out["normal"])[b] == bits(ref["normal"])[b]).all()
+        assert np.abs(out["u"] - ref["u"])[b].max(initial=0) <= 4e-7 and np.abs(out["v"] - ref["v"])[b].max(initial=0) <= 4e-7
+        rp = g[f"{kind}_probes"]
+        if rp.size:
+            assert (probes["hit1"] == rp["hit1"]).all() and (probes["hit2"] == rp["hit2"]).all()
+            assert (bits(probes["t1"]) == bits(rp["t1"])).all() and (bits(probes["t2"]) == bits(rp["t2"])).all()
+        assert (ref["flags"][b] & 1).sum() == 0, "the harness identified every reference hit by bit-equal t"
+
+
+@pytest.mark.parametrize("sc", SCENES)
+def test_camera_initialize_matches_reference(sc, earth, tmp_path):
+    """Camera::initialize restated in the oracle reproduces every derived field of the reference's dump,
+    at the scene default and at the harness' small-image override."""
+    path = golden_scene_path(sc, str(tmp_path))
+    ref = F.read_scene(path)["camera"]
+    osc = O.OracleScene(path, earth)
+    osc.override()                              # re-run initialize on the stored inputs
+    assert osc.camera.tobytes() == ref.tobytes()
+
+
+@pytest.mark.parametrize("sc", SCENES)
+def test_noisy_frame_statistics(sc, earth, tmp_path):
+    """Oracle (Philox) vs reference (XORWOW) at 96 px / 64 spp: the streams differ, so agreement is statistical.
+    RMSE(oracle, ref_a) must sit at the reference's own seed-to-seed level RMSE(ref_a, ref_b)."""
+    g = np.load(f"{GOLDEN}/small_{sc}.npz")
+    ra, rb = g["smallhdr_a"], g["smallhdr_b"]
+    H, W = ra.shape[:2]
+    osc = O.OracleScene(golden_scene_path(sc, str(tmp_path)), earth)
+    osc.override(width=96, spp=64)
+    assert (int(osc.camera["image_height"]), int(osc.camera["image_width"])) == (H, W)
+    if sc == 8:
+        osc.override(width=96, spp=16)          # brute-force scene: keep the CPU suite short (noise scaled below)
+    hdr, rgba, st = osc.render(seed=2024)
+    n_or = int(osc.camera["sqrt_spp"]) ** 2
+    n_ref = 64
+    ok = (ra[..., 3] == 0) & (rb[..., 3] == 0) & (hdr[..., 3] == 0)
+    ok &= np.isfinite(ra[..., :3]).all(-1) & np.isfinite(rb[..., :3]).all(-1) & np.isfinite(hdr[..., :3]).all(-1)
+    nan_ref = float(((ra[..., 3] > 0) | ~np.isfinite(ra[..., :3]).all(-1)).mean())
+    nan_or = float(((hdr[..., 3] > 0) | ~np.isfinite(hdr[..., :3]).all(-1)).mean())
+    assert abs(nan_ref - nan_or) <= 0.03 + 0.1 * nan_ref, f"NaN-flushed pixel fraction: oracle {nan_or} vs reference {nan_ref}"
+    if ok.sum() < 200:
+        return
+    a, b, o = ra[..., :3][ok] / n_ref, rb[..., :3][ok] / n_ref, hdr[..., :3][ok] / n_or
+    floor = np.sqrt(((a - b) ** 2).mean())                    # = sqrt(2) sigma_64
+    mine = np.sqrt(((o - a) ** 2).mean())                     # = sqrt(sigma_64^2 + sigma_n^2) if unbiased
+    expect = floor * np.sqrt(0.5 + 0.5 * n_ref / n_or)
+    assert mine <= 1.25 * expect + 1e-4, f"scene {sc}: RMSE vs reference {mine:.5f}, expected about {expect:.5f}"
+    la, lb, lo = luminance(a).mean(), luminance(b).mean(), luminance(o).mean()
+    tol = 4 * abs(la - lb) + 0.02 * la + 1e-4
+    assert abs(lo - la) <= tol, f"scene {sc}: mean luminance oracle {lo:.5f} vs reference {la:.5f} / {lb:.5f}"
+
+
+def test_8bit_frame_semantics(earth, tmp_path):
+    """The 8-bit frame is bottom-up, alpha 255, NaN pixels flushed to 0 (camera.cuh:194-207)."""
+    g = np.load(f"{GOLDEN}/small_7.npz")
+    ref8, rhdr = g["small8_a"], g["smallhdr_a"]
+    # scene 7's bogus light handle (App. A-Q5) turns most pixels NaN; in the reference's own frame they are black
+    nan_px = rhdr[..., 3] > 0
+    assert nan_px.mean() > 0.5 and (ref8[..., 3] == 255).all()
+    osc = O.OracleScene(golden_scene_path(7, str(tmp_path)), earth)
+    osc.override(width=96, spp=64)
+    hdr, rgba, _ = osc.render(seed=1)
+    mine_nan = hdr[..., 3] > 0
+    assert (rgba[..., :3][mine_nan] == 0).all() and (rgba[..., 3] == 255).all()
+    assert abs(mine_nan.mean() - nan_px.mean()) < 0.03
+    # the directly visible lamp is the same white blob in both frames
+    lamp_ref = (ref8[..., :3] > 250).all(-1); lamp_mine = (rgba[..., :3] > 250).all(-1)
+    assert lamp_ref.sum() > 20 and abs(int(lamp_ref.sum()) - int(lamp_mine.sum())) <= 0.1 * lamp_ref.sum() + 4
+    # orientation: sky scenes are brighter at the top = last rows of a bottom-up frame
+    g1 = np.load(f"{GOLDEN}/small_1.npz")["small8_a"]
+    assert g1[-5:, :, 2].mean() > g1[:5, :, 2].mean()
+
+
+def test_sample_split_partitions_the_sample_set(earth, tmp_path):
+    osc = O.OracleScene(golden_scene_path(6, str(tmp_path)), earth)
+    osc.override(width=32, spp=16)
+    full, _, st = osc.render(seed=3, want_rgba8=False)
+    parts = [osc.render(seed=3, sj_mod=2, sj_rem=r, want_rgba8=False) for r in range(2)]
+    assert parts[0][2]["samples"] + parts[1][2]["samples"] == st["samples"]
+    tot = parts[0][0] + parts[1][0]
+    assert np.array_equal(tot[..., 3], full[..., 3])
+    assert np.allclose(tot[..., :3], full[..., :3], rtol=1e-5, atol=1e-5, equal_nan=True)
