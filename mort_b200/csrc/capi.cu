@@ -290,13 +290,13 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         launches = 1;
         ctx->stats.threads_per_block = threads; ctx->stats.blocks_per_sm = bps; ctx->stats.regs_per_thread = regs; ctx->stats.staged_nodes = n_staged;
     } else if (o.mode == MORT_MODE_WAVEFRONT) {
-        int n_paths = o.wavefront_paths > 0 ? o.wavefront_paths : 1 << 21;
+        int n_paths = std::max(o.wavefront_paths > 0 ? o.wavefront_paths : 1 << 21, p.n_pixels);   // at least one slot per pixel
         if (!ctx->wave || ctx->wave_paths != n_paths) {
             wavefront_free(ctx->wave); ctx->wave = nullptr;
             CU(wavefront_alloc(&ctx->wave, n_paths)); ctx->wave_paths = n_paths;
         }
         CU(wavefront_render(p, ctx->wave, n_paths, ctx->prop.multiProcessorCount, ctx->stream, &launches));
-        ctx->stats.threads_per_block = 256; ctx->stats.blocks_per_sm = 0; ctx->stats.staged_nodes = 0;
+        ctx->stats.threads_per_block = 128; ctx->stats.blocks_per_sm = 8; ctx->stats.staged_nodes = 0; ctx->stats.regs_per_thread = 0;
     } else return fail(ctx, MORT_ERR_ARG, "mort_render: unknown mode");
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     unsigned long long cnt[2] = {0, 0};

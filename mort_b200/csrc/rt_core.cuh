@@ -21,10 +21,10 @@
 
 #if defined(__CUDACC__)
 #define MORT_HD __host__ __device__ __forceinline__
-#define MORT_HD_NOINLINE __host__ __device__ __noinline__
+#define MORT_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define MORT_HD inline
-#define MORT_HD_NOINLINE inline
+#define MORT_HD_NOINLINE static inline
 #endif
 
 namespace mort {
@@ -415,9 +415,14 @@ MORT_HD bool medium_hit(const DeviceScene& sc, const Medium& m, const Ray& r, fl
     return true;
 }
 
-// world::hit (world.cuh:104-171): surfaces, then media clipped to the closest surface, then top-level lists
+// world::hit (world.cuh:104-171) in two stages so the megakernel and the wavefront kernels share it:
+//   segment_trace  : surfaces, then media clipped to the closest surface, then top-level lists -> SegHit
+//   segment_record : the hit_record of the winner (surface primitive or medium event)
+#define MORT_PRIM_MEDIUM 0xFFFFFFFEu
+struct SegHit { Hit h; };                         // h.prim == MORT_PRIM_NONE: miss; == MORT_PRIM_MEDIUM: medium event, h.a = medium index bits
+
 template <bool kStaged>
-MORT_HD bool world_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, const Ray& r, Rng& g, Record& rec) {
+MORT_HD void segment_trace(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, const Ray& r, Rng& g, SegHit& out) {
     const float tmin = 0.001f;
     Hit h;
     bool any;
@@ -433,15 +438,26 @@ MORT_HD bool world_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_stag
         Hit h2;
         if (closest_hit<kStaged>(sc, staged, n_staged, r, tmin, closest, h2, sc.post_media_order, 0x7FFFFFFF)) { h = h2; any = true; med = -1; }
     }
-    if (med >= 0) {
-        rec.t = tmed; rec.p = xat(r.o, r.d, tmed); rec.normal = mk3(1, 0, 0); rec.front_face = true;
+    if (med >= 0) { h.t = tmed; h.prim = MORT_PRIM_MEDIUM; h.a = i2f_bits(med); h.b = 0.f; }
+    else if (!any) { h.prim = MORT_PRIM_NONE; }
+    out.h = h;
+}
+MORT_HD int seghit_material(const DeviceScene& sc, const SegHit& sh) {     // material gid of the winner (-1: none)
+    if (sh.h.prim == MORT_PRIM_NONE) return -1;
+    if (sh.h.prim == MORT_PRIM_MEDIUM) return sc.media[f2i_bits(sh.h.a)].mat_gid;
+    uint32_t i = sh.h.prim & 0x07FFFFFFu;
+    if (sh.h.prim & MORT_LEAF_QUAD_BIT) { F4 v = ld4(reinterpret_cast<const float*>(sc.quads + i) + 8); return f2i_bits(v.w); }
+    F4 v = ld4(sc.sphere_info + i); return f2i_bits(v.x);
+}
+MORT_HD void segment_record(const DeviceScene& sc, const Ray& r, const SegHit& sh, Record& rec) {
+    if (sh.h.prim == MORT_PRIM_MEDIUM) {                                 // objects.cuh:425-431
+        int med = f2i_bits(sh.h.a);
+        rec.t = sh.h.t; rec.p = xat(r.o, r.d, sh.h.t); rec.normal = mk3(1, 0, 0); rec.front_face = true;
         rec.mat_gid = sc.media[med].mat_gid; rec.u = rec.v = 0.f; rec.sphere_uv = false;
         rec.leaf_type = MORT_OBJ_CONSTANT_MEDIUM; rec.leaf_idx = sc.media[med].obj_idx;
-        return true;
+        return;
     }
-    if (!any) return false;
-    resolve_hit(sc, r, h, rec);
-    return true;
+    resolve_hit(sc, r, sh.h, rec);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -639,29 +655,37 @@ struct Path { Ray ray; f3 thr; int depth; };
 
 enum { SEG_CONTINUE = 0, SEG_DONE = 1 };
 
-// Advances one segment.  On SEG_DONE `color` is the finished sample (may be NaN/inf, like the reference's).
-// `traced` is set when a closest-hit query was issued (the unit of the Mrays/s metric).
-template <bool kStaged>
-MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const Bvh4Node* staged, int n_staged, Path& P, Rng& g, f3& color, bool& traced) {
-    traced = false;
-    if (P.depth >= cam.bounce_limit) { color = P.thr * mk3(0, 0, 0); return SEG_DONE; }   // camera.cuh:161-163 (0 * inf stays NaN)
-    Record rec;
-    if (isnan3(P.ray.d) || isnan3(P.ray.o)) { color = mk3(NAN, NAN, NAN); return SEG_DONE; }
-    traced = true;
-    if (!world_hit<kStaged>(sc, staged, n_staged, P.ray, g, rec)) {
+// Material classes = the wavefront's shade queues.
+enum { CLASS_TERMINAL = 0, CLASS_DIFFUSE = 1, CLASS_METAL = 2, CLASS_DIELECTRIC = 3, CLASS_ANY = 4 };
+MORT_HD int material_class(const DeviceScene& sc, int mat_gid) {
+    if (mat_gid < 0) return CLASS_TERMINAL;
+    int type = f2i_bits(ld4(sc.materials + mat_gid).x);
+    if (type == MORT_MAT_LAMBERTIAN || type == MORT_MAT_ISOTROPIC) return CLASS_DIFFUSE;
+    if (type == MORT_MAT_METAL) return CLASS_METAL;
+    if (type == MORT_MAT_DIELECTRIC) return CLASS_DIELECTRIC;
+    return CLASS_TERMINAL;                                     // diffuse_light, unknown tags
+}
+
+// Shades one hit (or miss).  On SEG_DONE `color` is the finished sample (may be NaN/inf, like the reference's).
+// kClass prunes the material switch for the per-material wavefront kernels; CLASS_ANY keeps all of it.
+template <int kClass>
+MORT_HD int segment_shade(const DeviceScene& sc, const CameraParams& cam, const SegHit& sh, Path& P, Rng& g, f3& color) {
+    if (sh.h.prim == MORT_PRIM_NONE) {
         color = P.thr * mk3(cam.background[0], cam.background[1], cam.background[2]);   // camera.cuh:154-158
         return SEG_DONE;
     }
+    Record rec;
+    segment_record(sc, P.ray, sh, rec);
     if (rec.mat_gid < 0) { color = P.thr * mk3(0, 0, 0); return SEG_DONE; }             // dispatchers' default: no scatter, no emission
     const Material* M = sc.materials + rec.mat_gid;
     F4 m0 = ld4(M), m1 = ld4(reinterpret_cast<const float*>(M) + 4);
     int type = f2i_bits(m0.x), tex = f2i_bits(m0.y);
-    if (type == MORT_MAT_DIFFUSE_LIGHT) {                                                 // materials.cuh:151-163
+    if ((kClass == CLASS_ANY || kClass == CLASS_TERMINAL) && type == MORT_MAT_DIFFUSE_LIGHT) {   // materials.cuh:151-163
         f3 e = rec.front_face ? texture_value(sc, tex, rec) : mk3(0, 0, 0);
         color = P.thr * e;
         return SEG_DONE;
     }
-    if (type == MORT_MAT_METAL) {                                                         // materials.cuh:73-84
+    if ((kClass == CLASS_ANY || kClass == CLASS_METAL) && type == MORT_MAT_METAL) {      // materials.cuh:73-84
         f3 refl = reflect3(P.ray.d, rec.normal);
         float fuzz = m1.y;
         refl = unit3(refl) + fuzz * random_unit_vector(g);
@@ -669,7 +693,7 @@ MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const B
         P.ray.o = rec.p; P.ray.d = refl; P.depth++;
         return SEG_CONTINUE;
     }
-    if (type == MORT_MAT_DIELECTRIC) {                                                    // materials.cuh:107-130
+    if ((kClass == CLASS_ANY || kClass == CLASS_DIELECTRIC) && type == MORT_MAT_DIELECTRIC) {   // materials.cuh:107-130
         float ratio = rec.front_face ? m1.z : m1.y;
         f3 ud = unit3(P.ray.d);
         float cos_theta = fminf(dot3(-ud, rec.normal), 1.0f);
@@ -681,7 +705,9 @@ MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const B
         P.ray.o = rec.p; P.ray.d = dir; P.depth++;       // attenuation (1,1,1)
         return SEG_CONTINUE;
     }
-    if (type != MORT_MAT_LAMBERTIAN && type != MORT_MAT_ISOTROPIC) { color = P.thr * mk3(0, 0, 0); return SEG_DONE; }
+    if (!(kClass == CLASS_ANY || kClass == CLASS_DIFFUSE) || (type != MORT_MAT_LAMBERTIAN && type != MORT_MAT_ISOTROPIC)) {
+        color = P.thr * mk3(0, 0, 0); return SEG_DONE;
+    }
 
     // lambertian / isotropic: importance-sampled bounce (camera.cuh:115-140, pdf.cuh)
     f3 atten = texture_value(sc, tex, rec);
@@ -707,6 +733,27 @@ MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const B
     P.thr = rp * ((spdf * atten) * P.thr);
     P.ray.o = rec.p; P.ray.d = dir; P.depth++;
     return SEG_CONTINUE;
+}
+
+// A finished path contributes thr * terminal; a path that reaches the bounce limit contributes thr * 0
+// (camera.cuh:161-163; IEEE keeps inf * 0 = NaN exactly like the reference's unwind).
+MORT_HD bool path_exhausted(const CameraParams& cam, const Path& P, f3& color) {
+    if (P.depth < cam.bounce_limit) return false;
+    color = P.thr * mk3(0, 0, 0);
+    return true;
+}
+MORT_HD bool ray_is_nan(const Ray& r) { return isnan3(r.d) || isnan3(r.o); }
+
+// Megakernel form: one whole segment.  `traced` is set when a closest-hit query was issued (the unit of Mrays/s).
+template <bool kStaged>
+MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const Bvh4Node* staged, int n_staged, Path& P, Rng& g, f3& color, bool& traced) {
+    traced = false;
+    if (path_exhausted(cam, P, color)) return SEG_DONE;
+    if (ray_is_nan(P.ray)) { color = mk3(NAN, NAN, NAN); return SEG_DONE; }
+    traced = true;
+    SegHit sh;
+    segment_trace<kStaged>(sc, staged, n_staged, P.ray, g, sh);
+    return segment_shade<CLASS_ANY>(sc, cam, sh, P, g, color);
 }
 
 MORT_HD void path_start(const CameraParams& cam, uint32_t seed, uint32_t frame, int pixel, int s_i, int s_j, Path& P, Rng& g) {
