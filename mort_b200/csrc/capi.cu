@@ -169,13 +169,18 @@ int mort_get_camera(mort_ctx* ctx, mort_camera_desc* o) {
     return MORT_OK;
 }
 int mort_set_camera(mort_ctx* ctx, const mort_camera_desc* d) {
-    CTX_CHECK(ctx && d); invalidate(ctx);
+    CTX_CHECK(ctx && d);
     if (d->image_width < 1 || !(d->aspect_ratio > 0) || d->samples_per_pixel < 1 || d->bounce_limit < 0) return fail(ctx, MORT_ERR_ARG, "mort_set_camera: bad width / aspect / spp / depth");
     Camera& c = ctx->scene.cam;
     c.aspect_ratio = d->aspect_ratio; c.image_width = d->image_width; c.samples_per_pixel = d->samples_per_pixel; c.bounce_limit = d->bounce_limit; c.vfov = d->vfov;
     c.background = v3(d->background); c.lookfrom = v3(d->lookfrom); c.lookat = v3(d->lookat); c.vup = v3(d->vup);
-    c.defocus_angle = d->defocus_angle; c.focus_dist = d->focus_dist; c.light_obj_type = d->light_obj_type; c.light_obj_idx = d->light_obj_idx;
+    c.defocus_angle = d->defocus_angle; c.focus_dist = d->focus_dist;
+    // a camera move keeps the committed geometry (the reference re-runs only cam.initialize() per frame, mort.cu:90);
+    // a different light handle changes the device light table, so it needs a new commit
+    if (c.light_obj_type != d->light_obj_type || c.light_obj_idx != d->light_obj_idx) invalidate(ctx);
+    c.light_obj_type = d->light_obj_type; c.light_obj_idx = d->light_obj_idx;
     c.initialize();
+    if (ctx->committed) camera_params(c, ctx->flat.cam);
     return MORT_OK;
 }
 int mort_override_camera(mort_ctx* ctx, int w, float aspect, int spp, int depth) {

@@ -40,8 +40,8 @@ struct alignas(32) QuadRec {
 
 enum { INST_OP_TRANSLATE = 1, INST_OP_ROTATE_Y = 2 };
 struct alignas(32) Instance {
-    int32_t nops; int32_t kind[3];          // up to 3 ops: covers translate(rotate_y(x)) and one more level
-    float a[3][4];                          // translate: offset xyz ; rotate_y: sin, cos
+    int32_t nops; int32_t pad[3];           // up to 3 ops: covers translate(rotate_y(x)) and one more level
+    float a[3][4];                          // translate: {x,y,z, kind} ; rotate_y: {sin, cos, 0, kind}  (kind as int bits)
 };
 
 struct alignas(32) Material {               // gid = running index over lambertian|metal|dielectric|diffuse_light|isotropic

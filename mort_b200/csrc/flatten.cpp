@@ -27,13 +27,15 @@ struct Flattener {
         Instance I; memset(&I, 0, sizeof(I));
         I.nops = c.n;
         for (int k = 0; k < c.n; k++) {
+            int32_t kind;
             if (c.kind[k] == MORT_OBJ_TRANSLATE) {
-                I.kind[k] = INST_OP_TRANSLATE;
+                kind = INST_OP_TRANSLATE;
                 for (int a = 0; a < 3; a++) I.a[k][a] = s.translates[c.idx[k]].offset[a];
             } else {
-                I.kind[k] = INST_OP_ROTATE_Y;
+                kind = INST_OP_ROTATE_Y;
                 I.a[k][0] = s.rotates[c.idx[k]].sin_theta; I.a[k][1] = s.rotates[c.idx[k]].cos_theta;
             }
+            memcpy(&I.a[k][3], &kind, 4);
         }
         int id = (int)out.instances.size();
         out.instances.push_back(I); inst_ids[c] = id;

@@ -68,7 +68,7 @@ MORT_HD f3 operator*(float t, f3 a) { return mk3(t * a.x, t * a.y, t * a.z); }
 MORT_HD float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 MORT_HD float len2(f3 a) { return dot3(a, a); }
 MORT_HD f3 cross3(f3 u, f3 v) { return mk3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x); }
-MORT_HD f3 unit3(f3 a) { float r = 1.0f / sqrtf(len2(a)); return r * a; }     // vec3.cuh:133-136: (1/len) * v
+MORT_HD f3 unit3(f3 a);                                                           // vec3.cuh:133-136, defined after rsqrt_fast
 MORT_HD bool isnan3(f3 a) { return a.x != a.x || a.y != a.y || a.z != a.z; }
 // exact forms (reference contraction: e2*f2 fused last, first product fused onto the plain middle one)
 MORT_HD float xdot(f3 a, f3 b) { return xfma(a.z, b.z, xfma(a.x, b.x, xmul(a.y, b.y))); }
@@ -85,10 +85,16 @@ struct Ray { f3 o, d; float tm; };
 // Philox4x32-10, canonical stream: key = (seed, frame), counter = (pixel, sample, block, 0);
 // uniforms u = (x >> 8) * 2^-24 consumed in program order (identical to oracle/mort_oracle.c).
 // ---------------------------------------------------------------------------------------------------
-struct Rng { uint32_t k0, k1, pixel, sample, block; uint32_t buf[4]; int have; };
+struct Rng { uint32_t k0, k1, pixel, sample, block; };
+struct U4 { uint32_t x, y, z, w; };
+struct R4 { float x, y, z, w; };
 
-MORT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
-#pragma unroll
+// One Philox block.  Deliberately NOT inlined: a path draws at many sites, and inlined copies of the 10-round
+// block (28 copies, ~2.8 k SASS instructions in the first version) pushed the megakernel out of the
+// instruction cache (profiles/r01_mega_cornell_v1.md: 72 % of stall samples were `no_inst`).
+MORT_HD_NOINLINE U4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) {
+    uint32_t c3 = 0u;
+#pragma unroll 1
     for (int r = 0; r < 10; r++) {
 #if defined(__CUDA_ARCH__)
         uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -101,24 +107,41 @@ MORT_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
         c0 = n0; c1 = l1; c2 = n2; c3 = l0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    U4 o = {c0, c1, c2, c3};
+    return o;
 }
 MORT_HD void rng_init(Rng& g, uint32_t seed, uint32_t frame, uint32_t pixel, uint32_t sample) {
-    g.k0 = seed; g.k1 = frame; g.pixel = pixel; g.sample = sample; g.block = 0; g.have = 0;
+    g.k0 = seed; g.k1 = frame; g.pixel = pixel; g.sample = sample; g.block = 0;
 }
-MORT_HD float rnd(Rng& g) {
-    if (g.have == 0) { philox4x32_10(g.pixel, g.sample, g.block, 0u, g.k0, g.k1, g.buf); g.block++; g.have = 4; }
-    uint32_t x = g.have == 4 ? g.buf[0] : (g.have == 3 ? g.buf[1] : (g.have == 2 ? g.buf[2] : g.buf[3]));
-    g.have--;
-    return (float)(x >> 8) * (1.0f / 16777216.0f);
+// The canonical stream is consumed a block at a time: every stage that draws (camera, one medium free-flight,
+// one scatter stage, one rejection attempt) opens a fresh block and uses its words in order — the oracle's
+// rng_align() points.  No buffered state, no refill branches: the generator is 3 live registers.
+MORT_HD R4 rng_block(Rng& g) {
+    U4 o = philox_block(g.pixel, g.sample, g.block, g.k0, g.k1);
+    g.block++;
+    const float s = 1.0f / 16777216.0f;
+    R4 r = {(float)(o.x >> 8) * s, (float)(o.y >> 8) * s, (float)(o.z >> 8) * s, (float)(o.w >> 8) * s};
+    return r;
 }
-MORT_HD float rnd_range(Rng& g, float lo, float hi) { return rnd(g) * (hi - lo) + lo; }          // rng.cuh:25-28
-MORT_HD int rnd_int(Rng& g, int lo, int hi) {                                                    // rng.cuh:30-42
-    float r = 1.0f - rnd(g);
-    r = (float)((double)r * (hi - lo + 0.999999));
+MORT_HD int rnd_int_from(float u, int lo, int hi) {                                             // rng.cuh:30-42
+    float r = 1.0f - u;                                  // curand_uniform is (0,1] = 1 - [0,1)
+    r = r * (float)(hi - lo + 0.999999);                 // the reference multiplies in double; same index except exactly on a bin edge
     r += (float)lo;
     return (int)truncf(r);
 }
+
+MORT_HD float rsqrt_fast(float x);
+// fast single-precision helpers for SHADING arithmetic only (never for hit decisions)
+#if defined(__CUDA_ARCH__)
+MORT_HD float rsqrt_fast(float x) { return rsqrtf(x); }
+MORT_HD float div_fast(float a, float b) { return __fdividef(a, b); }
+MORT_HD float rcp_fast(float a) { return __frcp_rn(a); }
+#else
+MORT_HD float rsqrt_fast(float x) { return 1.0f / sqrtf(x); }
+MORT_HD float div_fast(float a, float b) { return a / b; }
+MORT_HD float rcp_fast(float a) { return 1.0f / a; }
+#endif
+MORT_HD f3 unit3(f3 a) { float r = rsqrt_fast(len2(a)); return r * a; }
 
 // ---------------------------------------------------------------------------------------------------
 // instance transforms (objects.cuh:268-278, 334-366)
@@ -126,11 +149,11 @@ MORT_HD int rnd_int(Rng& g, int lo, int hi) {                                   
 MORT_HD void ray_to_object(const Instance* insts, int inst, f3& o, f3& d) {
     if (inst < 0) return;
     const Instance* I = insts + inst;
-    F4 hd = ld4(I);                                       // nops, kind[0..2]
-    int nops = f2i_bits(hd.x);
+    const int nops = I->nops;
+#pragma unroll 1
     for (int k = 0; k < nops; k++) {
-        int kind = f2i_bits(k == 0 ? hd.y : (k == 1 ? hd.z : hd.w));
-        F4 a = ld4(&I->a[k][0]);
+        F4 a = ld4(&I->a[k][0]);                          // {x,y,z | sin,cos,-} + op kind in the 4th word
+        const int kind = f2i_bits(a.w);
         if (kind == INST_OP_TRANSLATE) { o = xsub3(o, mk3(a.x, a.y, a.z)); }
         else {
             float s = a.x, c = a.y;
@@ -143,11 +166,11 @@ MORT_HD void ray_to_object(const Instance* insts, int inst, f3& o, f3& d) {
 MORT_HD void record_to_world(const Instance* insts, int inst, f3& p, f3& n) {
     if (inst < 0) return;
     const Instance* I = insts + inst;
-    F4 hd = ld4(I);
-    int nops = f2i_bits(hd.x);
+    const int nops = I->nops;
+#pragma unroll 1
     for (int k = nops - 1; k >= 0; k--) {
-        int kind = f2i_bits(k == 0 ? hd.y : (k == 1 ? hd.z : hd.w));
         F4 a = ld4(&I->a[k][0]);
+        const int kind = f2i_bits(a.w);
         if (kind == INST_OP_TRANSLATE) { p = xadd3(p, mk3(a.x, a.y, a.z)); }
         else {
             float s = a.x, c = a.y;
@@ -262,9 +285,13 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
     const float oix = r.o.x * idx, oiy = r.o.y * idy, oiz = r.o.z * idz;
     uint32_t stack_c[MORT_STACK]; float stack_t[MORT_STACK];
     int sp = 0;
-    uint32_t cur = 0;
-    for (;;) {
-        if (!(cur & MORT_LEAF_BIT)) {
+    uint32_t cur = 0;                                   // root; MORT_CHILD_EMPTY (leaf bit set) = traversal finished
+    // "while-while" (Aila & Laine): an inner loop that only descends internal nodes, then one leaf step.  The
+    // loops are structured (no continue / break across them) so the compiler's convergence barriers sit at
+    // the loop exits: the warp's lanes test nodes together and intersect leaves together instead of drifting
+    // apart for the whole traversal (lane utilisation 6.6/32 with the former single loop).
+    while (cur != MORT_CHILD_EMPTY) {
+        while (!(cur & MORT_LEAF_BIT)) {
             F4 lx, ly, lz, hx, hy, hz, chf;
 #if defined(__CUDA_ARCH__)
             if (kStaged) {
@@ -279,9 +306,8 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
                 const float* n = reinterpret_cast<const float*>(sc.nodes + cur);
                 lx = ld4(n); ly = ld4(n + 4); lz = ld4(n + 8); hx = ld4(n + 12); hy = ld4(n + 16); hz = ld4(n + 20); chf = ld4(n + 24);
             }
-            struct { uint32_t x, y, z, w; } ch = {(uint32_t)f2i_bits(chf.x), (uint32_t)f2i_bits(chf.y), (uint32_t)f2i_bits(chf.z), (uint32_t)f2i_bits(chf.w)};
             (void)staged; (void)n_staged;
-            float tn[4]; uint32_t cw[4] = {ch.x, ch.y, ch.z, ch.w};
+            float tn[4]; uint32_t cw[4] = {(uint32_t)f2i_bits(chf.x), (uint32_t)f2i_bits(chf.y), (uint32_t)f2i_bits(chf.z), (uint32_t)f2i_bits(chf.w)};
             const float lxa[4] = {lx.x, lx.y, lx.z, lx.w}, lya[4] = {ly.x, ly.y, ly.z, ly.w}, lza[4] = {lz.x, lz.y, lz.z, lz.w};
             const float hxa[4] = {hx.x, hx.y, hx.z, hx.w}, hya[4] = {hy.x, hy.y, hy.z, hy.w}, hza[4] = {hz.x, hz.y, hz.z, hz.w};
 #pragma unroll
@@ -293,24 +319,29 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
                 float tfar = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
                 bool h = (tnear <= tfar) && (cw[k] != MORT_CHILD_EMPTY);
                 tn[k] = h ? tnear : INFINITY;
-                if (!h) cw[k] = MORT_CHILD_EMPTY;
+                cw[k] = h ? cw[k] : MORT_CHILD_EMPTY;
             }
-            // sort the 4 (tn, child) pairs ascending: 5-comparator network
-#define MORT_CSWAP(i, j) { if (tn[j] < tn[i]) { float tt = tn[i]; tn[i] = tn[j]; tn[j] = tt; uint32_t cc = cw[i]; cw[i] = cw[j]; cw[j] = cc; } }
+            // sort the 4 (tn, child) pairs ascending: 5-comparator network (misses carry EMPTY + inf and sink)
+#define MORT_CSWAP(i, j) { bool sw = tn[j] < tn[i]; float ta = sw ? tn[j] : tn[i], tb = sw ? tn[i] : tn[j]; uint32_t ca = sw ? cw[j] : cw[i], cb = sw ? cw[i] : cw[j]; tn[i] = ta; tn[j] = tb; cw[i] = ca; cw[j] = cb; }
             MORT_CSWAP(0, 1) MORT_CSWAP(2, 3) MORT_CSWAP(0, 2) MORT_CSWAP(1, 3) MORT_CSWAP(1, 2)
 #undef MORT_CSWAP
-            // misses carry EMPTY + inf and sort to the back; push far-to-near, continue with the nearest
+            // push far-to-near, continue with the nearest; nothing hit -> pop
 #pragma unroll
             for (int k = 3; k >= 1; k--)
                 if (cw[k] != MORT_CHILD_EMPTY && sp < MORT_STACK) { stack_c[sp] = cw[k]; stack_t[sp] = tn[k]; sp++; }
-            if (cw[0] != MORT_CHILD_EMPTY) { cur = cw[0]; continue; }
-        } else {
-            leaf_intersect(sc, cur, r, tmin, best, order_lo, order_hi);
+            uint32_t next = cw[0];
+            if (next == MORT_CHILD_EMPTY) {
+                // entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit
+                while (sp > 0 && next == MORT_CHILD_EMPTY) { sp--; if (stack_t[sp] <= best.t) next = stack_c[sp]; }
+            }
+            cur = next;
         }
-        // pop; entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit
-        bool found = false;
-        while (sp > 0) { sp--; if (stack_t[sp] <= best.t) { cur = stack_c[sp]; found = true; break; } }
-        if (!found) break;
+        if (cur != MORT_CHILD_EMPTY) {
+            leaf_intersect(sc, cur, r, tmin, best, order_lo, order_hi);
+            uint32_t next = MORT_CHILD_EMPTY;
+            while (sp > 0 && next == MORT_CHILD_EMPTY) { sp--; if (stack_t[sp] <= best.t) next = stack_c[sp]; }
+            cur = next;
+        }
     }
     return best.prim != MORT_PRIM_NONE;
 }
@@ -409,10 +440,27 @@ MORT_HD bool medium_hit(const DeviceScene& sc, const Medium& m, const Ray& r, fl
     if (t1 < 0) t1 = 0;
     float ray_length = xsqrt(xdot(r.d, r.d));
     float inside = (t2 - t1) * ray_length;
-    double hit_distance = m.neg_inv_density * (double)logf(rnd(g));
+    double hit_distance = m.neg_inv_density * (double)logf(rng_block(g).x);       // aligned draw (rng_align in the oracle)
     if (hit_distance > (double)inside) return false;
     t_out = (float)((double)t1 + hit_distance / (double)ray_length);
     return true;
+}
+
+MORT_HD_NOINLINE Hit closest_hit_second_pass(const DeviceScene& sc, Ray r, float tmin, float tmax) {
+    Hit h; closest_hit<false>(sc, nullptr, 0, r, tmin, tmax, h, sc.post_media_order, 0x7FFFFFFF);
+    return h;
+}
+
+// all media of the scene in array order, each clipped to the closest event so far (world.cuh:154-160)
+struct MediaOut { Rng g; int med; float t; };
+MORT_HD_NOINLINE MediaOut media_scan(const DeviceScene& sc, Ray r, float tmin, float closest, Rng g) {
+    MediaOut o; o.med = -1; o.t = 0.f;
+    for (int m = 0; m < sc.n_media; m++) {
+        float t;
+        if (medium_hit(sc, sc.media[m], r, tmin, closest, g, t)) { o.med = m; o.t = t; closest = t; }
+    }
+    o.g = g;
+    return o;
 }
 
 // world::hit (world.cuh:104-171) in two stages so the megakernel and the wavefront kernels share it:
@@ -425,18 +473,19 @@ template <bool kStaged>
 MORT_HD void segment_trace(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, const Ray& r, Rng& g, SegHit& out) {
     const float tmin = 0.001f;
     Hit h;
-    bool any;
-    if (!sc.two_pass) any = closest_hit<kStaged>(sc, staged, n_staged, r, tmin, INFINITY, h);
-    else any = closest_hit<kStaged>(sc, staged, n_staged, r, tmin, INFINITY, h, 0, sc.post_media_order);
+    // one traversal; only when media and top-level lists coexist (no shipped scene) is the visit-order window
+    // narrower than everything and a second, out-of-line pass needed
+    bool any = closest_hit<kStaged>(sc, staged, n_staged, r, tmin, INFINITY, h, 0, sc.two_pass ? sc.post_media_order : 0x7FFFFFFF);
     float closest = any ? h.t : INFINITY;
     int med = -1; float tmed = 0.f;
-    for (int m = 0; m < sc.n_media; m++) {
-        float t;
-        if (medium_hit(sc, sc.media[m], r, tmin, closest, g, t)) { med = m; tmed = t; closest = t; }
+    if (sc.n_media > 0) {                                   // cold for most scenes: kept out of line
+        MediaOut mo = media_scan(sc, r, tmin, closest, g);
+        g = mo.g; med = mo.med; tmed = mo.t;
+        if (med >= 0) closest = tmed;
     }
     if (sc.two_pass) {
-        Hit h2;
-        if (closest_hit<kStaged>(sc, staged, n_staged, r, tmin, closest, h2, sc.post_media_order, 0x7FFFFFFF)) { h = h2; any = true; med = -1; }
+        Hit h2 = closest_hit_second_pass(sc, r, tmin, closest);
+        if (h2.prim != MORT_PRIM_NONE) { h = h2; any = true; med = -1; }
     }
     if (med >= 0) { h.t = tmed; h.prim = MORT_PRIM_MEDIUM; h.a = i2f_bits(med); h.b = 0.f; }
     else if (!any) { h.prim = MORT_PRIM_NONE; }
@@ -487,28 +536,20 @@ MORT_HD_NOINLINE float perlin_turb(const NoiseTables* N, f3 p) {                
     return fabsf((float)accum);
 }
 
-MORT_HD f3 texture_value(const DeviceScene& sc, int gid, Record& rec) {               // textures.cuh:327-349
-    for (int guard = 0; guard < 8; guard++) {
-        if (gid < 0) break;
+// image / noise / error textures: rare in the shipped scenes' hot loops, transcendental-heavy -> out of line
+MORT_HD_NOINLINE f3 texture_cold(const DeviceScene& sc, int gid, int need_sphere_uv, f3 outward, float u, float v, f3 p) {
+    if (need_sphere_uv) sphere_uv(outward, u, v);
+    if (gid >= 0) {
         const Texture* T = sc.textures + gid;
         F4 a = ld4(T), b = ld4(reinterpret_cast<const float*>(T) + 4);
         int type = f2i_bits(a.x);
-        if (type == MORT_TEX_SOLID) return mk3(a.y, a.z, a.w);
-        if (type == MORT_TEX_CHECKER) {                                               // textures.cuh:52-60
-            float inv = a.y;
-            int xi = (int)floorf(inv * rec.p.x), yi = (int)floorf(inv * rec.p.y), zi = (int)floorf(inv * rec.p.z);
-            bool even = (xi + yi + zi) % 2 == 0;
-            gid = even ? f2i_bits(b.x) : f2i_bits(b.y);
-            continue;
-        }
-        if (rec.sphere_uv) { sphere_uv(rec.outward, rec.u, rec.v); rec.sphere_uv = false; }
         if (type == MORT_TEX_IMAGE) {                                                 // textures.cuh:129-146
             const ImageDesc im = sc.images[f2i_bits(b.x)];
             if (im.height <= 0 || im.texels == nullptr) return mk3(0, 1, 1);
-            float u = rec.u < 0 ? 0 : (rec.u > 1 ? 1 : rec.u);
-            float vc = rec.v < 0 ? 0 : (rec.v > 1 ? 1 : rec.v);
-            float v = (float)(1.0 - (double)vc);
-            int i = (int)(u * im.width), j = (int)(v * im.height);
+            float uc = u < 0 ? 0 : (u > 1 ? 1 : u);
+            float vc = v < 0 ? 0 : (v > 1 ? 1 : v);
+            float vf = (float)(1.0 - (double)vc);
+            int i = (int)(uc * im.width), j = (int)(vf * im.height);
             if (j > im.height - 1) j = im.height - 1;
             if (j < 0) j = 0;
             int x0 = i * 3; int cmax = im.cols - 1;
@@ -519,15 +560,29 @@ MORT_HD f3 texture_value(const DeviceScene& sc, int gid, Record& rec) {         
         }
         if (type == MORT_TEX_NOISE) {                                                 // textures.cuh:198-202
             const NoiseTables* N = sc.noises + f2i_bits(b.x);
-            f3 s = N->scale * rec.p;
+            f3 s = N->scale * p;
             float f = (float)(1.0 + sin((double)s.z + 10.0 * (double)perlin_turb(N, s)));
             return mk3(0.5f * f, 0.5f * f, 0.5f * f);
         }
-        break;
     }
-    if (rec.sphere_uv) { sphere_uv(rec.outward, rec.u, rec.v); rec.sphere_uv = false; }
-    float e = (float)(((int)floorf(rec.u * 1000.0f) % 2) == ((int)floorf(rec.v * 1000.0f) % 2));   // textures.cuh:347-348
+    float e = (float)(((int)floorf(u * 1000.0f) % 2) == ((int)floorf(v * 1000.0f) % 2));   // textures.cuh:347-348
     return mk3(e, 0.f, e);
+}
+
+MORT_HD f3 texture_value(const DeviceScene& sc, int gid, Record& rec) {               // textures.cuh:327-349
+    for (int guard = 0; guard < 8 && gid >= 0; guard++) {
+        const Texture* T = sc.textures + gid;
+        F4 a = ld4(T);
+        int type = f2i_bits(a.x);
+        if (type == MORT_TEX_SOLID) return mk3(a.y, a.z, a.w);
+        if (type != MORT_TEX_CHECKER) break;
+        F4 b = ld4(reinterpret_cast<const float*>(T) + 4);                            // textures.cuh:52-60
+        float inv = a.y;
+        int xi = (int)floorf(inv * rec.p.x), yi = (int)floorf(inv * rec.p.y), zi = (int)floorf(inv * rec.p.z);
+        bool even = (xi + yi + zi) % 2 == 0;
+        gid = even ? f2i_bits(b.x) : f2i_bits(b.y);
+    }
+    return texture_cold(sc, gid, rec.sphere_uv ? 1 : 0, rec.outward, rec.u, rec.v, rec.p);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -543,27 +598,38 @@ MORT_HD void onb_from_w(Onb& b, f3 w) {
 MORT_HD f3 onb_local(const Onb& b, f3 a) { return a.x * b.u + a.y * b.v + a.z * b.w; }
 MORT_HD f3 random_unit_vector(Rng& g) {
     for (;;) {
-        float x = rnd_range(g, -1, 1), y = rnd_range(g, -1, 1), z = rnd_range(g, -1, 1);
+        R4 b = rng_block(g);                               // one aligned block per rejection attempt
+        float x = b.x * 2.0f - 1.0f, y = b.y * 2.0f - 1.0f, z = b.z * 2.0f - 1.0f;
         f3 p = mk3(x, y, z);
         if (len2(p) >= 1) continue;
         return unit3(p);
     }
 }
-MORT_HD f3 random_cosine_direction(Rng& g) {
-    float r1 = rnd(g), r2 = rnd(g);
-    float phi = (float)(2 * 3.1415926 * (double)r1);
-    float sr = sqrtf(r2);
-    return mk3(cosf(phi) * sr, sinf(phi) * sr, sqrtf(1 - r2));
+// Shading-side arithmetic is single precision: where the reference silently promotes to double through a
+// literal (2 * 3.1415926 * r1, x / 3.1415926, sqrt(1.0 - c*c) ...) the float result differs by at most an ulp,
+// far below Monte-Carlo noise, and FP64 sequences + libm slow paths are what the kernel cannot afford.
+MORT_HD void sincos_fast(float x, float& s, float& c) {
+#if defined(__CUDA_ARCH__)
+    __sincosf(x, &s, &c);
+#else
+    s = sinf(x); c = cosf(x);
+#endif
+}
+MORT_HD f3 random_cosine_direction(float r1, float r2) {
+    float phi = 6.2831852f * r1;                       // 2 * 3.1415926 (vec3.cuh:185)
+    float sr = sqrtf(r2), sn, cs;
+    sincos_fast(phi, sn, cs);
+    return mk3(cs * sr, sn * sr, sqrtf(1 - r2));
 }
 MORT_HD f3 reflect3(f3 v, f3 n) { return v - (2 * dot3(v, n)) * n; }
 MORT_HD f3 refract3(f3 uv, f3 n, float eta) {
     float cos_theta = fminf(dot3(-uv, n), 1.0f);
     f3 perp = eta * (uv + cos_theta * n);
-    f3 par = ((float)(-sqrt(fabs(1.0 - (double)len2(perp))))) * n;
+    f3 par = (-sqrtf(fabsf(1.0f - len2(perp)))) * n;
     return perp + par;
 }
 MORT_HD float reflectance(float cosine, float ref_idx) {
-    float r0 = (1 - ref_idx) / (1 + ref_idx); r0 = r0 * r0;
+    float r0 = div_fast(1 - ref_idx, 1 + ref_idx); r0 = r0 * r0;
     float x = 1 - cosine, x2 = x * x;
     return r0 + (1 - r0) * (x2 * x2 * x);
 }
@@ -575,9 +641,9 @@ MORT_HD float light_prim_pdf(const LightPrim* L, f3 origin, f3 dir) {
         F4 c = ld4(&L->a[0][0]);
         float t;
         if (!sphere_test(mk3(c.x, c.y, c.z), c.w, mk3(0, 0, 0), origin, dir, 0.f, 0.001f, HUGE_VALF, t)) return 0.f;
-        float cos_theta_max = sqrtf(1 - c.w * c.w / len2(mk3(c.x, c.y, c.z) - origin));
-        float solid_angle = (float)(2 * 3.1415926 * (double)(1 - cos_theta_max));
-        return (float)(1.0 / (double)solid_angle);
+        float cos_theta_max = sqrtf(1 - div_fast(c.w * c.w, len2(mk3(c.x, c.y, c.z) - origin)));
+        float solid_angle = 6.2831852f * (1 - cos_theta_max);
+        return 1.0f / solid_angle;
     }
     if (kind == LIGHT_QUAD) {                                                         // objects.cuh:217-229
         float t, al, be;
@@ -585,12 +651,12 @@ MORT_HD float light_prim_pdf(const LightPrim* L, f3 origin, f3 dir) {
         if (!quad_test(nD, &L->a[1][0], origin, dir, 0.001f, HUGE_VALF, t, al, be)) return 0.f;
         float d2 = t * t * len2(dir);
         f3 n = mk3(nD.x, nD.y, nD.z);                  // |dot| is the same for the flipped normal
-        float cosine = fabsf(dot3(dir, n) / sqrtf(len2(dir)));
-        return d2 / (cosine * hd.y);
+        float cosine = fabsf(dot3(dir, n) * rsqrt_fast(len2(dir)));
+        return d2 / (cosine * hd.y);              // IEEE: cosine = 0 must give inf
     }
     return 0.f;
 }
-MORT_HD f3 light_prim_random(const LightPrim* L, f3 origin, Rng& g) {
+MORT_HD f3 light_prim_random(const LightPrim* L, f3 origin, float r1, float r2) {
     F4 hd = ld4(L);
     int kind = f2i_bits(hd.x);
     if (kind == LIGHT_SPHERE) {                                                       // objects.cuh:124-145
@@ -598,15 +664,14 @@ MORT_HD f3 light_prim_random(const LightPrim* L, f3 origin, Rng& g) {
         f3 direction = mk3(c.x, c.y, c.z) - origin;
         float d2 = len2(direction);
         Onb uvw; onb_from_w(uvw, direction);
-        float r1 = rnd(g), r2 = rnd(g);
-        float z = 1 + r2 * (sqrtf(1 - c.w * c.w / d2) - 1);
-        float phi = (float)(2 * 3.141592 * (double)r1);
-        float s = sqrtf(1 - z * z);
-        return onb_local(uvw, mk3(cosf(phi) * s, sinf(phi) * s, z));
+        float z = 1 + r2 * (sqrtf(1 - div_fast(c.w * c.w, d2)) - 1);
+        float phi = 6.283184f * r1;                     // 2 * 3.141592 (objects.cuh:140)
+        float s = sqrtf(1 - z * z), sn, cs;
+        sincos_fast(phi, sn, cs);
+        return onb_local(uvw, mk3(cs * s, sn * s, z));
     }
     if (kind == LIGHT_QUAD) {                                                         // objects.cuh:231-235
         F4 Q = ld4(&L->a[1][0]), U = ld4(&L->a[2][0]), Vv = ld4(&L->a[3][0]);
-        float r1 = rnd(g), r2 = rnd(g);
         f3 p = mk3(Q.x, Q.y, Q.z) + r1 * mk3(U.x, U.y, U.z) + r2 * mk3(Vv.x, Vv.y, Vv.z);
         return p - origin;
     }
@@ -615,15 +680,16 @@ MORT_HD f3 light_prim_random(const LightPrim* L, f3 origin, Rng& g) {
 MORT_HD float light_pdf_value(const DeviceScene& sc, f3 origin, f3 dir) {             // objects.cuh:947-962
     if (sc.light_kind == LIGHT_SPHERE || sc.light_kind == LIGHT_QUAD) return light_prim_pdf(sc.lights, origin, dir);
     if (sc.light_kind == LIGHT_LIST) {
-        float weight = (float)(1.0 / (double)(float)sc.n_lights), sum = 0.f;
+        float weight = 1.0f / (float)sc.n_lights, sum = 0.f;
         for (int i = 0; i < sc.n_lights; i++) sum += weight * light_prim_pdf(sc.lights + i, origin, dir);
         return sum;
     }
     return 0.f;
 }
-MORT_HD f3 light_random(const DeviceScene& sc, f3 origin, Rng& g) {                   // objects.cuh:964-979
-    if (sc.light_kind == LIGHT_SPHERE || sc.light_kind == LIGHT_QUAD) return light_prim_random(sc.lights, origin, g);
-    if (sc.light_kind == LIGHT_LIST) { int k = rnd_int(g, 0, sc.n_lights - 1); return light_prim_random(sc.lights + k, origin, g); }
+// b = the scatter stage's block; b.x was the mixture coin, so the light draws are b.y, b.z, b.w in order
+MORT_HD f3 light_random(const DeviceScene& sc, f3 origin, R4 b) {                     // objects.cuh:964-979
+    if (sc.light_kind == LIGHT_SPHERE || sc.light_kind == LIGHT_QUAD) return light_prim_random(sc.lights, origin, b.y, b.z);
+    if (sc.light_kind == LIGHT_LIST) { int k = rnd_int_from(b.y, 0, sc.n_lights - 1); return light_prim_random(sc.lights + k, origin, b.z, b.w); }
     return mk3(1, 0, 0);
 }
 
@@ -631,20 +697,23 @@ MORT_HD f3 light_random(const DeviceScene& sc, f3 origin, Rng& g) {             
 // camera (camera.cuh:210-242) and one path segment (camera.cuh:96-159, forward form)
 // ---------------------------------------------------------------------------------------------------
 MORT_HD void camera_ray(const CameraParams& c, int x, int y, int s_i, int s_j, Rng& g, Ray& r) {
-    double px = (double)(((float)s_i + rnd(g)) * c.recip_sqrt_spp) - 0.5;
-    double py = (double)(((float)s_j + rnd(g)) * c.recip_sqrt_spp) - 0.5;
-    float ox = (float)px, oy = (float)py;
-    float tu = (float)((double)x + (double)ox), tv = (float)((double)y + (double)oy);
+    // camera.cuh:237-241 + 213 evaluate these in double; every step is a single rounding of an exactly
+    // representable double result, so the float forms below give the same bits
+    R4 b = rng_block(g);                                  // jitter x, jitter y, time (no lens) in one block
+    float ox = xsub(xmul(xadd((float)s_i, b.x), c.recip_sqrt_spp), 0.5f);
+    float oy = xsub(xmul(xadd((float)s_j, b.y), c.recip_sqrt_spp), 0.5f);
+    float tm = b.z;
+    float tu = xadd((float)x, ox), tv = xadd((float)y, oy);
     f3 ps = mk3(xfma(tv, c.dv[0], xfma(tu, c.du[0], c.pixel00[0])), xfma(tv, c.dv[1], xfma(tu, c.du[1], c.pixel00[1])),
                 xfma(tv, c.dv[2], xfma(tu, c.du[2], c.pixel00[2])));
     f3 origin = mk3(c.center[0], c.center[1], c.center[2]);
     if (!(c.defocus_angle <= 0)) {
         float dx, dy;
-        for (;;) { dx = rnd_range(g, -1, 1); dy = rnd_range(g, -1, 1); if (dx * dx + dy * dy < 1) break; }
+        for (;;) { R4 d = rng_block(g); dx = d.x * 2.0f - 1.0f; dy = d.y * 2.0f - 1.0f; tm = d.z; if (dx * dx + dy * dy < 1) break; }
         origin = mk3(xfma(dy, c.defocus_v[0], xfma(dx, c.defocus_u[0], c.center[0])), xfma(dy, c.defocus_v[1], xfma(dx, c.defocus_u[1], c.center[1])),
                      xfma(dy, c.defocus_v[2], xfma(dx, c.defocus_u[2], c.center[2])));
     }
-    r.o = origin; r.d = xsub3(ps, origin); r.tm = rnd(g);
+    r.o = origin; r.d = xsub3(ps, origin); r.tm = tm;
 }
 
 // Path state.  The reference stores (A, E, spdf, pdf) per bounce and unwinds L = E + A*spdf*L/pdf backwards
@@ -697,10 +766,10 @@ MORT_HD int segment_shade(const DeviceScene& sc, const CameraParams& cam, const 
         float ratio = rec.front_face ? m1.z : m1.y;
         f3 ud = unit3(P.ray.d);
         float cos_theta = fminf(dot3(-ud, rec.normal), 1.0f);
-        float sin_theta = (float)sqrt(1.0 - (double)(cos_theta * cos_theta));
+        float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
         bool cant_refract = (ratio * sin_theta) > 1.0f;
         f3 dir;
-        if (cant_refract || reflectance(cos_theta, ratio) > rnd(g)) dir = reflect3(ud, rec.normal);
+        if (cant_refract || reflectance(cos_theta, ratio) > rng_block(g).x) dir = reflect3(ud, rec.normal);
         else dir = refract3(ud, rec.normal, ratio);
         P.ray.o = rec.p; P.ray.d = dir; P.depth++;       // attenuation (1,1,1)
         return SEG_CONTINUE;
@@ -716,20 +785,24 @@ MORT_HD int segment_shade(const DeviceScene& sc, const CameraParams& cam, const 
     if (cosine) onb_from_w(uvw, rec.normal);
     f3 dir; float pdf;
     const float inv4pi = (float)(1 / (4 * 3.1415926));
+    const float inv_pi_a = (float)(1 / 3.1415926), inv_pi_b = (float)(1 / 3.141592565);   // pdf.cuh:48, materials.cuh:54
     if (sc.light_kind == LIGHT_NONE) {
-        dir = cosine ? onb_local(uvw, random_cosine_direction(g)) : random_unit_vector(g);
-        pdf = cosine ? fmaxf(0.f, (float)((double)dot3(unit3(dir), uvw.w) / 3.1415926)) : inv4pi;
+        if (cosine) { R4 b = rng_block(g); dir = onb_local(uvw, random_cosine_direction(b.x, b.y)); }
+        else dir = random_unit_vector(g);
+        pdf = cosine ? fmaxf(0.f, dot3(unit3(dir), uvw.w) * inv_pi_a) : inv4pi;
     } else {
-        if (rnd(g) < 0.5f) dir = light_random(sc, rec.p, g);
-        else dir = cosine ? onb_local(uvw, random_cosine_direction(g)) : random_unit_vector(g);
-        float pm = cosine ? fmaxf(0.f, (float)((double)dot3(unit3(dir), uvw.w) / 3.1415926)) : inv4pi;
-        pdf = (float)(0.5 * (double)light_pdf_value(sc, rec.p, dir) + 0.5 * (double)pm);
+        R4 b = rng_block(g);                                  // mixture coin, then the chosen branch's draws
+        if (b.x < 0.5f) dir = light_random(sc, rec.p, b);
+        else if (cosine) dir = onb_local(uvw, random_cosine_direction(b.y, b.z));
+        else dir = random_unit_vector(g);
+        float pm = cosine ? fmaxf(0.f, dot3(unit3(dir), uvw.w) * inv_pi_a) : inv4pi;
+        pdf = 0.5f * light_pdf_value(sc, rec.p, dir) + 0.5f * pm;
     }
     float spdf;
-    if (cosine) { float ct = dot3(rec.normal, unit3(dir)); spdf = (ct < 0) ? 0.f : (float)((double)ct / 3.141592565); }   // materials.cuh:51-55
+    if (cosine) { float ct = dot3(rec.normal, unit3(dir)); spdf = (ct < 0) ? 0.f : ct * inv_pi_b; }   // materials.cuh:51-55
     else spdf = inv4pi;
     // (attenuation * scattering_pdf * L) / pdf  with vec/scalar = (1/pdf) * vec  (camera.cuh:172, vec3.cuh:109-112)
-    float rp = 1.0f / pdf;
+    float rp = 1.0f / pdf;                                  // IEEE: pdf = 0 must give inf (NaN semantics of camera.cuh:172)
     P.thr = rp * ((spdf * atten) * P.thr);
     P.ray.o = rec.p; P.ray.d = dir; P.depth++;
     return SEG_CONTINUE;

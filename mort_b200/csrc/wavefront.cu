@@ -24,7 +24,7 @@ enum { C_ACTIVE0 = 0, C_ACTIVE1 = 1, C_CLASS0 = 2, /* 2..5 */ C_HEAD_EXTEND = 6,
 struct WavefrontBuffers {
     int n = 0;
     float4 *ray_o = nullptr, *ray_d = nullptr, *thr = nullptr, *hit = nullptr, *acc = nullptr;
-    uint4* rng = nullptr;                       // block, have, next subset sample index, current sample id
+    uint4* rng = nullptr;                       // Philox block counter, -, next subset sample index, current sample id
     uint32_t* q_active[2] = {nullptr, nullptr};
     uint32_t* q_class[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t* counters = nullptr;               // C_N words
@@ -97,8 +97,7 @@ __device__ __forceinline__ void for_each_item(const uint32_t* q, uint32_t count,
 struct SlotState { Path path; Rng g; uint32_t k_next; };
 
 __device__ __forceinline__ void rng_restore(Rng& g, const FrameParams& f, uint32_t pixel, uint4 r) {
-    g.k0 = f.seed; g.k1 = f.frame; g.pixel = pixel; g.sample = r.w; g.block = r.x; g.have = (int)r.y;
-    if (g.have > 0) philox4x32_10(g.pixel, g.sample, g.block - 1u, 0u, g.k0, g.k1, g.buf);     // the partly consumed block
+    g.k0 = f.seed; g.k1 = f.frame; g.pixel = pixel; g.sample = r.w; g.block = r.x;             // block-aligned stream: no buffered words
 }
 __device__ __forceinline__ void load_slot(const WfParams& P, uint32_t slot, SlotState& s) {
     float4 o = P.ray_o[slot], d = P.ray_d[slot], t = P.thr[slot]; uint4 r = P.rng[slot];
@@ -111,7 +110,7 @@ __device__ __forceinline__ void store_slot(const WfParams& P, uint32_t slot, con
     P.ray_o[slot] = make_float4(s.path.ray.o.x, s.path.ray.o.y, s.path.ray.o.z, s.path.ray.tm);
     P.ray_d[slot] = make_float4(s.path.ray.d.x, s.path.ray.d.y, s.path.ray.d.z, 0.f);
     P.thr[slot] = make_float4(s.path.thr.x, s.path.thr.y, s.path.thr.z, __int_as_float(s.path.depth));
-    P.rng[slot] = make_uint4(s.g.block, (uint32_t)s.g.have, s.k_next, s.g.sample);
+    P.rng[slot] = make_uint4(s.g.block, 0u, s.k_next, s.g.sample);
 }
 
 // Brings a slot to its next traceable segment: finishes samples that are already decided (bounce limit,
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(128) wf_extend(const __grid_constant__ WfParam
             SegHit sh;
             segment_trace<false>(P.f.sc, nullptr, 0, r, g, sh);
             n_seg++;
-            if (need_rng) P.rng[slot] = make_uint4(g.block, (uint32_t)g.have, rs.z, rs.w);
+            if (need_rng) P.rng[slot] = make_uint4(g.block, 0u, rs.z, rs.w);
             P.hit[slot] = make_float4(sh.h.t, __uint_as_float(sh.h.prim), sh.h.a, sh.h.b);
             cls = material_class(P.f.sc, seghit_material(P.f.sc, sh));
         }

@@ -11,8 +11,11 @@
  * Two deliberate substitutions, both dictated by BASELINE.json's north_star:
  *   * RNG: cuRAND XORWOW per-pixel state (rng.cuh) -> counter-based Philox4x32-10, key = (seed, frame),
  *     counter = (pixel, sample, block, 0), uniforms u = (x >> 8) * 2^-24 in [0,1) consumed in the reference's
- *     program order.  The product uses the identical stream, so product-vs-oracle images agree far below
- *     Monte-Carlo noise, while oracle-vs-reference agreement is statistical.
+ *     program order, with ALIGNMENT POINTS (rng_align: the rest of the current block is discarded, the next
+ *     draw opens a new block) at the start of every scatter stage, before every medium free-flight draw and
+ *     before every attempt of a rejection loop.  Alignment makes every stage's draws "word k of a fresh
+ *     block" — which is how the product indexes them statically.  The product uses the identical stream, so
+ *     product-vs-oracle images agree far below Monte-Carlo noise; oracle-vs-reference agreement is statistical.
  *   * Primitive ids: hit_record (hit_record.cuh:10-17) has none; this restatement carries (type, slot) of
  *     the sphere / quad that produced the record.
  *
@@ -88,6 +91,7 @@ static float random_float(rng_t* g) {                /* replaces rng.cuh:17-22; 
     uint32_t x = g->buf[4 - g->have]; g->have--;
     return (float)(x >> 8) * (1.0f / 16777216.0f);
 }
+static void rng_align(rng_t* g) { g->have = 0; }    /* canonical stream: the next draw is word 0 of a fresh block */
 static float random_float_range(rng_t* g, float lo, float hi) { return random_float(g) * (hi - lo) + lo; }  /* rng.cuh:25-28 */
 static int random_int(rng_t* g, int lo, int hi) {    /* rng.cuh:30-42: curand_uniform is (0,1] = 1 - [0,1) */
     float r = 1.0f - random_float(g);
@@ -289,6 +293,7 @@ static int medium_hit(const oracle_scene* S, const mscn_medium* m, const ray_t* 
     if (rec1.t < 0) rec1.t = 0;
     float ray_length = vlen(r->d);
     float distance_inside = (rec2.t - rec1.t) * ray_length;
+    rng_align(g);
     double hit_distance = m->neg_inv_density * (double)logf(random_float(g));
     if (hit_distance > (double)distance_inside) return 0;
     rec->t = (float)(rec1.t + hit_distance / ray_length);
@@ -475,6 +480,7 @@ static v3 onb_local(const onb_t* b, v3 a) {       /* a.x*u + a.y*v + a.z*w with 
 }
 static v3 random_in_unit_sphere(rng_t* g) {
     for (;;) {
+        rng_align(g);
         float x = random_float_range(g, -1, 1), y = random_float_range(g, -1, 1), z = random_float_range(g, -1, 1);
         v3 p = V(x, y, z);
         if (vlen2(p) >= 1) continue;
@@ -484,6 +490,7 @@ static v3 random_in_unit_sphere(rng_t* g) {
 static v3 random_unit_vector(rng_t* g) { return vunit(random_in_unit_sphere(g)); }
 static v3 random_in_unit_disk(rng_t* g) {
     for (;;) {
+        rng_align(g);
         float x = random_float_range(g, -1, 1), y = random_float_range(g, -1, 1);
         v3 p = V(x, y, 0);
         if (vlen2(p) < 1) return p;
@@ -653,6 +660,7 @@ static v3 ray_color(const oracle_scene* S, const ray_t* r, rng_t* g, uint64_t* s
         if (world_hit(S, &cur, 0.001f, INFINITY, &rec, g, 1, NULL, NULL)) {
             ray_t scattered; v3 emission = emit_dispatch(S, &rec);
             float pdf, scattering_pdf; scatter_rec sr;
+            rng_align(g);                                  /* scatter stage */
             if (scatter_dispatch(S, &cur, &rec, &sr, g)) {
                 if (sr.skip_pdf) {
                     cur = sr.skip_ray; att[iter] = sr.attenuation; em[iter] = V(0, 0, 0); spdf[iter] = 1.0f; pdfv[iter] = 1.0f;

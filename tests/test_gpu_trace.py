@@ -31,7 +31,9 @@ def _check(out, ref, what, probes=None, ref_probes=None, check_top=True):
     assert (bits(out["p"])[b] == bits(ref["p"])[b]).all(), f"{what}: hit points not bit-equal"
     assert (bits(out["normal"])[b] == bits(ref["normal"])[b]).all(), f"{what}: normals not bit-equal"
     # u,v go through acosf/atan2f (libm): a few ulp
-    assert np.abs(out["u"] - ref["u"])[b].max(initial=0) <= 4e-7 and np.abs(out["v"] - ref["v"])[b].max(initial=0) <= 4e-7
+    for k in ("u", "v"):                               # acosf(-y) is NaN on both sides when rounding pushes |y| past 1
+        both_nan = np.isnan(out[k]) & np.isnan(ref[k])
+        assert np.abs(np.where(both_nan, 0, out[k] - ref[k]))[b].max(initial=0) <= 4e-7, k
     if probes is not None and ref_probes is not None and ref_probes.size:
         for k in ("hit1", "hit2"):
             assert (probes[k] == ref_probes[k]).all(), f"{what}: medium probe {k} differs"
