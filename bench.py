@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--depth", type=int, default=WORKLOAD["depth"])
     ap.add_argument("--aspect", type=float, default=0.0)
     ap.add_argument("--stage", type=int, default=-1)
+    ap.add_argument("--bps", type=int, default=0, help="megakernel blocks per SM (selects the register-capped variant)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -190,7 +191,7 @@ def run_mort(a):
     def step(i, timed):
         nonlocal seg_total, ker_ms, launches
         flush.zero_()                                                       # L2 flush between iterations
-        r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage)
+        r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps)
         s = r.stats
         if world > 1:
             D.combine(accum, how="reduce")
@@ -229,11 +230,11 @@ def run_mort(a):
     host_rgba = torch.empty(H, W, 4, dtype=torch.uint8).pin_memory()
     e2e_ms = None
     if world == 1:
-        r.render_into(host_rgba.data_ptr(), 0, seed=69420, frame=0, mode=mode, stage_nodes=a.stage)      # warm
+        r.render_into(host_rgba.data_ptr(), 0, seed=69420, frame=0, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps)      # warm
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(a.steps):
-            r.render_into(host_rgba.data_ptr(), 0, seed=69420, frame=a.warmup + i, mode=mode, stage_nodes=a.stage)
+            r.render_into(host_rgba.data_ptr(), 0, seed=69420, frame=a.warmup + i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps)
             _ = int(host_rgba[0, 0, 3])                                        # touch the result on the host
         e2e_ms = (time.perf_counter() - t0) * 1e3
     else:
@@ -242,7 +243,7 @@ def run_mort(a):
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(a.steps):
-            r.render_device(accum.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage)
+            r.render_device(accum.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps)
             D.combine(accum, how="reduce")
             if rank == 0:
                 r.tonemap_device(accum.data_ptr(), n_spp, rgba.data_ptr())

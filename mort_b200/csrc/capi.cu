@@ -17,6 +17,8 @@
 
 using namespace mort;
 
+#define MORT_DEFAULT_BLOCKS_PER_SM 4      // megakernel occupancy target (register-capped variant); see profiles/
+
 namespace {
 
 struct DeviceArena {                 // every device allocation of one committed scene
@@ -224,7 +226,7 @@ int mort_commit(mort_ctx* ctx) {
     CU(ctx->arena.upload(f.media, &d.media)); d.n_media = (int)f.media.size();
     CU(ctx->arena.upload(f.boundary, &d.boundary)); d.n_boundary = (int)f.boundary.size();
     CU(ctx->arena.upload(f.lights, &d.lights)); d.n_lights = (int)f.lights.size(); d.light_kind = f.light_kind;
-    d.post_media_order = f.post_media_order; d.two_pass = f.two_pass; d.empty = f.empty;
+    d.post_media_order = f.post_media_order; d.two_pass = f.two_pass; d.empty = f.empty; d.linear = f.linear;
     ctx->dscene = d;
     const Scene& s = ctx->scene;
     int32_t off[8] = {0, 0, (int32_t)s.lambertians.size(), 0, 0, 0, 0, 0};
@@ -266,8 +268,10 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     p.n_rows = cam.sqrt_spp > o.sample_rem ? (cam.sqrt_spp - o.sample_rem + o.sample_mod - 1) / o.sample_mod : 0;
     p.n_subset = p.n_rows * cam.sqrt_spp;
     p.n_pixels = cam.width * cam.height;
-    int G = 1; while (G < 32 && G < p.n_subset) G <<= 1;
-    p.lanes_per_pixel = G;
+    // pixels per warp task: enough samples per task (~2048) to amortise the end-of-task tail, at most 16 pixels
+    int PT = p.n_subset > 0 ? (2048 + p.n_subset - 1) / p.n_subset : 1;
+    PT = std::max(1, std::min(16, PT));
+    p.lanes_per_pixel = PT;
     p.accum = reinterpret_cast<float4*>(d_accum);
     p.counters = ctx->d_counters; p.work_counter = ctx->d_work;
 
@@ -287,11 +291,12 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     if (o.mode == MORT_MODE_MEGAKERNEL) {
         int occ = 0, regs = 0;
-        CU(mega_query(threads, n_staged, &occ, &regs));
+        const int min_blocks = o.blocks_per_sm > 0 ? o.blocks_per_sm : MORT_DEFAULT_BLOCKS_PER_SM;   // selects the register-capped variant
+        CU(mega_query(threads, n_staged, min_blocks, &occ, &regs));
         if (occ < 1) return fail(ctx, MORT_ERR_CUDA, "megakernel does not fit on an SM with this configuration");
         int bps = o.blocks_per_sm > 0 ? std::min(o.blocks_per_sm, occ) : occ;
         LaunchShape sh; sh.threads = threads; sh.blocks = bps * ctx->prop.multiProcessorCount; sh.smem_bytes = n_staged * (int)sizeof(Bvh4Node);
-        CU(mega_launch(p, sh, ctx->stream));
+        CU(mega_launch(p, sh, min_blocks, ctx->stream));
         launches = 1;
         ctx->stats.threads_per_block = threads; ctx->stats.blocks_per_sm = bps; ctx->stats.regs_per_thread = regs; ctx->stats.staged_nodes = n_staged;
     } else if (o.mode == MORT_MODE_WAVEFRONT) {

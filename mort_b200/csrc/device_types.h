@@ -99,6 +99,7 @@ struct DeviceScene {
     int32_t post_media_order;                // leaves with order >= this are visited after the media (top-level lists)
     int32_t two_pass;                        // 1 when media and post-media leaves coexist
     int32_t empty;                           // no visible primitive at all
+    int32_t linear;                          // few leaves: records sorted by instance, scanned linearly (no tree)
 };
 
 }  // namespace mort

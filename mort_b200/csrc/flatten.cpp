@@ -3,7 +3,10 @@
 
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 #include <map>
+
+#define MORT_LINEAR_MAX_LEAVES 40      // == MORT_LINEAR_MAX in rt_core.cuh
 
 namespace mort {
 namespace {
@@ -263,7 +266,23 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
     out.stats.pad = pad; out.stats.scene_extent = M; out.stats.n_leaves = (int)out.leaves.size();
 
     std::vector<int> order;
-    build_bvh4(prims, out.nodes, order, out.stats);
+    if ((int)prims.size() <= MORT_LINEAR_MAX_LEAVES) {
+        // a handful of primitives: no tree.  Records sorted by (instance, visit order) so consecutive records
+        // share the object-space ray; the kernels scan them in lockstep.
+        out.linear = 1;
+        order.resize(prims.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            if (out.leaves[a].inst != out.leaves[b].inst) return out.leaves[a].inst < out.leaves[b].inst;
+            return out.leaves[a].order < out.leaves[b].order;
+        });
+        Bvh4Node n; memset(&n, 0, sizeof(n));
+        for (int k = 0; k < 4; k++) { n.lox[k] = n.loy[k] = n.loz[k] = INFINITY; n.hix[k] = n.hiy[k] = n.hiz[k] = -INFINITY; n.child[k] = MORT_CHILD_EMPTY; }
+        out.nodes.assign(1, n);
+        out.stats.n_nodes = 1; out.stats.max_depth = 0;
+    } else {
+        build_bvh4(prims, out.nodes, order, out.stats);
+    }
 
     // ---- emit primitive records in leaf order; rewrite leaf child words to per-type record indices ----
     std::vector<int> rec_index(order.size());

@@ -34,7 +34,7 @@ struct FlatScene {
     std::vector<LightPrim> lights;
     std::vector<LeafRef> leaves;               // visit order (kept for tests / stats)
     int light_kind = LIGHT_NONE;
-    int post_media_order = 0, two_pass = 0, empty = 1;
+    int post_media_order = 0, two_pass = 0, empty = 1, linear = 0;
     CameraParams cam;
     BuildStats stats;
 };

@@ -11,12 +11,13 @@
 #include "mort_b200.h"
 
 static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
-                            "            [--mode mega|wave] [--stage N] [--assets DIR] [--out image.ppm] [--device K]\n"); return -1; }
+                            "            [--mode mega|wave] [--stage N] [--bps blocks/SM] [--tpb threads] [--field G [--fieldcam 0|1]]\n"
+                            "            [--assets DIR] [--out image.ppm] [--device K]\n"); return -1; }
 
 int main(int argc, char** argv) {
     if (argc < 2) return usage();                       // mort.cu:638-641
     int scene = atoi(argv[1]);
-    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = -1, mode = MORT_MODE_MEGAKERNEL;
+    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = -1, mode = MORT_MODE_MEGAKERNEL, bps = 0, tpb = 0, field = 0, fieldcam = 0;
     float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
@@ -26,18 +27,21 @@ int main(int argc, char** argv) {
         else if (a == "--seed") seed = (unsigned)strtoul(nx(), 0, 10); else if (a == "--frames") frames = atoi(nx());
         else if (a == "--assets") assets = nx(); else if (a == "--out") out = nx(); else if (a == "--device") device = atoi(nx());
         else if (a == "--stage") stage = atoi(nx());
+        else if (a == "--bps") bps = atoi(nx()); else if (a == "--tpb") tpb = atoi(nx());
+        else if (a == "--field") field = atoi(nx()); else if (a == "--fieldcam") fieldcam = atoi(nx());
         else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : MORT_MODE_MEGAKERNEL; }
         else return usage();
     }
     mort_ctx* ctx = nullptr;
     if (mort_create(device, &ctx) != MORT_OK) { fprintf(stderr, "mort: no usable CUDA device %d (this renderer has no CPU path)\n", device); return 2; }
     auto die = [&](const char* what) { fprintf(stderr, "mort: %s: %s\n", what, mort_last_error(ctx)); mort_destroy(ctx); return 3; };
-    if (mort_build_scene(ctx, scene, assets.c_str()) != MORT_OK) return die("scene");
+    if (field > 0) { if (mort_build_sphere_field(ctx, field, 69420, fieldcam) != MORT_OK) return die("sphere field"); }
+    else if (mort_build_scene(ctx, scene, assets.c_str()) != MORT_OK) return die("scene");
     if (mort_override_camera(ctx, width, aspect, spp, depth) != MORT_OK) return die("camera");
     if (mort_commit(ctx) != MORT_OK) return die("commit");
     mort_stats st; mort_get_stats(ctx, &st);
     std::vector<uint8_t> img((size_t)st.width * st.height * 4);
-    mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.stage_nodes = stage;
+    mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.stage_nodes = stage; o.blocks_per_sm = bps; o.threads_per_block = tpb;
     double total = 0;
     for (int f = 0; f < frames; f++) {
         o.frame = (uint32_t)f;
@@ -47,9 +51,9 @@ int main(int argc, char** argv) {
         printf("Avg. time per frame: %3.1f ms\n", total / (f + 1));
     }
     double samples = (double)st.width * st.height * st.sqrt_spp * st.sqrt_spp;
-    printf("{\"scene\":%d,\"width\":%d,\"height\":%d,\"spp_eff\":%d,\"depth\":%d,\"ms\":%.3f,\"msamples_per_s\":%.3f,\"mrays_per_s\":%.3f,\"nodes\":%d,\"leaves\":%d}\n",
+    printf("{\"scene\":%d,\"width\":%d,\"height\":%d,\"spp_eff\":%d,\"depth\":%d,\"ms\":%.3f,\"msamples_per_s\":%.3f,\"mrays_per_s\":%.3f,\"nodes\":%d,\"leaves\":%d,\"regs\":%d,\"bps\":%d,\"build_ms\":%.2f}\n",
            scene, st.width, st.height, st.sqrt_spp * st.sqrt_spp, st.bounce_limit, st.last_render_ms, samples / (st.last_render_ms * 1e3),
-           (double)st.last_segments / (st.last_render_ms * 1e3), st.n_nodes, st.n_leaves);
+           (double)st.last_segments / (st.last_render_ms * 1e3), st.n_nodes, st.n_leaves, st.regs_per_thread, st.blocks_per_sm, st.build_ms);
     if (!out.empty()) {
         FILE* f = fopen(out.c_str(), "wb");
         if (!f) { perror(out.c_str()); mort_destroy(ctx); return 4; }

@@ -15,9 +15,37 @@
 namespace mort {
 
 // ------------------------------------------------------------------------------------------------------
-template <bool kStaged>
-__global__ void __launch_bounds__(128) mega_kernel(const __grid_constant__ FrameParams P) {
+// Exact, order-independent accumulation.  A finished sample is added as Q31.32 fixed point into 64-bit
+// integers (integer addition is associative: ANY distribution of a pixel's samples over lanes, warps, waves or
+// schedules gives the same bits), with NaN / +inf samples counted on the side so the frame keeps the IEEE
+// semantics of the reference's float sum (camera.cuh:190-198: one NaN sample poisons the pixel).
+//   word 0..2 : sum of r, g, b   (samples >= 2^30 are counted as +inf: they saturate the 8-bit frame anyway)
+//   word 3    : [0,20) NaN samples  [20,34) +inf in r  [34,48) +inf in g  [48,62) +inf in b
+// ------------------------------------------------------------------------------------------------------
+#define MEGA_PMAX 16
+__device__ __forceinline__ void fx_add(long long& acc, unsigned long long& flags, float v, int inf_shift) {
+    if (v != v) return;                                                    // NaN: counted once per sample by the caller
+    if (!(fabsf(v) < 1073741824.0f)) { flags += 1ull << inf_shift; return; }
+    acc += __float2ll_rn(v * 4294967296.0f);
+}
+__device__ __forceinline__ float4 fx_resolve(long long r, long long g, long long b, unsigned long long flags) {
+    const float s = 1.0f / 4294967296.0f;
+    const unsigned nan_n = (unsigned)(flags & 0xFFFFFu);
+    float4 o;
+    o.x = __ll2float_rn(r) * s; o.y = __ll2float_rn(g) * s; o.z = __ll2float_rn(b) * s; o.w = (float)nan_n;
+    if ((flags >> 20) & 0x3FFFu) o.x = INFINITY;
+    if ((flags >> 34) & 0x3FFFu) o.y = INFINITY;
+    if ((flags >> 48) & 0x3FFFu) o.z = INFINITY;
+    if (nan_n) { o.x = o.y = o.z = __int_as_float(0x7fc00000); }
+    return o;
+}
+
+// kMinBlocks = occupancy target handed to ptxas (register cap 65536 / (128 * kMinBlocks)): 4 -> 128 regs,
+// 6 -> 80, 8 -> 64.  Which one wins is a measurement (profiles/), selectable through mort_render_opts.blocks_per_sm.
+template <bool kStaged, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ unsigned long long part[4][MEGA_PMAX][4];                    // per warp: per task pixel: r, g, b, flags
     const Bvh4Node* staged = reinterpret_cast<const Bvh4Node*>(smem_raw);
     if (kStaged) {
         float4* dst = reinterpret_cast<float4*>(smem_raw);
@@ -27,31 +55,50 @@ __global__ void __launch_bounds__(128) mega_kernel(const __grid_constant__ Frame
         __syncthreads();
     }
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int G = P.lanes_per_pixel, ppw = 32 / G;
-    const int lp = lane / G, ls = lane - lp * G;
-    const int sqrt_spp = P.cam.sqrt_spp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int PT = P.lanes_per_pixel;                     // pixels per warp task (1..MEGA_PMAX)
+    const int sqrt_spp = P.cam.sqrt_spp, n_subset = P.n_subset;
     unsigned long long n_seg = 0, n_smp = 0;
 
+    // A warp task = PT consecutive pixels = PT * n_subset samples in pixel-major order.  Lanes pull the next
+    // sample the moment their path ends (ballot + prefix count: deterministic, no atomics), so the warp only
+    // idles in the last few iterations of a task instead of after every lane's private quota.
     for (;;) {
         int base = 0;
-        if (lane == 0) base = (int)atomicAdd(P.work_counter, (unsigned)ppw);
+        if (lane == 0) base = (int)atomicAdd(P.work_counter, (unsigned)PT);
         base = __shfl_sync(full, base, 0);
         if (base >= P.n_pixels) break;
-        const int pixel = base + lp;
-        const bool valid = pixel < P.n_pixels;
-        int k = ls;                                    // index into this call's sample subset
-        float ax = 0.f, ay = 0.f, az = 0.f, an = 0.f;
+        const int npx = min(PT, P.n_pixels - base);
+        const int items = npx * n_subset;
+        if (lane < npx * 4) part[warp][lane >> 2][lane & 3] = 0ull;
+        if (lane + 32 < npx * 4) part[warp][(lane + 32) >> 2][(lane + 32) & 3] = 0ull;
+        __syncwarp();
+        int next = 0;                                     // warp-uniform: next unassigned sample of the task
+        int cur_p = -1;                                   // task pixel this lane's registers accumulate for
+        long long ar = 0, ag = 0, ab = 0; unsigned long long af = 0ull;
         bool alive = false;
         Path path; Rng g;
         path.depth = 0; path.thr = mk3(1, 1, 1); path.ray.o = path.ray.d = mk3(0, 0, 0); path.ray.tm = 0.f;
         rng_init(g, 0, 0, 0, 0);
         for (;;) {
-            if (!alive && valid && k < P.n_subset) {
-                const int row = k / sqrt_spp;
-                const int s_i = k - row * sqrt_spp, s_j = P.sj_rem + row * P.sj_mod;
-                path_start(P.cam, P.seed, P.frame, pixel, s_i, s_j, path, g);
-                alive = true; k += G; n_smp++;
+            const unsigned need = __ballot_sync(full, !alive);
+            if (need != 0u && next < items) {
+                const int idx = next + __popc(need & lt_mask);
+                next += __popc(need);
+                if (!alive && idx < items) {
+                    const int p = idx / n_subset, k = idx - p * n_subset;
+                    if (p != cur_p) {
+                        if (cur_p >= 0) {                 // pixel switch: hand the finished partial sums over
+                            atomicAdd(&part[warp][cur_p][0], (unsigned long long)ar); atomicAdd(&part[warp][cur_p][1], (unsigned long long)ag);
+                            atomicAdd(&part[warp][cur_p][2], (unsigned long long)ab); atomicAdd(&part[warp][cur_p][3], af);
+                        }
+                        ar = ag = ab = 0; af = 0ull; cur_p = p;
+                    }
+                    const int row = k / sqrt_spp;
+                    path_start(P.cam, P.seed, P.frame, base + p, k - row * sqrt_spp, P.sj_rem + row * P.sj_mod, path, g);
+                    alive = true; n_smp++;
+                }
             }
             if (__ballot_sync(full, alive) == 0u) break;
             if (alive) {
@@ -59,45 +106,53 @@ __global__ void __launch_bounds__(128) mega_kernel(const __grid_constant__ Frame
                 const int st = path_segment<kStaged>(P.sc, P.cam, staged, P.n_staged, path, g, col, traced);
                 n_seg += traced ? 1u : 0u;
                 if (st == SEG_DONE) {
-                    ax += col.x; ay += col.y; az += col.z;            // IEEE: a NaN sample poisons the channel (camera.cuh:190-198)
-                    an += isnan3(col) ? 1.f : 0.f;
+                    if (isnan3(col)) af += 1ull;
+                    else { fx_add(ar, af, col.x, 20); fx_add(ag, af, col.y, 34); fx_add(ab, af, col.z, 48); }
                     alive = false;
                 }
             }
         }
-        for (int off = G >> 1; off > 0; off >>= 1) {
-            ax += __shfl_xor_sync(full, ax, off); ay += __shfl_xor_sync(full, ay, off);
-            az += __shfl_xor_sync(full, az, off); an += __shfl_xor_sync(full, an, off);
+        if (cur_p >= 0) {
+            atomicAdd(&part[warp][cur_p][0], (unsigned long long)ar); atomicAdd(&part[warp][cur_p][1], (unsigned long long)ag);
+            atomicAdd(&part[warp][cur_p][2], (unsigned long long)ab); atomicAdd(&part[warp][cur_p][3], af);
         }
-        if (ls == 0 && valid) P.accum[pixel] = make_float4(ax, ay, az, an);
+        __syncwarp();
+        if (lane < npx)
+            P.accum[base + lane] = fx_resolve((long long)part[warp][lane][0], (long long)part[warp][lane][1], (long long)part[warp][lane][2], part[warp][lane][3]);
+        __syncwarp();
     }
     for (int off = 16; off > 0; off >>= 1) { n_seg += __shfl_xor_sync(full, n_seg, off); n_smp += __shfl_xor_sync(full, n_smp, off); }
     if (lane == 0) { atomicAdd(P.counters, n_seg); atomicAdd(P.counters + 1, n_smp); }
 }
 
-cudaError_t mega_query(int threads, int n_staged, int* max_blocks_per_sm, int* regs) {
+typedef void (*MegaFn)(const FrameParams);
+static MegaFn mega_variant(bool staged, int min_blocks) {
+    if (staged) return min_blocks >= 7 ? (MegaFn)mega_kernel<true, 8> : (min_blocks >= 5 ? (MegaFn)mega_kernel<true, 6> : (MegaFn)mega_kernel<true, 4>);
+    return min_blocks >= 7 ? (MegaFn)mega_kernel<false, 8> : (min_blocks >= 5 ? (MegaFn)mega_kernel<false, 6> : (MegaFn)mega_kernel<false, 4>);
+}
+
+cudaError_t mega_query(int threads, int n_staged, int min_blocks, int* max_blocks_per_sm, int* regs) {
+    MegaFn fn = mega_variant(n_staged > 0, min_blocks);
     cudaFuncAttributes fa;
-    cudaError_t e = n_staged > 0 ? cudaFuncGetAttributes(&fa, mega_kernel<true>) : cudaFuncGetAttributes(&fa, mega_kernel<false>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, (const void*)fn);
     if (e != cudaSuccess) return e;
     if (regs) *regs = fa.numRegs;
     size_t smem = (size_t)n_staged * sizeof(Bvh4Node);
     if (n_staged > 0) {
-        e = cudaFuncSetAttribute(mega_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, mega_kernel<true>, threads, smem);
     }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, mega_kernel<false>, threads, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, (const void*)fn, threads, smem);
 }
 
-cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, cudaStream_t st) {
+cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, int min_blocks, cudaStream_t st) {
+    MegaFn fn = mega_variant(p.n_staged > 0, min_blocks);
     if (p.n_staged > 0) {
-        cudaError_t e = cudaFuncSetAttribute(mega_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shape.smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, shape.smem_bytes);
         if (e != cudaSuccess) return e;
-        mega_kernel<true><<<shape.blocks, shape.threads, shape.smem_bytes, st>>>(p);
-    } else {
-        mega_kernel<false><<<shape.blocks, shape.threads, 0, st>>>(p);
     }
-    return cudaGetLastError();
+    void* args[] = {(void*)&p};
+    return cudaLaunchKernel((const void*)fn, dim3(shape.blocks), dim3(shape.threads), args, (size_t)shape.smem_bytes, st);
 }
 
 // ------------------------------------------------------------------------------------------------------

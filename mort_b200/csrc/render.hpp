@@ -15,7 +15,7 @@ struct FrameParams {
     int32_t sj_mod, sj_rem;         // sample-split: strata rows s_j % sj_mod == sj_rem
     int32_t n_rows;                 // strata rows this call renders
     int32_t n_subset;               // samples per pixel this call renders = n_rows * sqrt_spp
-    int32_t lanes_per_pixel;        // power of two <= 32
+    int32_t lanes_per_pixel;        // megakernel: pixels per warp task (1..16)
     int32_t n_pixels;
     int32_t n_staged;               // BVH nodes copied to shared memory per block
     float4* accum;                  // W*H
@@ -26,8 +26,8 @@ struct FrameParams {
 struct LaunchShape { int threads, blocks, smem_bytes; };
 
 // megakernel (render.cu)
-cudaError_t mega_query(int threads, int n_staged, int* max_blocks_per_sm, int* regs);
-cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, cudaStream_t st);
+cudaError_t mega_query(int threads, int n_staged, int min_blocks, int* max_blocks_per_sm, int* regs);
+cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, int min_blocks, cudaStream_t st);
 
 // wavefront (wavefront.cu)
 struct WavefrontBuffers;            // opaque SoA queues

@@ -267,6 +267,34 @@ MORT_HD void leaf_intersect(const DeviceScene& sc, uint32_t w, const Ray& r, flo
     }
 }
 
+// Small scenes (<= MORT_LINEAR_MAX leaves; records sorted by instance): every lane walks the same record
+// sequence, so the warp stays in lockstep and the loads are warp-uniform broadcasts — for a dozen primitives
+// this beats any tree (profiles/r01_mega_cornell_v2.md: in the BVH loops only half of the live lanes did work).
+#define MORT_LINEAR_MAX 40
+MORT_HD void closest_hit_linear(const DeviceScene& sc, const Ray& r, float tmin, Hit& best, int order_lo, int order_hi) {
+    int cur_inst = -1; f3 o = r.o, d = r.d;
+#pragma unroll 1
+    for (int i = 0; i < sc.n_spheres; i++) {
+        const float* s = reinterpret_cast<const float*>(sc.spheres + i);
+        F4 c = ld4(s), v = ld4(s + 4);
+        const int inst = f2i_bits(v.w);
+        if (inst != cur_inst) { o = r.o; d = r.d; ray_to_object(sc.instances, inst, o, d); cur_inst = inst; }
+        float t;
+        if (sphere_test(mk3(c.x, c.y, c.z), c.w, mk3(v.x, v.y, v.z), o, d, r.tm, tmin, best.t, t))
+            consider(sc, best, t, MORT_LEAF_BIT | (uint32_t)i, 0.f, 0.f, order_lo, order_hi);
+    }
+#pragma unroll 1
+    for (int i = 0; i < sc.n_quads; i++) {
+        const float* q = reinterpret_cast<const float*>(sc.quads + i);
+        F4 nD = ld4(q), Qi = ld4(q + 4);
+        const int inst = f2i_bits(Qi.w);
+        if (inst != cur_inst) { o = r.o; d = r.d; ray_to_object(sc.instances, inst, o, d); cur_inst = inst; }
+        float t, al, be;
+        if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be))
+            consider(sc, best, t, MORT_LEAF_BIT | MORT_LEAF_QUAD_BIT | (uint32_t)i, al, be, order_lo, order_hi);
+    }
+}
+
 MORT_HD float safe_rcp_dir(float d) {
     // axis-parallel rays: keep the slab arithmetic finite (inf * 0 would make NaN); 1e-20 tilts the ray by
     // far less than the box padding
@@ -281,6 +309,7 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
                          int order_lo = 0, int order_hi = 0x7FFFFFFF) {
     best.t = tmax; best.prim = MORT_PRIM_NONE; best.a = best.b = 0.f;
     if (sc.empty) return false;
+    if (sc.linear) { closest_hit_linear(sc, r, tmin, best, order_lo, order_hi); return best.prim != MORT_PRIM_NONE; }
     const float idx = safe_rcp_dir(r.d.x), idy = safe_rcp_dir(r.d.y), idz = safe_rcp_dir(r.d.z);
     const float oix = r.o.x * idx, oiy = r.o.y * idy, oiz = r.o.z * idz;
     uint32_t stack_c[MORT_STACK]; float stack_t[MORT_STACK];

@@ -29,7 +29,7 @@ static DeviceScene make_device_scene(const Scene& s, const FlatScene& f, std::ve
     d.media = f.media.data(); d.n_media = (int)f.media.size();
     d.boundary = f.boundary.data(); d.n_boundary = (int)f.boundary.size();
     d.lights = f.lights.data(); d.n_lights = (int)f.lights.size(); d.light_kind = f.light_kind;
-    d.post_media_order = f.post_media_order; d.two_pass = f.two_pass; d.empty = f.empty;
+    d.post_media_order = f.post_media_order; d.two_pass = f.two_pass; d.empty = f.empty; d.linear = f.linear;
     return d;
 }
 
