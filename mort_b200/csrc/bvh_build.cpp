@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <queue>
@@ -41,7 +42,9 @@ struct Builder {
     std::vector<int> idx;
     std::vector<Node2> nodes;
     int max_depth = 0;
+    int max_leaf = MORT_MAX_LEAF;
     explicit Builder(const std::vector<BuildPrim>& p) : prims(p) {
+        if (const char* e = getenv("MORT_MAX_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) max_leaf = v; }   // experiments only
         idx.resize(p.size());
         for (size_t i = 0; i < p.size(); i++) idx[i] = (int)i;
         nodes.reserve(p.size() * 2 + 1);
@@ -64,7 +67,7 @@ struct Builder {
         }
         nodes[me].box = box;
         int n = e - b;
-        bool can_leaf = n <= MORT_MAX_LEAF && homogeneous;
+        bool can_leaf = n <= max_leaf && homogeneous;
 
         // best binned SAH split
         float best_cost = std::numeric_limits<float>::infinity(); int best_axis = -1, best_bin = -1;

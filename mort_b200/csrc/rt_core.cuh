@@ -206,7 +206,11 @@ MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3
     f3 n = mk3(nD.x, nD.y, nD.z);
     float denom = xdot(n, d);
     if (fabsf(denom) <= 1e-8f) return false;          // == ((double)fabsf(denom) < 1e-8): 1e-8f is the largest float below 1e-8
-    float t = xdiv(xsub(nD.w, xdot(n, o)), denom);
+    const float num = xsub(nD.w, xdot(n, o));
+    // a ray leaving a surface has its origin on that surface's plane: num ~ 0, and the IEEE division would take its
+    // slow path.  |num| < tmin/2 * |denom| implies |t| < tmin, i.e. the reference rejects it (t < t_min) as well.
+    if (tmin > 0.f && fabsf(num) < 0.5f * tmin * fabsf(denom)) return false;
+    float t = xdiv(num, denom);
     if (t < tmin || t > tmax) return false;
     F4 Q = ld4(rec), U = ld4(rec + 4), Vv = ld4(rec + 8), W = ld4(rec + 12);
     f3 P = xat(o, d, t);
@@ -767,7 +771,7 @@ MORT_HD int material_class(const DeviceScene& sc, int mat_gid) {
 // Shades one hit (or miss).  On SEG_DONE `color` is the finished sample (may be NaN/inf, like the reference's).
 // kClass prunes the material switch for the per-material wavefront kernels; CLASS_ANY keeps all of it.
 template <int kClass>
-MORT_HD int segment_shade(const DeviceScene& sc, const CameraParams& cam, const SegHit& sh, Path& P, Rng& g, f3& color) {
+MORT_HD int segment_shade(const DeviceScene& sc, const CameraParams& cam, const SegHit& sh, Path& P, Rng& g, const R4& sb, f3& color) {
     if (sh.h.prim == MORT_PRIM_NONE) {
         color = P.thr * mk3(cam.background[0], cam.background[1], cam.background[2]);   // camera.cuh:154-158
         return SEG_DONE;
@@ -798,7 +802,7 @@ MORT_HD int segment_shade(const DeviceScene& sc, const CameraParams& cam, const 
         float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
         bool cant_refract = (ratio * sin_theta) > 1.0f;
         f3 dir;
-        if (cant_refract || reflectance(cos_theta, ratio) > rng_block(g).x) dir = reflect3(ud, rec.normal);
+        if (cant_refract || reflectance(cos_theta, ratio) > sb.x) dir = reflect3(ud, rec.normal);
         else dir = refract3(ud, rec.normal, ratio);
         P.ray.o = rec.p; P.ray.d = dir; P.depth++;       // attenuation (1,1,1)
         return SEG_CONTINUE;
@@ -816,13 +820,13 @@ MORT_HD int segment_shade(const DeviceScene& sc, const CameraParams& cam, const 
     const float inv4pi = (float)(1 / (4 * 3.1415926));
     const float inv_pi_a = (float)(1 / 3.1415926), inv_pi_b = (float)(1 / 3.141592565);   // pdf.cuh:48, materials.cuh:54
     if (sc.light_kind == LIGHT_NONE) {
-        if (cosine) { R4 b = rng_block(g); dir = onb_local(uvw, random_cosine_direction(b.x, b.y)); }
+        if (cosine) dir = onb_local(uvw, random_cosine_direction(sb.x, sb.y));
         else dir = random_unit_vector(g);
         pdf = cosine ? fmaxf(0.f, dot3(unit3(dir), uvw.w) * inv_pi_a) : inv4pi;
     } else {
-        R4 b = rng_block(g);                                  // mixture coin, then the chosen branch's draws
-        if (b.x < 0.5f) dir = light_random(sc, rec.p, b);
-        else if (cosine) dir = onb_local(uvw, random_cosine_direction(b.y, b.z));
+        // sb = the bounce's stage block: mixture coin, then the chosen branch's draws
+        if (sb.x < 0.5f) dir = light_random(sc, rec.p, sb);
+        else if (cosine) dir = onb_local(uvw, random_cosine_direction(sb.y, sb.z));
         else dir = random_unit_vector(g);
         float pm = cosine ? fmaxf(0.f, dot3(unit3(dir), uvw.w) * inv_pi_a) : inv4pi;
         pdf = 0.5f * light_pdf_value(sc, rec.p, dir) + 0.5f * pm;
@@ -853,9 +857,12 @@ MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const B
     if (path_exhausted(cam, P, color)) return SEG_DONE;
     if (ray_is_nan(P.ray)) { color = mk3(NAN, NAN, NAN); return SEG_DONE; }
     traced = true;
+    // the bounce's stage block is generated here, by every live lane together, whether or not the shading
+    // below ends up drawing from it (one convergent Philox call instead of one per divergent material branch)
+    const R4 sb = rng_block(g);
     SegHit sh;
     segment_trace<kStaged>(sc, staged, n_staged, P.ray, g, sh);
-    return segment_shade<CLASS_ANY>(sc, cam, sh, P, g, color);
+    return segment_shade<CLASS_ANY>(sc, cam, sh, P, g, sb, color);
 }
 
 MORT_HD void path_start(const CameraParams& cam, uint32_t seed, uint32_t frame, int pixel, int s_i, int s_j, Path& P, Rng& g) {

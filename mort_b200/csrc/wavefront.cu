@@ -169,13 +169,14 @@ __global__ void __launch_bounds__(128) wf_extend(const __grid_constant__ WfParam
         if (valid) {
             float4 o = P.ray_o[slot], d = P.ray_d[slot];
             Ray r; r.o = mk3(o.x, o.y, o.z); r.tm = o.w; r.d = mk3(d.x, d.y, d.z);
-            Rng g; uint4 rs = make_uint4(0, 0, 0, 0);
-            const bool need_rng = P.f.sc.n_media > 0;                 // only media draw random numbers while tracing
-            if (need_rng) { rs = P.rng[slot]; rng_restore(g, P.f, slot / (uint32_t)P.S, rs); } else rng_init(g, 0, 0, 0, 0);
+            // canonical stream: the bounce's stage block comes first (wf_shade regenerates it from block - 1 ... see
+            // rng.y), then the media draws of this segment
+            Rng g; uint4 rs = P.rng[slot]; rng_restore(g, P.f, slot / (uint32_t)P.S, rs);
+            const uint32_t stage_block = g.block; g.block++;
             SegHit sh;
             segment_trace<false>(P.f.sc, nullptr, 0, r, g, sh);
             n_seg++;
-            if (need_rng) P.rng[slot] = make_uint4(g.block, 0u, rs.z, rs.w);
+            P.rng[slot] = make_uint4(g.block, stage_block, rs.z, rs.w);
             P.hit[slot] = make_float4(sh.h.t, __uint_as_float(sh.h.prim), sh.h.a, sh.h.b);
             cls = material_class(P.f.sc, seghit_material(P.f.sc, sh));
         }
@@ -197,7 +198,9 @@ __global__ void __launch_bounds__(128) wf_shade(const __grid_constant__ WfParams
             float4 hv = P.hit[slot];
             SegHit sh; sh.h.t = hv.x; sh.h.prim = __float_as_uint(hv.y); sh.h.a = hv.z; sh.h.b = hv.w;
             f3 color = mk3(0, 0, 0);
-            const int st = segment_shade<kClass>(P.f.sc, P.f.cam, sh, s.path, s.g, color);
+            Rng sgen = s.g; sgen.block = P.rng[slot].y;                       // the stage block reserved by wf_extend
+            const R4 sb = kClass == CLASS_TERMINAL || kClass == CLASS_METAL ? R4{0.f, 0.f, 0.f, 0.f} : rng_block(sgen);
+            const int st = segment_shade<kClass>(P.f.sc, P.f.cam, sh, s.path, s.g, sb, color);
             float4 acc = P.acc[slot];
             active = settle_slot(P, slot, s, true, st == SEG_DONE, color, acc, n_smp);
             P.acc[slot] = acc;

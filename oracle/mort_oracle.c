@@ -12,9 +12,12 @@
  *   * RNG: cuRAND XORWOW per-pixel state (rng.cuh) -> counter-based Philox4x32-10, key = (seed, frame),
  *     counter = (pixel, sample, block, 0), uniforms u = (x >> 8) * 2^-24 in [0,1) consumed in the reference's
  *     program order, with ALIGNMENT POINTS (rng_align: the rest of the current block is discarded, the next
- *     draw opens a new block) at the start of every scatter stage, before every medium free-flight draw and
- *     before every attempt of a rejection loop.  Alignment makes every stage's draws "word k of a fresh
- *     block" — which is how the product indexes them statically.  The product uses the identical stream, so
+ *     draw opens a new block) before every medium free-flight draw and before every attempt of a rejection
+ *     loop; the (at most four) non-loop draws of a bounce's scatter stage — mixture coin, light pick, r1, r2,
+ *     or the dielectric's reflectance draw — come from ONE block that is generated at the top of the bounce,
+ *     before the closest-hit query, whether or not the bounce ends up using it (so all lanes of a warp can
+ *     generate it together).  Every draw is therefore "word k of a known block", which is how the product
+ *     indexes them statically.  The product uses the identical stream, so
  *     product-vs-oracle images agree far below Monte-Carlo noise; oracle-vs-reference agreement is statistical.
  *   * Primitive ids: hit_record (hit_record.cuh:10-17) has none; this restatement carries (type, slot) of
  *     the sphere / quad that produced the record.
@@ -582,7 +585,7 @@ static v3 random_dispatch(const oracle_scene* S, int type, int idx, v3 origin, r
 enum { PDF_NONE = 0, PDF_COSINE = 1, PDF_SPHERE = 2 };
 typedef struct { v3 attenuation; int pdf_kind; onb_t uvw; int skip_pdf; ray_t skip_ray; } scatter_rec;
 
-static int scatter_dispatch(const oracle_scene* S, const ray_t* r_in, const hitrec* rec, scatter_rec* sr, rng_t* g) {   /* materials.cuh:272-296 */
+static int scatter_dispatch(const oracle_scene* S, const ray_t* r_in, const hitrec* rec, scatter_rec* sr, rng_t* g, rng_t* sg) {   /* materials.cuh:272-296 */
     switch (rec->mat_type) {
         case MORT_MAT_LAMBERTIAN: {                                                   /* materials.cuh:38-44 */
             const mscn_lambertian* m = &S->lam[rec->mat_idx];
@@ -607,7 +610,7 @@ static int scatter_dispatch(const oracle_scene* S, const ray_t* r_in, const hitr
             float sin_theta = (float)sqrt(1.0 - cos_theta * cos_theta);
             int cant_refract = (double)(ratio * sin_theta) > 1.0;
             v3 dir;
-            if (cant_refract || reflectance(cos_theta, ratio) > random_float(g)) dir = reflect(ud, rec->normal);
+            if (cant_refract || reflectance(cos_theta, ratio) > random_float(sg)) dir = reflect(ud, rec->normal);
             else dir = refract(ud, rec->normal, ratio);
             sr->skip_ray.o = rec->p; sr->skip_ray.d = dir; sr->skip_ray.tm = r_in->tm;
             return 1;
@@ -642,9 +645,9 @@ static float mat_pdf_value(const scatter_rec* sr, v3 dir) {                     
     if (sr->pdf_kind == PDF_COSINE) { float c = vdot(vunit(dir), sr->uvw.w); return fmaxf(0, (float)(c / 3.1415926)); }
     return (float)(1 / (4 * 3.1415926));
 }
-static v3 mat_pdf_generate(const scatter_rec* sr, rng_t* g) {                         /* pdf.cuh:35-37, 52-54 */
-    if (sr->pdf_kind == PDF_COSINE) return onb_local(&sr->uvw, random_cosine_direction(g));
-    return random_unit_vector(g);
+static v3 mat_pdf_generate(const scatter_rec* sr, rng_t* g, rng_t* sg) {              /* pdf.cuh:35-37, 52-54 */
+    if (sr->pdf_kind == PDF_COSINE) return onb_local(&sr->uvw, random_cosine_direction(sg));
+    return random_unit_vector(g);                       /* rejection loop: own aligned blocks */
 }
 
 /* Camera::ray_color, camera.cuh:86-176 (forward pass into per-bounce arrays, then the unwind) */
@@ -657,22 +660,24 @@ static v3 ray_color(const oracle_scene* S, const ray_t* r, rng_t* g, uint64_t* s
     int iter = 0; ray_t cur = *r; v3 final = V(0, 0, 0);
     while (iter < limit) {
         (*segments)++;
+        /* canonical stream: this bounce's stage block, generated before the closest-hit query */
+        rng_t sg = *g; rng_align(&sg); (void)random_float(&sg); sg.have = 4;      /* sg.buf = block, nothing consumed yet */
+        g->ctr[2] = sg.ctr[2]; rng_align(g);                                       /* the main stream continues after it */
         if (world_hit(S, &cur, 0.001f, INFINITY, &rec, g, 1, NULL, NULL)) {
             ray_t scattered; v3 emission = emit_dispatch(S, &rec);
             float pdf, scattering_pdf; scatter_rec sr;
-            rng_align(g);                                  /* scatter stage */
-            if (scatter_dispatch(S, &cur, &rec, &sr, g)) {
+            if (scatter_dispatch(S, &cur, &rec, &sr, g, &sg)) {
                 if (sr.skip_pdf) {
                     cur = sr.skip_ray; att[iter] = sr.attenuation; em[iter] = V(0, 0, 0); spdf[iter] = 1.0f; pdfv[iter] = 1.0f;
                     iter++; continue;
                 }
                 if (cam->light_obj_type == -1) {
-                    scattered.o = rec.p; scattered.d = mat_pdf_generate(&sr, g); scattered.tm = r->tm;
+                    scattered.o = rec.p; scattered.d = mat_pdf_generate(&sr, g, &sg); scattered.tm = r->tm;
                     pdf = mat_pdf_value(&sr, scattered.d);
                 } else {                                                             /* pdf.cuh:85-103 */
                     v3 dir;
-                    if (random_float(g) < 0.5f) dir = random_dispatch(S, cam->light_obj_type, cam->light_obj_idx, rec.p, g);
-                    else dir = mat_pdf_generate(&sr, g);
+                    if (random_float(&sg) < 0.5f) dir = random_dispatch(S, cam->light_obj_type, cam->light_obj_idx, rec.p, &sg);
+                    else dir = mat_pdf_generate(&sr, g, &sg);
                     scattered.o = rec.p; scattered.d = dir; scattered.tm = r->tm;
                     pdf = (float)(0.5 * pdf_value_dispatch(S, cam->light_obj_type, cam->light_obj_idx, rec.p, dir) + 0.5 * mat_pdf_value(&sr, dir));
                 }
