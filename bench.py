@@ -148,7 +148,7 @@ def cpu_baseline(a):
     from mort_b200 import formats as F
     earth = F.read_ppm(os.path.join(ROOT, "mort_b200", "assets", "earthmap.ppm"))
     osc = O.OracleScene(tmp, earth)
-    w, spp = 96, 256
+    w, spp = 192, 1024                                         # ~10 s of CPU work on 16 threads
     osc.override(width=w, spp=spp, depth=a.depth)
     cores = os.cpu_count() or 1
     t0 = time.time()
@@ -255,6 +255,7 @@ def run_mort(a):
         del part
 
     if rank == 0:
+        st2 = r.stats
         clocks = cs.summary()
         peaks = {}
         try:
@@ -285,8 +286,8 @@ def run_mort(a):
                          "how": f"algorithmic {FLOP_PER_RAY:.0f} FLOP per path segment (SURVEY.md §8d, config 2) x segments per launch / CUDA-event kernel time; "
                                 f"peak = {st['sm_count']} SMs x 128 lanes x 2 x median SM clock under load (the path is neither HBM- nor tensor-bound)",
                          "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
-            "kernel": {"regs": st["regs_per_thread"], "threads_per_block": st["threads_per_block"], "blocks_per_sm": st["blocks_per_sm"],
-                       "staged_nodes": st["staged_nodes"], "bvh_nodes": st["n_nodes"], "leaves": st["n_leaves"]},
+            "kernel": {"regs": st2["regs_per_thread"], "threads_per_block": st2["threads_per_block"], "blocks_per_sm": st2["blocks_per_sm"],
+                       "staged_nodes": st2["staged_nodes"], "bvh_nodes": st2["n_nodes"], "leaves": st2["n_leaves"], "linear_scan": st2["n_nodes"] == 1},
         }
         if world == 1 and not a.no_cpu_baseline:
             try:
