@@ -46,6 +46,8 @@ template <bool kStaged, int kMinBlocks>
 __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long part[4][MEGA_PMAX][4];                    // per warp: per task pixel: r, g, b, flags
+    __shared__ unsigned long long lacc[4][4][32];                           // per warp: r, g, b, flags of every lane's current pixel
+                                                                            // (shared memory instead of 8 live registers per lane; lane-private, conflict-free)
     const Bvh4Node* staged = reinterpret_cast<const Bvh4Node*>(smem_raw);
     if (kStaged) {
         float4* dst = reinterpret_cast<float4*>(smem_raw);
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
     const unsigned lt_mask = (1u << lane) - 1u;
     const int PT = P.lanes_per_pixel;                     // pixels per warp task (1..MEGA_PMAX)
     const int sqrt_spp = P.cam.sqrt_spp, n_subset = P.n_subset;
-    unsigned long long n_seg = 0, n_smp = 0;
+    unsigned n_seg = 0, n_smp = 0;                        // per task, flushed to the 64-bit global counters at task end
 
     // A warp task = PT consecutive pixels = PT * n_subset samples in pixel-major order.  Lanes pull the next
     // sample the moment their path ends (ballot + prefix count: deterministic, no atomics), so the warp only
@@ -75,8 +77,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
         if (lane + 32 < npx * 4) part[warp][(lane + 32) >> 2][(lane + 32) & 3] = 0ull;
         __syncwarp();
         int next = 0;                                     // warp-uniform: next unassigned sample of the task
-        int cur_p = -1;                                   // task pixel this lane's registers accumulate for
-        long long ar = 0, ag = 0, ab = 0; unsigned long long af = 0ull;
+        int cur_p = -1;                                   // task pixel this lane currently accumulates for (in lacc)
+        lacc[warp][0][lane] = 0ull; lacc[warp][1][lane] = 0ull; lacc[warp][2][lane] = 0ull; lacc[warp][3][lane] = 0ull;
         bool alive = false;
         Path path; Rng g;
         path.depth = 0; path.thr = mk3(1, 1, 1); path.ray.o = path.ray.d = mk3(0, 0, 0); path.ray.tm = 0.f;
@@ -90,10 +92,10 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
                     const int p = idx / n_subset, k = idx - p * n_subset;
                     if (p != cur_p) {
                         if (cur_p >= 0) {                 // pixel switch: hand the finished partial sums over
-                            atomicAdd(&part[warp][cur_p][0], (unsigned long long)ar); atomicAdd(&part[warp][cur_p][1], (unsigned long long)ag);
-                            atomicAdd(&part[warp][cur_p][2], (unsigned long long)ab); atomicAdd(&part[warp][cur_p][3], af);
+#pragma unroll
+                            for (int c = 0; c < 4; c++) { atomicAdd(&part[warp][cur_p][c], lacc[warp][c][lane]); lacc[warp][c][lane] = 0ull; }
                         }
-                        ar = ag = ab = 0; af = 0ull; cur_p = p;
+                        cur_p = p;
                     }
                     const int row = k / sqrt_spp;
                     path_start(P.cam, P.seed, P.frame, base + p, k - row * sqrt_spp, P.sj_rem + row * P.sj_mod, path, g);
@@ -106,23 +108,30 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
                 const int st = path_segment<kStaged>(P.sc, P.cam, staged, P.n_staged, path, g, col, traced);
                 n_seg += traced ? 1u : 0u;
                 if (st == SEG_DONE) {
-                    if (isnan3(col)) af += 1ull;
-                    else { fx_add(ar, af, col.x, 20); fx_add(ag, af, col.y, 34); fx_add(ab, af, col.z, 48); }
+                    unsigned long long af = 0ull;
+                    if (isnan3(col)) af = 1ull;
+                    else {
+                        long long dr = 0, dg = 0, db = 0;
+                        fx_add(dr, af, col.x, 20); fx_add(dg, af, col.y, 34); fx_add(db, af, col.z, 48);
+                        lacc[warp][0][lane] += (unsigned long long)dr; lacc[warp][1][lane] += (unsigned long long)dg; lacc[warp][2][lane] += (unsigned long long)db;
+                    }
+                    if (af) lacc[warp][3][lane] += af;
                     alive = false;
                 }
             }
         }
         if (cur_p >= 0) {
-            atomicAdd(&part[warp][cur_p][0], (unsigned long long)ar); atomicAdd(&part[warp][cur_p][1], (unsigned long long)ag);
-            atomicAdd(&part[warp][cur_p][2], (unsigned long long)ab); atomicAdd(&part[warp][cur_p][3], af);
+#pragma unroll
+            for (int c = 0; c < 4; c++) atomicAdd(&part[warp][cur_p][c], lacc[warp][c][lane]);
         }
         __syncwarp();
         if (lane < npx)
             P.accum[base + lane] = fx_resolve((long long)part[warp][lane][0], (long long)part[warp][lane][1], (long long)part[warp][lane][2], part[warp][lane][3]);
         __syncwarp();
+        for (int off = 16; off > 0; off >>= 1) { n_seg += __shfl_xor_sync(full, n_seg, off); n_smp += __shfl_xor_sync(full, n_smp, off); }
+        if (lane == 0) { atomicAdd(P.counters, (unsigned long long)n_seg); atomicAdd(P.counters + 1, (unsigned long long)n_smp); }
+        n_seg = 0; n_smp = 0;
     }
-    for (int off = 16; off > 0; off >>= 1) { n_seg += __shfl_xor_sync(full, n_seg, off); n_smp += __shfl_xor_sync(full, n_smp, off); }
-    if (lane == 0) { atomicAdd(P.counters, n_seg); atomicAdd(P.counters + 1, n_smp); }
 }
 
 typedef void (*MegaFn)(const FrameParams);

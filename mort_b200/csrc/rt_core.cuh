@@ -202,7 +202,10 @@ MORT_HD bool sphere_test(f3 c, float r, f3 vel, f3 o, f3 d, float tm, float tmin
     t_out = root;
     return true;
 }
-MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3 d, float tmin, float tmax, float& t_out, float& alpha, float& beta) {
+// `pre` (may be null) = the record's {v x w}, {w x u} rows: a cheap estimate of (alpha, beta) that discards candidates
+// clearly outside the quad; everything that survives goes through the reference's exact expressions.
+MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3 d, float tmin, float tmax, float& t_out, float& alpha, float& beta,
+                       const float* pre = nullptr) {
     f3 n = mk3(nD.x, nD.y, nD.z);
     float denom = xdot(n, d);
     if (fabsf(denom) <= 1e-8f) return false;          // == ((double)fabsf(denom) < 1e-8): 1e-8f is the largest float below 1e-8
@@ -212,9 +215,17 @@ MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3
     if (tmin > 0.f && fabsf(num) < 0.5f * tmin * fabsf(denom)) return false;
     float t = xdiv(num, denom);
     if (t < tmin || t > tmax) return false;
-    F4 Q = ld4(rec), U = ld4(rec + 4), Vv = ld4(rec + 8), W = ld4(rec + 12);
+    F4 Q = ld4(rec);
     f3 P = xat(o, d, t);
     f3 hp = xsub3(P, mk3(Q.x, Q.y, Q.z));
+    if (pre) {
+        // both forms evaluate the same real number; inside or near the quad every term is O(1), so they agree to ~1e-6:
+        // a 1e-3 margin can never discard a candidate the exact test would accept
+        F4 A = ld4(pre), B = ld4(pre + 4);
+        float ac = hp.x * A.x + hp.y * A.y + hp.z * A.z, bc = hp.x * B.x + hp.y * B.y + hp.z * B.z;
+        if (ac < -1e-3f || ac > 1.001f || bc < -1e-3f || bc > 1.001f) return false;
+    }
+    F4 U = ld4(rec + 4), Vv = ld4(rec + 8), W = ld4(rec + 12);
     f3 w = mk3(W.x, W.y, W.z);
     float al = xdot(w, xcross(hp, mk3(Vv.x, Vv.y, Vv.z)));
     float be = xdot(w, xcross(mk3(U.x, U.y, U.z), hp));
@@ -255,7 +266,7 @@ MORT_HD void leaf_intersect(const DeviceScene& sc, uint32_t w, const Ray& r, flo
             f3 o = r.o, d = r.d;
             ray_to_object(sc.instances, f2i_bits(Qi.w), o, d);
             float t, al, be;
-            if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be))
+            if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be, q + 24))
                 consider(sc, best, t, MORT_LEAF_BIT | MORT_LEAF_QUAD_BIT | (first + i), al, be, order_lo, order_hi);
         }
     } else {
@@ -294,7 +305,7 @@ MORT_HD void closest_hit_linear(const DeviceScene& sc, const Ray& r, float tmin,
         const int inst = f2i_bits(Qi.w);
         if (inst != cur_inst) { o = r.o; d = r.d; ray_to_object(sc.instances, inst, o, d); cur_inst = inst; }
         float t, al, be;
-        if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be))
+        if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be, q + 24))
             consider(sc, best, t, MORT_LEAF_BIT | MORT_LEAF_QUAD_BIT | (uint32_t)i, al, be, order_lo, order_hi);
     }
 }
