@@ -269,6 +269,13 @@ def run_mort(a):
         kernel_ms_per_launch = ker_ms_max / a.steps
         per_gpu_rays_per_s = (seg_all / world) / a.steps / (kernel_ms_per_launch * 1e-3)
         achieved = per_gpu_rays_per_s * FLOP_PER_RAY / 1e12
+        traffic = None
+        try:    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this config, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if (a.scene, a.width, a.spp, a.depth, a.mode) == (6, 600, 1024, 50, "mega") and world == 1:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         res = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -283,7 +290,7 @@ def run_mort(a):
                     "note": "per step: kernel-parameter block up (the scene is resident, as in the reference's frame loop), RGBA8 frame down to pinned host memory"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": None, "kernel": "mega_kernel" if a.mode == "mega" else "wavefront kernels",
+                         "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (ncu)", "kernel": "mega_kernel" if a.mode == "mega" else "wavefront kernels",
                          "kernel_ms_per_launch": kernel_ms_per_launch,
                          "how": f"algorithmic {FLOP_PER_RAY:.0f} FLOP per path segment (SURVEY.md §8d, config 2) x segments per launch / CUDA-event kernel time; "
                                 f"peak = {st['sm_count']} SMs x 128 lanes x 2 x median SM clock under load (the path is neither HBM- nor tensor-bound)",

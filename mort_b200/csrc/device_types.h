@@ -5,7 +5,7 @@
 //   Bvh4Node   128 B   4 child boxes in SoA (6 x float4) + 4 child words + 4 spare words; read as 8 x LDG.128
 //   SphereGeom  32 B   {cx,cy,cz,r} {vx,vy,vz,inst}          hot: intersected during traversal
 //   PrimInfo    16 B   {mat_gid, obj_idx, order, 0}           cold: read once for the winning primitive / on ties
-//   QuadRec    128 B   {n,D} {Q,inst} {u,mat_gid} {v,order} {w,obj_idx} {area,top,-,-} {v x w} {w x u}; first 16 B decide most misses
+//   QuadRec     96 B   {n,D} {Q,inst} {u,mat_gid} {v,order} {w,obj_idx} {area,top,-,-}; first 16 B decide most misses
 //   Instance    64 B   up to 4 ops (translate / rotate_y), outermost first
 //   Material    32 B   Texture 32 B
 //
@@ -36,8 +36,6 @@ struct alignas(32) QuadRec {
     float vx, vy, vz; int32_t order;
     float wx, wy, wz; int32_t obj_idx;
     float area; int32_t pad[3];             // pad[0] = (top-level object type << 24) | slot
-    float vwx, vwy, vwz, pad6;              // v x w and w x u: alpha = hp.(v x w), beta = hp.(w x u) — the cheap, NOT bit-faithful form,
-    float wux, wuy, wuz, pad7;              // used only to discard candidates that are clearly outside before the exact test
 };
 
 enum { INST_OP_TRANSLATE = 1, INST_OP_ROTATE_Y = 2 };

@@ -305,11 +305,6 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
             r.vx = q.v[0]; r.vy = q.v[1]; r.vz = q.v[2]; r.order = L.order;
             r.wx = q.w[0]; r.wy = q.w[1]; r.wz = q.w[2]; r.obj_idx = L.idx;
             r.area = q.area; r.pad[0] = (L.top_type << 24) | (L.top_idx & 0xFFFFFF);
-            {   // pre-filter vectors, in double: hp.(v x w) == w.(hp x v), hp.(w x u) == w.(u x hp)
-                double u[3] = {q.u[0], q.u[1], q.u[2]}, v[3] = {q.v[0], q.v[1], q.v[2]}, w[3] = {q.w[0], q.w[1], q.w[2]};
-                r.vwx = (float)(v[1] * w[2] - v[2] * w[1]); r.vwy = (float)(v[2] * w[0] - v[0] * w[2]); r.vwz = (float)(v[0] * w[1] - v[1] * w[0]);
-                r.wux = (float)(w[1] * u[2] - w[2] * u[1]); r.wuy = (float)(w[2] * u[0] - w[0] * u[2]); r.wuz = (float)(w[0] * u[1] - w[1] * u[0]);
-            }
             rec_index[i] = (int)out.quads.size();
             out.quads.push_back(r);
         }

@@ -12,20 +12,20 @@
 
 static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
                             "            [--mode mega|wave] [--stage N] [--bps blocks/SM] [--tpb threads] [--field G [--fieldcam 0|1]]\n"
-                            "            [--assets DIR] [--out image.ppm] [--device K]\n"); return -1; }
+                            "            [--assets DIR] [--out image.ppm] [--hdr image.pfm] [--device K]\n"); return -1; }
 
 int main(int argc, char** argv) {
     if (argc < 2) return usage();                       // mort.cu:638-641
     int scene = atoi(argv[1]);
     int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = -1, mode = MORT_MODE_MEGAKERNEL, bps = 0, tpb = 0, field = 0, fieldcam = 0;
-    float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out;
+    float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         auto nx = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(-1); } return argv[++i]; };
         if (a == "--width") width = atoi(nx()); else if (a == "--aspect") aspect = (float)atof(nx());
         else if (a == "--spp") spp = atoi(nx()); else if (a == "--depth") depth = atoi(nx());
         else if (a == "--seed") seed = (unsigned)strtoul(nx(), 0, 10); else if (a == "--frames") frames = atoi(nx());
-        else if (a == "--assets") assets = nx(); else if (a == "--out") out = nx(); else if (a == "--device") device = atoi(nx());
+        else if (a == "--assets") assets = nx(); else if (a == "--out") out = nx(); else if (a == "--hdr") hdr = nx(); else if (a == "--device") device = atoi(nx());
         else if (a == "--stage") stage = atoi(nx());
         else if (a == "--bps") bps = atoi(nx()); else if (a == "--tpb") tpb = atoi(nx());
         else if (a == "--field") field = atoi(nx()); else if (a == "--fieldcam") fieldcam = atoi(nx());
@@ -41,11 +41,12 @@ int main(int argc, char** argv) {
     if (mort_commit(ctx) != MORT_OK) return die("commit");
     mort_stats st; mort_get_stats(ctx, &st);
     std::vector<uint8_t> img((size_t)st.width * st.height * 4);
+    std::vector<float> acc(hdr.empty() ? 0 : (size_t)st.width * st.height * 4);
     mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.stage_nodes = stage; o.blocks_per_sm = bps; o.threads_per_block = tpb;
     double total = 0;
     for (int f = 0; f < frames; f++) {
         o.frame = (uint32_t)f;
-        if (mort_render(ctx, &o, img.data(), nullptr) != MORT_OK) return die("render");
+        if (mort_render(ctx, &o, img.data(), acc.empty() ? nullptr : acc.data()) != MORT_OK) return die("render");
         mort_get_stats(ctx, &st);
         total += st.last_render_ms;
         printf("Avg. time per frame: %3.1f ms\n", total / (f + 1));
@@ -59,6 +60,15 @@ int main(int argc, char** argv) {
         if (!f) { perror(out.c_str()); mort_destroy(ctx); return 4; }
         fprintf(f, "P6\n%d %d\n255\n", st.width, st.height);
         for (int y = st.height - 1; y >= 0; y--) for (int x = 0; x < st.width; x++) fwrite(&img[4 * ((size_t)y * st.width + x)], 1, 3, f);
+        fclose(f);
+    }
+    if (!hdr.empty()) {
+        // linear radiance as PFM (rows bottom-up — the frame's own order, camera.cuh:70-78); NaN-poisoned pixels stay NaN
+        FILE* f = fopen(hdr.c_str(), "wb");
+        if (!f) { perror(hdr.c_str()); mort_destroy(ctx); return 4; }
+        fprintf(f, "PF\n%d %d\n-1.0\n", st.width, st.height);
+        const float inv = 1.0f / (float)(st.sqrt_spp * st.sqrt_spp);
+        for (size_t i = 0; i < (size_t)st.width * st.height; i++) { float px[3] = {acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv}; fwrite(px, 4, 3, f); }
         fclose(f);
     }
     mort_destroy(ctx);

@@ -202,10 +202,7 @@ MORT_HD bool sphere_test(f3 c, float r, f3 vel, f3 o, f3 d, float tm, float tmin
     t_out = root;
     return true;
 }
-// `pre` (may be null) = the record's {v x w}, {w x u} rows: a cheap estimate of (alpha, beta) that discards candidates
-// clearly outside the quad; everything that survives goes through the reference's exact expressions.
-MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3 d, float tmin, float tmax, float& t_out, float& alpha, float& beta,
-                       const float* pre = nullptr) {
+MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3 d, float tmin, float tmax, float& t_out, float& alpha, float& beta) {
     f3 n = mk3(nD.x, nD.y, nD.z);
     float denom = xdot(n, d);
     if (fabsf(denom) <= 1e-8f) return false;          // == ((double)fabsf(denom) < 1e-8): 1e-8f is the largest float below 1e-8
@@ -218,13 +215,6 @@ MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3
     F4 Q = ld4(rec);
     f3 P = xat(o, d, t);
     f3 hp = xsub3(P, mk3(Q.x, Q.y, Q.z));
-    if (pre) {
-        // both forms evaluate the same real number; inside or near the quad every term is O(1), so they agree to ~1e-6:
-        // a 1e-3 margin can never discard a candidate the exact test would accept
-        F4 A = ld4(pre), B = ld4(pre + 4);
-        float ac = hp.x * A.x + hp.y * A.y + hp.z * A.z, bc = hp.x * B.x + hp.y * B.y + hp.z * B.z;
-        if (ac < -1e-3f || ac > 1.001f || bc < -1e-3f || bc > 1.001f) return false;
-    }
     F4 U = ld4(rec + 4), Vv = ld4(rec + 8), W = ld4(rec + 12);
     f3 w = mk3(W.x, W.y, W.z);
     float al = xdot(w, xcross(hp, mk3(Vv.x, Vv.y, Vv.z)));
@@ -266,7 +256,7 @@ MORT_HD void leaf_intersect(const DeviceScene& sc, uint32_t w, const Ray& r, flo
             f3 o = r.o, d = r.d;
             ray_to_object(sc.instances, f2i_bits(Qi.w), o, d);
             float t, al, be;
-            if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be, q + 24))
+            if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be))
                 consider(sc, best, t, MORT_LEAF_BIT | MORT_LEAF_QUAD_BIT | (first + i), al, be, order_lo, order_hi);
         }
     } else {
@@ -305,7 +295,7 @@ MORT_HD void closest_hit_linear(const DeviceScene& sc, const Ray& r, float tmin,
         const int inst = f2i_bits(Qi.w);
         if (inst != cur_inst) { o = r.o; d = r.d; ray_to_object(sc.instances, inst, o, d); cur_inst = inst; }
         float t, al, be;
-        if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be, q + 24))
+        if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be))
             consider(sc, best, t, MORT_LEAF_BIT | MORT_LEAF_QUAD_BIT | (uint32_t)i, al, be, order_lo, order_hi);
     }
 }
@@ -327,6 +317,10 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
     if (sc.linear) { closest_hit_linear(sc, r, tmin, best, order_lo, order_hi); return best.prim != MORT_PRIM_NONE; }
     const float idx = safe_rcp_dir(r.d.x), idy = safe_rcp_dir(r.d.y), idz = safe_rcp_dir(r.d.z);
     const float oix = r.o.x * idx, oiy = r.o.y * idy, oiz = r.o.z * idz;
+    // per-ray octant: which of the node's lo/hi planes is the entry ("near") plane on each axis.  Picking the
+    // rows by address replaces 12 of the 18 min/max per child (float offsets into Bvh4Node: lo rows at 0/4/8, hi at 12/16/20).
+    const int nxo = idx < 0.f ? 12 : 0, nyo = idy < 0.f ? 16 : 4, nzo = idz < 0.f ? 20 : 8;
+    const int fxo = 12 - nxo, fyo = 20 - nyo, fzo = 28 - nzo;
     uint32_t stack_c[MORT_STACK]; float stack_t[MORT_STACK];
     int sp = 0;
     uint32_t cur = 0;                                   // root; MORT_CHILD_EMPTY (leaf bit set) = traversal finished
@@ -336,31 +330,30 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
     // apart for the whole traversal (lane utilisation 6.6/32 with the former single loop).
     while (cur != MORT_CHILD_EMPTY) {
         while (!(cur & MORT_LEAF_BIT)) {
-            F4 lx, ly, lz, hx, hy, hz, chf;
+            F4 nx, ny, nz, fx, fy, fz, chf;
 #if defined(__CUDA_ARCH__)
             if (kStaged) {
                 // generic 128-bit loads: the pointer may be shared or global
-                const float4* n4 = reinterpret_cast<const float4*>(((int)cur < n_staged ? staged : sc.nodes) + cur);
-                float4 a0 = n4[0], a1 = n4[1], a2 = n4[2], a3 = n4[3], a4 = n4[4], a5 = n4[5], a6 = n4[6];
-                lx = F4{a0.x, a0.y, a0.z, a0.w}; ly = F4{a1.x, a1.y, a1.z, a1.w}; lz = F4{a2.x, a2.y, a2.z, a2.w};
-                hx = F4{a3.x, a3.y, a3.z, a3.w}; hy = F4{a4.x, a4.y, a4.z, a4.w}; hz = F4{a5.x, a5.y, a5.z, a5.w}; chf = F4{a6.x, a6.y, a6.z, a6.w};
+                const float* n = reinterpret_cast<const float*>(((int)cur < n_staged ? staged : sc.nodes) + cur);
+                float4 a0 = *reinterpret_cast<const float4*>(n + nxo), a1 = *reinterpret_cast<const float4*>(n + nyo), a2 = *reinterpret_cast<const float4*>(n + nzo);
+                float4 a3 = *reinterpret_cast<const float4*>(n + fxo), a4 = *reinterpret_cast<const float4*>(n + fyo), a5 = *reinterpret_cast<const float4*>(n + fzo);
+                float4 a6 = *reinterpret_cast<const float4*>(n + 24);
+                nx = F4{a0.x, a0.y, a0.z, a0.w}; ny = F4{a1.x, a1.y, a1.z, a1.w}; nz = F4{a2.x, a2.y, a2.z, a2.w};
+                fx = F4{a3.x, a3.y, a3.z, a3.w}; fy = F4{a4.x, a4.y, a4.z, a4.w}; fz = F4{a5.x, a5.y, a5.z, a5.w}; chf = F4{a6.x, a6.y, a6.z, a6.w};
             } else
 #endif
             {
                 const float* n = reinterpret_cast<const float*>(sc.nodes + cur);
-                lx = ld4(n); ly = ld4(n + 4); lz = ld4(n + 8); hx = ld4(n + 12); hy = ld4(n + 16); hz = ld4(n + 20); chf = ld4(n + 24);
+                nx = ld4(n + nxo); ny = ld4(n + nyo); nz = ld4(n + nzo); fx = ld4(n + fxo); fy = ld4(n + fyo); fz = ld4(n + fzo); chf = ld4(n + 24);
             }
             (void)staged; (void)n_staged;
             float tn[4]; uint32_t cw[4] = {(uint32_t)f2i_bits(chf.x), (uint32_t)f2i_bits(chf.y), (uint32_t)f2i_bits(chf.z), (uint32_t)f2i_bits(chf.w)};
-            const float lxa[4] = {lx.x, lx.y, lx.z, lx.w}, lya[4] = {ly.x, ly.y, ly.z, ly.w}, lza[4] = {lz.x, lz.y, lz.z, lz.w};
-            const float hxa[4] = {hx.x, hx.y, hx.z, hx.w}, hya[4] = {hy.x, hy.y, hy.z, hy.w}, hza[4] = {hz.x, hz.y, hz.z, hz.w};
+            const float nxa[4] = {nx.x, nx.y, nx.z, nx.w}, nya[4] = {ny.x, ny.y, ny.z, ny.w}, nza[4] = {nz.x, nz.y, nz.z, nz.w};
+            const float fxa[4] = {fx.x, fx.y, fx.z, fx.w}, fya[4] = {fy.x, fy.y, fy.z, fy.w}, fza[4] = {fz.x, fz.y, fz.z, fz.w};
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                float t0x = fmaf(lxa[k], idx, -oix), t1x = fmaf(hxa[k], idx, -oix);
-                float t0y = fmaf(lya[k], idy, -oiy), t1y = fmaf(hya[k], idy, -oiy);
-                float t0z = fmaf(lza[k], idz, -oiz), t1z = fmaf(hza[k], idz, -oiz);
-                float tnear = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
-                float tfar = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), best.t));
+                float tnear = fmaxf(fmaxf(fmaf(nxa[k], idx, -oix), fmaf(nya[k], idy, -oiy)), fmaxf(fmaf(nza[k], idz, -oiz), tmin));
+                float tfar = fminf(fminf(fmaf(fxa[k], idx, -oix), fmaf(fya[k], idy, -oiy)), fminf(fmaf(fza[k], idz, -oiz), best.t));
                 bool h = (tnear <= tfar) && (cw[k] != MORT_CHILD_EMPTY);
                 tn[k] = h ? tnear : INFINITY;
                 cw[k] = h ? cw[k] : MORT_CHILD_EMPTY;

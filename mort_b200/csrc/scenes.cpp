@@ -285,9 +285,11 @@ bool build_sphere_field(Scene& s, int G, uint64_t seed, int camera_kind) {
     if (G < 1) { s.error = "sphere field: G must be >= 1"; return false; }
     uint64_t st = seed;
     Handle c1 = s.add_solid(V3(.2f, .3f, .1f)), c2 = s.add_solid(V3(.9f, .9f, .9f));
-    // ground: a flat checkered quad (a radius-1000 sphere as in scene 1 would drop 134 units by x = 500)
+    // ground: a flat checkered quad (a radius-1000 sphere as in scene 1 would drop 134 units by x = 500).  It sits
+    // half a millimetre below y = 0: the 3-D checker takes floor(y / 0.32), and on a plane exactly at y = 0 the
+    // sign of the rounding noise of the hit point would pick the colour.
     float L = (float)G + 50.0f;
-    s.add_quad(V3(-L, 0, -L), V3(0, 0, 2 * L), V3(2 * L, 0, 0), s.add_lambertian(s.add_checker(0.32f, c1, c2)));
+    s.add_quad(V3(-L, -0.0005f, -L), V3(0, 0, 2 * L), V3(2 * L, 0, 0), s.add_lambertian(s.add_checker(0.32f, c1, c2)));
     Handle glass = s.add_dielectric(1.5f);
     // a palette of materials instead of one per sphere: 10^6 spheres share 4096 lambertians / 1024 metals
     std::vector<Handle> lam, met;

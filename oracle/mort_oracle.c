@@ -652,7 +652,10 @@ static v3 mat_pdf_generate(const scatter_rec* sr, rng_t* g, rng_t* sg) {        
 
 /* Camera::ray_color, camera.cuh:86-176 (forward pass into per-bounce arrays, then the unwind) */
 #define ORACLE_MAX_DEPTH 1024
+static int g_debug_pixel = -2;
 static v3 ray_color(const oracle_scene* S, const ray_t* r, rng_t* g, uint64_t* segments) {
+    if (g_debug_pixel == -2) { const char* e = getenv("ORACLE_DEBUG_PIXEL"); g_debug_pixel = e ? atoi(e) : -1; }
+    const int dbg = g_debug_pixel >= 0 && (int)g->ctr[0] == g_debug_pixel;
     const mscn_camera* cam = &S->cam;
     int limit = cam->bounce_limit > ORACLE_MAX_DEPTH ? ORACLE_MAX_DEPTH : cam->bounce_limit;
     v3 att[ORACLE_MAX_DEPTH], em[ORACLE_MAX_DEPTH]; float spdf[ORACLE_MAX_DEPTH], pdfv[ORACLE_MAX_DEPTH];
@@ -664,6 +667,8 @@ static v3 ray_color(const oracle_scene* S, const ray_t* r, rng_t* g, uint64_t* s
         rng_t sg = *g; rng_align(&sg); (void)random_float(&sg); sg.have = 4;      /* sg.buf = block, nothing consumed yet */
         g->ctr[2] = sg.ctr[2]; rng_align(g);                                       /* the main stream continues after it */
         if (world_hit(S, &cur, 0.001f, INFINITY, &rec, g, 1, NULL, NULL)) {
+            if (dbg) fprintf(stderr, "ORACLE px %u smp %u seg %d: hit type %d idx %d t %.9g mat %d/%d ff %d p %.9g %.9g %.9g d %.9g %.9g %.9g\n", g->ctr[0], g->ctr[1], iter,
+                             rec.leaf_type, rec.leaf_idx, rec.t, rec.mat_type, rec.mat_idx, rec.front_face, rec.p.x, rec.p.y, rec.p.z, cur.d.x, cur.d.y, cur.d.z);
             ray_t scattered; v3 emission = emit_dispatch(S, &rec);
             float pdf, scattering_pdf; scatter_rec sr;
             if (scatter_dispatch(S, &cur, &rec, &sr, g, &sg)) {
@@ -690,9 +695,11 @@ static v3 ray_color(const oracle_scene* S, const ray_t* r, rng_t* g, uint64_t* s
     if (iter == limit) final = V(0, 0, 0);
     while (iter > 0) {
         iter--;
+        if (dbg) fprintf(stderr, "ORACLE   unwind %d: att %.9g %.9g %.9g spdf %.9g pdf %.9g\n", iter, att[iter].x, att[iter].y, att[iter].z, spdf[iter], pdfv[iter]);
         v3 num = vmul(vscale(spdf[iter], att[iter]), final);      /* attenuation * scattering_pdf * finalValue */
         final = vadd(em[iter], vdiv(num, pdfv[iter]));
     }
+    if (dbg) fprintf(stderr, "ORACLE   color %.9g %.9g %.9g\n", final.x, final.y, final.z);
     return final;
 }
 

@@ -147,6 +147,21 @@ int main(int argc, char** argv) {
             for (int sj = 0; sj < cam.sqrt_spp; sj++) for (int si = 0; si < cam.sqrt_spp; si++) {
                 Path P; Rng g; f3 col;
                 path_start(cam, seed, 0, pix, si, sj, P, g);
+                static int dbgpix = getenv("HOSTSIM_DEBUG_PIXEL") ? atoi(getenv("HOSTSIM_DEBUG_PIXEL")) : -1;
+                if (pix == dbgpix) {
+                    Path Q = P; Rng h = g; f3 c2;
+                    for (int seg = 0;; seg++) {
+                        if (path_exhausted(cam, Q, c2) || ray_is_nan(Q.ray)) break;
+                        R4 sb = rng_block(h); SegHit sh; segment_trace<false>(d, nullptr, 0, Q.ray, h, sh);
+                        if (sh.h.prim == MORT_PRIM_NONE) { fprintf(stderr, "HOSTSIM px %d smp %d seg %d: miss\n", pix, sj * cam.sqrt_spp + si, seg); break; }
+                        Record rec; segment_record(d, Q.ray, sh, rec);
+                        fprintf(stderr, "HOSTSIM px %d smp %d seg %d: hit type %d idx %d t %.9g matgid %d ff %d p %.9g %.9g %.9g d %.9g %.9g %.9g\n", pix, sj * cam.sqrt_spp + si, seg,
+                                rec.leaf_type, rec.leaf_idx, rec.t, rec.mat_gid, (int)rec.front_face, rec.p.x, rec.p.y, rec.p.z, Q.ray.d.x, Q.ray.d.y, Q.ray.d.z);
+                        int stt = segment_shade<CLASS_ANY>(d, cam, sh, Q, h, sb, c2);
+                        fprintf(stderr, "HOSTSIM   thr %.9g %.9g %.9g\n", Q.thr.x, Q.thr.y, Q.thr.z);
+                        if (stt == SEG_DONE) { fprintf(stderr, "HOSTSIM   color %.9g %.9g %.9g\n", c2.x, c2.y, c2.z); break; }
+                    }
+                }
                 for (;;) { bool tr; int st = path_segment<false>(d, cam, nullptr, 0, P, g, col, tr); segs += tr; if (st == SEG_DONE) break; }
                 if (isnan3(col)) nan_n++; else { sx += col.x; sy += col.y; sz += col.z; }
             }
