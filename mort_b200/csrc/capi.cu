@@ -291,8 +291,9 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     if (o.mode == MORT_MODE_MEGAKERNEL) {
         int occ = 0, regs = 0;
-        // measured (profiles/r01_variants.md): 8 blocks/SM (64 regs) wins for the lockstep linear scan, 6 (80 regs) for BVH scenes
-        const int min_blocks = o.blocks_per_sm > 0 ? o.blocks_per_sm : (ctx->flat.linear ? 8 : 6);   // selects the register-capped variant
+        // measured (profiles/r01_v4_variants.jsonl): 6 blocks/SM (80 regs) wins for the lockstep linear scan, 8 (64 regs) for the
+        // larger BVH scenes; the spread between 6 and 8 is <= 3 % everywhere
+        const int min_blocks = o.blocks_per_sm > 0 ? o.blocks_per_sm : (ctx->flat.linear ? 6 : 8);   // selects the register-capped variant
         CU(mega_query(threads, n_staged, min_blocks, &occ, &regs));
         if (occ < 1) return fail(ctx, MORT_ERR_CUDA, "megakernel does not fit on an SM with this configuration");
         int bps = o.blocks_per_sm > 0 ? std::min(o.blocks_per_sm, occ) : occ;
