@@ -204,6 +204,11 @@ int mort_commit(mort_ctx* ctx) {
     CU(cudaSetDevice(ctx->device));
     std::string e;
     if (!flatten_scene(ctx->scene, ctx->flat, &e)) return fail(ctx, MORT_ERR_SCENE, e);
+    // the traversal stack holds 48 entries and a 4-wide node pushes at most 3: refuse (loudly) a tree it could overflow on
+    if (!ctx->flat.linear && ctx->flat.stats.max_depth * 3 > 48)
+        return fail(ctx, MORT_ERR_SCENE, "BVH deeper than 16 levels: the traversal stack (48 entries) could overflow; scene rejected");
+    if (ctx->flat.spheres.size() >= (1u << 27) || ctx->flat.quads.size() >= (1u << 27))
+        return fail(ctx, MORT_ERR_SCENE, "more than 2^27 primitives of one kind are not addressable by a leaf word");
     auto t0 = std::chrono::steady_clock::now();
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->arena.release();
