@@ -184,6 +184,9 @@ def run_mort(a):
     stream = torch.cuda.current_stream()
     r.set_stream(stream.cuda_stream)
     accum = torch.zeros(H, W, 4, dtype=torch.float32, device=dev)
+    # N > 1: ranks exchange EXACT partial frames (4 x int64 fixed-point words per pixel): integer sums are associative, so the
+    # combined frame is bit-identical to the single-GPU frame whatever the reduction order
+    exact = torch.zeros(H, W, 4, dtype=torch.int64, device=dev) if world > 1 else None
     rgba = torch.zeros(H, W, 4, dtype=torch.uint8, device=dev)
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     mode = MODE_MEGAKERNEL if a.mode == "mega" else MODE_WAVEFRONT
@@ -193,10 +196,17 @@ def run_mort(a):
     def step(i, timed):
         nonlocal seg_total, ker_ms, launches
         flush.zero_()                                                       # L2 flush between iterations
-        r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps)
-        s = r.stats
-        if world > 1:
-            D.combine(accum, how="reduce")
+        if world > 1 and mode == MODE_MEGAKERNEL:
+            r.render_device(exact.data_ptr(), seed=69420, frame=i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps, exact_accum=1)
+            s = r.stats
+            D.combine(exact, how="reduce")
+            if rank == 0:
+                r.resolve_exact_device(exact.data_ptr(), accum.data_ptr())
+        else:
+            r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps)
+            s = r.stats
+            if world > 1:
+                D.combine(accum, how="reduce")
         if rank == 0:
             r.tonemap_device(accum.data_ptr(), n_spp, rgba.data_ptr())
         if timed:
@@ -245,8 +255,14 @@ def run_mort(a):
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(a.steps):
-            r.render_device(accum.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps)
-            D.combine(accum, how="reduce")
+            if mode == MODE_MEGAKERNEL:
+                r.render_device(exact.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps, exact_accum=1)
+                D.combine(exact, how="reduce")
+                if rank == 0:
+                    r.resolve_exact_device(exact.data_ptr(), accum.data_ptr())
+            else:
+                r.render_device(accum.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps)
+                D.combine(accum, how="reduce")
             if rank == 0:
                 r.tonemap_device(accum.data_ptr(), n_spp, rgba.data_ptr())
                 host_rgba.copy_(rgba, non_blocking=False)
@@ -281,7 +297,7 @@ def run_mort(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"mort scene {a.scene} ({'cornell_box' if a.scene == 6 else 'scene'}) {W}x{H}, {a.spp} spp ({n_spp} effective), max depth {a.depth}",
                        "scene": a.scene, "width": W, "height": H, "spp": a.spp, "depth": a.depth, "mode": a.mode,
-                       "parallelism": f"sample-split x{world} + 1 NCCL reduce/frame" if world > 1 else "single GPU",
+                       "parallelism": f"sample-split x{world} + 1 NCCL int64 SUM reduce of the exact partial frames per frame" if world > 1 else "single GPU",
                        "l2": "192 MiB buffer written between timed iterations (L2 flush)"},
             "mrays_per_s": mrays, "segments_per_sample": seg_all / (samples_per_frame * a.steps),
             "clocks": clocks,

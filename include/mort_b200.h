@@ -101,7 +101,8 @@ typedef struct {
     int32_t threads_per_block;     /* 0 = default */
     int32_t blocks_per_sm;         /* 0 = default */
     int32_t wavefront_paths;       /* paths in flight for the wavefront mode, 0 = default */
-    int32_t reserved[7];
+    int32_t exact_accum;           /* 1: d_accum receives W*H x 4 uint64 (exact fixed-point sums, see mort_resolve_exact_device) */
+    int32_t reserved[6];
 } mort_render_opts;
 void mort_default_render_opts(mort_render_opts* o);
 
@@ -110,6 +111,11 @@ void mort_default_render_opts(mort_render_opts* o);
  * w = number of samples that contained a NaN. */
 /* Device-resident frame: d_accum is a device pointer owned by the caller (e.g. a torch tensor). */
 int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts, void* d_accum);
+/* Exact accumulation image (opts.exact_accum = 1, megakernel only): W*H x 4 uint64 per pixel = Q31.32 fixed-point sums of
+ * r, g, b and a word of NaN / +inf sample counts.  Integer sums are associative, so partial frames of a sample split can be
+ * added in ANY order (e.g. by an int64 SUM all-reduce) and the N-GPU frame equals the 1-GPU frame bit for bit.
+ * mort_resolve_exact_device turns it into the float4 accumulation image described above. */
+int mort_resolve_exact_device(mort_ctx* ctx, const void* d_exact, void* d_accum);
 /* Tone pipeline of camera.cuh:194-207 on device: mean over n_samples, NaN flush, gamma 2, quantise to RGBA8
  * (w=255).  d_rgba8 is a device pointer to W*H*4 bytes. */
 int mort_tonemap_device(mort_ctx* ctx, const void* d_accum, int samples_per_pixel_total, void* d_rgba8);

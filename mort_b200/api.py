@@ -47,7 +47,7 @@ class CameraDesc(C.Structure):
 class RenderOpts(C.Structure):
     _fields_ = [("seed", C.c_uint32), ("frame", C.c_uint32), ("mode", C.c_int32), ("sample_mod", C.c_int32),
                 ("sample_rem", C.c_int32), ("stage_nodes", C.c_int32), ("threads_per_block", C.c_int32),
-                ("blocks_per_sm", C.c_int32), ("wavefront_paths", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("blocks_per_sm", C.c_int32), ("wavefront_paths", C.c_int32), ("exact_accum", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class Stats(C.Structure):
@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "mort_add_constant_medium", "mort_add_list", "mort_list_add", "mort_add_bvh", "mort_add_box", "mort_add_rotated_box",
     "mort_host_rand",
     "mort_get_camera", "mort_set_camera", "mort_override_camera", "mort_get_camera_record",
-    "mort_commit", "mort_default_render_opts", "mort_render_device", "mort_tonemap_device", "mort_render",
+    "mort_commit", "mort_default_render_opts", "mort_render_device", "mort_resolve_exact_device", "mort_tonemap_device", "mort_render",
     "mort_trace", "mort_get_stats",
 ]
 
@@ -107,7 +107,7 @@ def load_library():
         "mort_get_camera": [P, C.POINTER(CameraDesc)], "mort_set_camera": [P, C.POINTER(CameraDesc)],
         "mort_override_camera": [P, I, Fl, I, I], "mort_get_camera_record": [P, P],
         "mort_commit": [P], "mort_default_render_opts": [C.POINTER(RenderOpts)],
-        "mort_render_device": [P, C.POINTER(RenderOpts), P], "mort_tonemap_device": [P, P, I, P],
+        "mort_render_device": [P, C.POINTER(RenderOpts), P], "mort_resolve_exact_device": [P, P, P], "mort_tonemap_device": [P, P, I, P],
         "mort_render": [P, C.POINTER(RenderOpts), P, P], "mort_trace": [P, P, I, P, P, I], "mort_get_stats": [P, C.POINTER(Stats)],
     }
     for name, args in sig.items():
@@ -274,6 +274,10 @@ class Renderer:
         """Device-resident frame into a caller-owned float4 buffer (e.g. a torch tensor's data_ptr())."""
         o = self.opts(**opts)
         self._ck(self._L.mort_render_device(self._h, C.byref(o), C.c_void_p(d_accum_ptr)))
+
+    def resolve_exact_device(self, d_exact_ptr: int, d_accum_ptr: int):
+        """(H, W, 4) uint64 exact sums (render_device(..., exact_accum=1)) -> (H, W, 4) float32 accumulation image."""
+        self._ck(self._L.mort_resolve_exact_device(self._h, C.c_void_p(d_exact_ptr), C.c_void_p(d_accum_ptr)))
 
     def tonemap_device(self, d_accum_ptr: int, samples_per_pixel_total: int, d_rgba8_ptr: int):
         self._ck(self._L.mort_tonemap_device(self._h, C.c_void_p(d_accum_ptr), int(samples_per_pixel_total), C.c_void_p(d_rgba8_ptr)))

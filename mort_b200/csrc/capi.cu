@@ -277,7 +277,9 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     int PT = p.n_subset > 0 ? (2048 + p.n_subset - 1) / p.n_subset : 1;
     PT = std::max(1, std::min(16, PT));
     p.lanes_per_pixel = PT;
-    p.accum = reinterpret_cast<float4*>(d_accum);
+    if (o.exact_accum && o.mode != MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render: exact_accum is a megakernel feature");
+    p.accum = o.exact_accum ? nullptr : reinterpret_cast<float4*>(d_accum);
+    p.accum_exact = o.exact_accum ? reinterpret_cast<unsigned long long*>(d_accum) : nullptr;
     p.counters = ctx->d_counters; p.work_counter = ctx->d_work;
 
     const int threads = o.threads_per_block > 0 ? (o.threads_per_block + 31) / 32 * 32 : 128;
@@ -325,6 +327,15 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     return MORT_OK;
 }
 
+int mort_resolve_exact_device(mort_ctx* ctx, const void* d_exact, void* d_accum) {
+    CTX_CHECK(ctx && d_exact && d_accum);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "scene not committed");
+    const CameraParams& cam = ctx->flat.cam;
+    CU(resolve_exact_launch(reinterpret_cast<const unsigned long long*>(d_exact), cam.width * cam.height, reinterpret_cast<float4*>(d_accum), ctx->stream));
+    ctx->stats.last_kernel_launches += 1;
+    return MORT_OK;
+}
+
 int mort_tonemap_device(mort_ctx* ctx, const void* d_accum, int spp_total, void* d_rgba8) {
     CTX_CHECK(ctx && d_accum && d_rgba8);
     if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "scene not committed");
@@ -343,7 +354,9 @@ int mort_render(mort_ctx* ctx, const mort_render_opts* opts, uint8_t* rgba8_out,
     size_t npix = (size_t)cam.width * cam.height;
     int rc = ensure_accum(ctx, npix);
     if (rc != MORT_OK) return rc;
-    rc = mort_render_device(ctx, opts, ctx->d_accum);
+    mort_render_opts oh; if (opts) oh = *opts; else mort_default_render_opts(&oh);
+    oh.exact_accum = 0;                                  // the host-buffer call returns the float4 image
+    rc = mort_render_device(ctx, &oh, ctx->d_accum);
     if (rc != MORT_OK) return rc;
     if (rgba8_out) {
         rc = mort_tonemap_device(ctx, ctx->d_accum, cam.sqrt_spp * cam.sqrt_spp, ctx->d_rgba);

@@ -125,7 +125,10 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
             for (int c = 0; c < 4; c++) atomicAdd(&part[warp][cur_p][c], lacc[warp][c][lane]);
         }
         __syncwarp();
-        if (lane < npx)
+        if (P.accum_exact) {                                  // 4 words per pixel, coalesced over the task's pixels
+            if (lane < npx * 4) P.accum_exact[(size_t)base * 4 + lane] = part[warp][lane >> 2][lane & 3];
+            if (lane + 32 < npx * 4) P.accum_exact[(size_t)base * 4 + lane + 32] = part[warp][(lane + 32) >> 2][(lane + 32) & 3];
+        } else if (lane < npx)
             P.accum[base + lane] = fx_resolve((long long)part[warp][lane][0], (long long)part[warp][lane][1], (long long)part[warp][lane][2], part[warp][lane][3]);
         __syncwarp();
         for (int off = 16; off > 0; off >>= 1) { n_seg += __shfl_xor_sync(full, n_seg, off); n_smp += __shfl_xor_sync(full, n_smp, off); }
@@ -213,6 +216,18 @@ cudaError_t trace_launch(const DeviceScene& sc, const float* d_rays, int n, mhit
                          int brute_force, const int32_t* d_mat_offsets, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     trace_kernel<<<(n + 127) / 128, 128, 0, st>>>(sc, d_rays, n, d_out, d_probes, brute_force, d_mat_offsets);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) resolve_exact_kernel(const unsigned long long* __restrict__ ex, int n, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ulonglong2 a = reinterpret_cast<const ulonglong2*>(ex)[2 * (size_t)i], b = reinterpret_cast<const ulonglong2*>(ex)[2 * (size_t)i + 1];
+    out[i] = fx_resolve((long long)a.x, (long long)a.y, (long long)b.x, b.y);
+}
+cudaError_t resolve_exact_launch(const unsigned long long* d_exact, int n_pixels, float4* d_accum, cudaStream_t st) {
+    if (n_pixels <= 0) return cudaSuccess;
+    resolve_exact_kernel<<<(n_pixels + 255) / 256, 256, 0, st>>>(d_exact, n_pixels, d_accum);
     return cudaGetLastError();
 }
 

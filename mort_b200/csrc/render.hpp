@@ -18,7 +18,8 @@ struct FrameParams {
     int32_t lanes_per_pixel;        // megakernel: pixels per warp task (1..16)
     int32_t n_pixels;
     int32_t n_staged;               // BVH nodes copied to shared memory per block
-    float4* accum;                  // W*H
+    float4* accum;                  // W*H (null when accum_exact is used)
+    unsigned long long* accum_exact;// W*H x 4 (r, g, b fixed point, flags) or null
     unsigned long long* counters;   // [0] segments, [1] samples
     unsigned int* work_counter;     // persistent-warp work queue head
 };
@@ -39,6 +40,7 @@ cudaError_t wavefront_render(const FrameParams& p, WavefrontBuffers* buf, int n_
 // parity hook + tone pipeline (render.cu)
 cudaError_t trace_launch(const DeviceScene& sc, const float* d_rays, int n, mhit_record* d_out, mhit_medium_probe* d_probes,
                          int brute_force, const int32_t* d_mat_offsets, cudaStream_t st);
+cudaError_t resolve_exact_launch(const unsigned long long* d_exact, int n_pixels, float4* d_accum, cudaStream_t st);
 cudaError_t tonemap_launch(const float4* d_accum, int n_pixels, float scale, uint8_t* d_rgba8, cudaStream_t st);
 
 }  // namespace mort

@@ -9,7 +9,9 @@ every pixel into a full-frame float4 accumulation buffer; the buffers are combin
   combine="gather"  all ranks' buffers gathered on rank 0 and summed in rank order — the same bits for any
                     world size that divides the strata rows evenly, at world x the traffic
 
-The renderer has no other collective.
+With `exact_accum=1` the partial frames are (H, W, 4) int64 tensors of exact fixed-point sums: integer addition is
+associative, so either way of combining gives the single-GPU frame bit for bit (Renderer.resolve_exact_device turns the
+combined buffer into the float4 accumulation image).  The renderer has no other collective.
 """
 from __future__ import annotations
 

@@ -106,6 +106,34 @@ def test_deterministic_and_sample_split(renderer):
         assert sum(D.rows_of_rank(8, r, world) for r in range(world)) == 8
 
 
+def test_exact_accumulation_makes_any_sample_split_bit_identical(renderer):
+    """N virtual ranks, exact int64 partial frames summed in any order == the single-GPU frame, bit for bit"""
+    import torch
+    renderer.build_scene(8).override_camera(width=40, spp=64).commit()       # media, noise, image texture, instances
+    st = renderer.stats
+    H, W = st["height"], st["width"]
+    full = torch.zeros(H, W, 4, dtype=torch.int64, device="cuda")
+    renderer.render_device(full.data_ptr(), seed=3, frame=1, exact_accum=1)
+    facc = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
+    renderer.resolve_exact_device(full.data_ptr(), facc.data_ptr())
+    plain = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
+    renderer.render_device(plain.data_ptr(), seed=3, frame=1)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(facc, nan=-1.0), torch.nan_to_num(plain, nan=-1.0)), "resolve(exact) must equal the float frame"
+    for world in (2, 3, 8):
+        parts = []
+        for r in reversed(range(world)):                     # reversed on purpose: the order must not matter
+            p = torch.zeros(H, W, 4, dtype=torch.int64, device="cuda")
+            renderer.render_device(p.data_ptr(), seed=3, frame=1, exact_accum=1, sample_mod=world, sample_rem=r)
+            parts.append(p)
+        tot = sum(parts[1:], parts[0].clone())
+        torch.cuda.synchronize()
+        assert torch.equal(tot, full), f"{world}-way exact sample split differs from the single-GPU frame"
+    from mort_b200.api import MortError, MODE_WAVEFRONT
+    with pytest.raises(MortError):
+        renderer.render_device(full.data_ptr(), exact_accum=1, mode=MODE_WAVEFRONT)
+
+
 def test_staging_and_launch_shapes_do_not_change_the_image(renderer):
     renderer.build_scene(1).override_camera(width=96, spp=25, depth=50).commit()
     base = renderer.render(seed=9).accum
