@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -274,7 +275,9 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     p.n_subset = p.n_rows * cam.sqrt_spp;
     p.n_pixels = cam.width * cam.height;
     // pixels per warp task: enough samples per task (~2048) to amortise the end-of-task tail, at most 16 pixels
-    int PT = p.n_subset > 0 ? (2048 + p.n_subset - 1) / p.n_subset : 1;
+    int task_samples = 2048;
+    if (const char* e = getenv("MORT_TASK_SAMPLES")) { int v = atoi(e); if (v >= 32) task_samples = v; }   // experiments only
+    int PT = p.n_subset > 0 ? (task_samples + p.n_subset - 1) / p.n_subset : 1;
     PT = std::max(1, std::min(16, PT));
     p.lanes_per_pixel = PT;
     if (o.exact_accum && o.mode != MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render: exact_accum is a megakernel feature");

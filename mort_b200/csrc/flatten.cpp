@@ -272,8 +272,17 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
         out.linear = 1;
         order.resize(prims.size());
         for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+        // within an instance group: largest surface first — a ray most likely hits something big, and once it has a
+        // hit the remaining (smaller) candidates mostly fail the cheap t-range test before their full test
+        auto area_of = [&](int i) {
+            const LeafRef& L = out.leaves[i];
+            if (L.type == MORT_OBJ_SPHERE) { float r = s.spheres[L.idx].radius; return 12.566371f * r * r; }
+            return s.quads[L.idx].area;
+        };
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
             if (out.leaves[a].inst != out.leaves[b].inst) return out.leaves[a].inst < out.leaves[b].inst;
+            float aa = area_of(a), ab = area_of(b);
+            if (aa != ab) return aa > ab;
             return out.leaves[a].order < out.leaves[b].order;
         });
         Bvh4Node n; memset(&n, 0, sizeof(n));
