@@ -249,22 +249,25 @@ MORT_HD void consider(const DeviceScene& sc, Hit& best, float t, uint32_t prim, 
 
 MORT_HD void leaf_intersect(const DeviceScene& sc, uint32_t w, const Ray& r, float tmin, Hit& best, int order_lo, int order_hi) {
     uint32_t first = w & 0x07FFFFFFu; int count = (int)((w >> 27) & 7u) + 1;
+    int cur_inst = -1; f3 o = r.o, d = r.d;               // neighbours in a leaf usually share their instance: transform the ray once
     if (w & MORT_LEAF_QUAD_BIT) {
+#pragma unroll 1
         for (int i = 0; i < count; i++) {
             const float* q = reinterpret_cast<const float*>(sc.quads + first + i);
             F4 nD = ld4(q); F4 Qi = ld4(q + 4);
-            f3 o = r.o, d = r.d;
-            ray_to_object(sc.instances, f2i_bits(Qi.w), o, d);
+            const int inst = f2i_bits(Qi.w);
+            if (inst != cur_inst) { o = r.o; d = r.d; ray_to_object(sc.instances, inst, o, d); cur_inst = inst; }
             float t, al, be;
             if (quad_test(nD, q + 4, o, d, tmin, best.t, t, al, be))
                 consider(sc, best, t, MORT_LEAF_BIT | MORT_LEAF_QUAD_BIT | (first + i), al, be, order_lo, order_hi);
         }
     } else {
+#pragma unroll 1
         for (int i = 0; i < count; i++) {
             const float* s = reinterpret_cast<const float*>(sc.spheres + first + i);
             F4 c = ld4(s), v = ld4(s + 4);
-            f3 o = r.o, d = r.d;
-            ray_to_object(sc.instances, f2i_bits(v.w), o, d);
+            const int inst = f2i_bits(v.w);
+            if (inst != cur_inst) { o = r.o; d = r.d; ray_to_object(sc.instances, inst, o, d); cur_inst = inst; }
             float t;
             if (sphere_test(mk3(c.x, c.y, c.z), c.w, mk3(v.x, v.y, v.z), o, d, r.tm, tmin, best.t, t))
                 consider(sc, best, t, MORT_LEAF_BIT | (first + i), 0.f, 0.f, order_lo, order_hi);
@@ -446,7 +449,8 @@ MORT_HD void resolve_hit(const DeviceScene& sc, const Ray& r, const Hit& h, Reco
 // ---------------------------------------------------------------------------------------------------
 // constant_medium (objects.cuh:396-434): boundary probes by linear scan in the reference's order
 // ---------------------------------------------------------------------------------------------------
-MORT_HD bool boundary_probe(const DeviceScene& sc, const Medium& m, const Ray& r, float tmin, float tmax, float& t_hit) {
+// out of line: medium_hit calls it twice, and each copy carries both exact primitive tests
+MORT_HD_NOINLINE bool boundary_probe(const DeviceScene& sc, const Medium& m, Ray r, float tmin, float tmax, float& t_hit) {
     bool any = false; float closest = tmax;
     for (int k = 0; k < m.count; k++) {
         const BoundaryPrim* B = sc.boundary + m.first + k;
