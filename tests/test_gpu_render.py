@@ -177,6 +177,11 @@ def test_custom_scene_through_builder_calls(renderer):
     ball = r.add_moving_sphere((190, 90, 190), (190, 120, 190), 90, r.add_metal(0.8, 0.85, 0.88, 0.1))
     smoke = r.add_sphere((400, 100, 150), 80, r.add_dielectric(1.5))
     r.add_constant_medium(smoke, 0.01, r.add_isotropic(r.add_solid(0.2, 0.4, 0.9)))
+    # a visible top-level list next to a medium: world::hit tests it AFTER the media (world.cuh:154-168), which the
+    # product reproduces with a second, visit-order-windowed traversal pass
+    lst = r.add_list(False)
+    r.list_add(lst, r.add_sphere((120, 60, 120), 60, r.add_lambertian(r.add_checker(40.0, r.add_solid(.9, .2, .2), r.add_solid(.2, .9, .2))), skip=True))
+    r.list_add(lst, r.add_quad((300, 0.5, 300), (150, 0, 0), (0, 0, 150), white, skip=True))
     cam = r.get_camera()
     cam.aspect_ratio = 1.0; cam.image_width = 48; cam.samples_per_pixel = 16; cam.bounce_limit = 12; cam.vfov = 40
     cam.background[:] = (0.02, 0.02, 0.02); cam.lookfrom[:] = (278, 278, -800); cam.lookat[:] = (278, 278, 0); cam.vup[:] = (0, 1, 0)
@@ -186,6 +191,14 @@ def test_custom_scene_through_builder_calls(renderer):
     path = "/tmp/mort_custom_scene.mscn"
     r.dump_scene(path)
     osc = O.OracleScene(path)
+    rng = np.random.default_rng(4)
+    rays = np.concatenate([np.tile([278, 278, -800], (4000, 1)), rng.normal(size=(4000, 3)) * [0.35, 0.35, 0.0] + [0, 0, 1], rng.random((4000, 1))], 1).astype(np.float32)
+    hits, probes = r.trace(rays)
+    ref_hits, ref_probes = osc.trace(rays)
+    b = ref_hits["hit"] == 1
+    assert (hits["hit"] == ref_hits["hit"]).all() and (hits["t"].view(np.uint32)[b] == ref_hits["t"].view(np.uint32)[b]).all()
+    assert ((hits["leaf_type"] == ref_hits["leaf_type"]) & (hits["leaf_idx"] == ref_hits["leaf_idx"]))[b].all()
+    assert (probes["hit2"] == ref_probes["hit2"]).all() and (probes["t2"].view(np.uint32) == ref_probes["t2"].view(np.uint32)).all()
     fr = r.render(seed=11)
     hdr, _, st = osc.render(seed=11)
     ok = (fr.accum[..., 3] == 0) & (hdr[..., 3] == 0) & np.isfinite(fr.accum[..., :3]).all(-1) & np.isfinite(hdr[..., :3]).all(-1)
