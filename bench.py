@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--aspect", type=float, default=0.0)
     ap.add_argument("--stage", type=int, default=-1)
     ap.add_argument("--bps", type=int, default=0, help="megakernel blocks per SM (selects the register-capped variant)")
+    ap.add_argument("--split", default="sample", choices=["sample", "tile"], help="how the frame is sharded over GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -172,8 +173,7 @@ def run_mort(a):
         raise SystemExit("bench.py: no CUDA device — mort_b200 has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line (NCCL prints its version banner there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL logs its banner to stdout)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -191,19 +191,22 @@ def run_mort(a):
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     mode = MODE_MEGAKERNEL if a.mode == "mega" else MODE_WAVEFRONT
     mod, rem = D.sample_split(rank, world)
+    split = dict(sample_mod=mod, sample_rem=rem) if a.split == "sample" else dict(tile_mod=world, tile_rem=rank)
     seg_total, ker_ms, launches = 0, 0.0, 0
 
     def step(i, timed):
         nonlocal seg_total, ker_ms, launches
         flush.zero_()                                                       # L2 flush between iterations
         if world > 1 and mode == MODE_MEGAKERNEL:
-            r.render_device(exact.data_ptr(), seed=69420, frame=i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps, exact_accum=1)
+            if a.split == "tile":
+                exact.zero_()                                   # ranks only write their own bands
+            r.render_device(exact.data_ptr(), seed=69420, frame=i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps, exact_accum=1, **split)
             s = r.stats
             D.combine(exact, how="reduce")
             if rank == 0:
                 r.resolve_exact_device(exact.data_ptr(), accum.data_ptr())
         else:
-            r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps)
+            r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps, **split)
             s = r.stats
             if world > 1:
                 D.combine(accum, how="reduce")
@@ -256,12 +259,14 @@ def run_mort(a):
         t0 = time.perf_counter()
         for i in range(a.steps):
             if mode == MODE_MEGAKERNEL:
-                r.render_device(exact.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps, exact_accum=1)
+                if a.split == "tile":
+                    exact.zero_()
+                r.render_device(exact.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps, exact_accum=1, **split)
                 D.combine(exact, how="reduce")
                 if rank == 0:
                     r.resolve_exact_device(exact.data_ptr(), accum.data_ptr())
             else:
-                r.render_device(accum.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, sample_mod=mod, sample_rem=rem, stage_nodes=a.stage, blocks_per_sm=a.bps)
+                r.render_device(accum.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps, **split)
                 D.combine(accum, how="reduce")
             if rank == 0:
                 r.tonemap_device(accum.data_ptr(), n_spp, rgba.data_ptr())
@@ -297,7 +302,7 @@ def run_mort(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"mort scene {a.scene} ({'cornell_box' if a.scene == 6 else 'scene'}) {W}x{H}, {a.spp} spp ({n_spp} effective), max depth {a.depth}",
                        "scene": a.scene, "width": W, "height": H, "spp": a.spp, "depth": a.depth, "mode": a.mode,
-                       "parallelism": f"sample-split x{world} + 1 NCCL int64 SUM reduce of the exact partial frames per frame" if world > 1 else "single GPU",
+                       "parallelism": f"{a.split}-split x{world} + 1 NCCL int64 SUM reduce of the exact partial frames per frame" if world > 1 else "single GPU",
                        "l2": "192 MiB buffer written between timed iterations (L2 flush)"},
             "mrays_per_s": mrays, "segments_per_sample": seg_all / (samples_per_frame * a.steps),
             "clocks": clocks,

@@ -102,7 +102,9 @@ typedef struct {
     int32_t blocks_per_sm;         /* 0 = default */
     int32_t wavefront_paths;       /* paths in flight for the wavefront mode, 0 = default */
     int32_t exact_accum;           /* 1: d_accum receives W*H x 4 uint64 (exact fixed-point sums, see mort_resolve_exact_device) */
-    int32_t reserved[6];
+    int32_t tile_mod, tile_rem;    /* tile-split across GPUs (megakernel): this call renders the 8-row bands b with b % mod == rem and leaves
+                                      every other pixel of d_accum untouched (0,0 or 1,0 = whole frame) */
+    int32_t reserved[4];
 } mort_render_opts;
 void mort_default_render_opts(mort_render_opts* o);
 

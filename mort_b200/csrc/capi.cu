@@ -274,6 +274,14 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     p.n_rows = cam.sqrt_spp > o.sample_rem ? (cam.sqrt_spp - o.sample_rem + o.sample_mod - 1) / o.sample_mod : 0;
     p.n_subset = p.n_rows * cam.sqrt_spp;
     p.n_pixels = cam.width * cam.height;
+    p.tile_mod = o.tile_mod > 1 ? o.tile_mod : 1; p.tile_rem = o.tile_mod > 1 ? o.tile_rem : 0;
+    if (p.tile_mod > 1) {
+        if (o.tile_rem < 0 || o.tile_rem >= o.tile_mod) return fail(ctx, MORT_ERR_ARG, "mort_render: bad tile split");
+        if (o.mode != MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render: tile split is a megakernel feature");
+        int n = 0;                                           // pixels in this rank's 8-row bands
+        for (int b = p.tile_rem; b * 8 < cam.height; b += p.tile_mod) n += std::min(8, cam.height - b * 8) * cam.width;
+        p.n_pixels = n;
+    }
     // pixels per warp task: enough samples per task (~2048) to amortise the end-of-task tail, at most 16 pixels
     int task_samples = 2048;
     if (const char* e = getenv("MORT_TASK_SAMPLES")) { int v = atoi(e); if (v >= 32) task_samples = v; }   // experiments only

@@ -42,6 +42,13 @@ __device__ __forceinline__ float4 fx_resolve(long long r, long long g, long long
 
 // kMinBlocks = occupancy target handed to ptxas (register cap 65536 / (128 * kMinBlocks)): 4 -> 128 regs,
 // 6 -> 80, 8 -> 64.  Which one wins is a measurement (profiles/), selectable through mort_render_opts.blocks_per_sm.
+// tile split: the rank's pixels are its 8-row bands packed back to back; local index -> frame index
+__device__ __forceinline__ int tile_to_global(int li, int band_px, int mod, int rem) {
+    if (mod <= 1) return li;
+    const int bl = li / band_px;
+    return (bl * mod + rem) * band_px + (li - bl * band_px);
+}
+
 template <bool kStaged, int kMinBlocks>
 __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -61,6 +68,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
     const unsigned lt_mask = (1u << lane) - 1u;
     const int PT = P.lanes_per_pixel;                     // pixels per warp task (1..MEGA_PMAX)
     const int sqrt_spp = P.cam.sqrt_spp, n_subset = P.n_subset;
+    const int band_px = 8 * P.cam.width;
     unsigned n_seg = 0, n_smp = 0;                        // per task, flushed to the 64-bit global counters at task end
 
     // A warp task = PT consecutive pixels = PT * n_subset samples in pixel-major order.  Lanes pull the next
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
                         cur_p = p;
                     }
                     const int row = k / sqrt_spp;
-                    path_start(P.cam, P.seed, P.frame, base + p, k - row * sqrt_spp, P.sj_rem + row * P.sj_mod, path, g);
+                    path_start(P.cam, P.seed, P.frame, tile_to_global(base + p, band_px, P.tile_mod, P.tile_rem), k - row * sqrt_spp, P.sj_rem + row * P.sj_mod, path, g);
                     alive = true; n_smp++;
                 }
             }
@@ -126,10 +134,10 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
         }
         __syncwarp();
         if (P.accum_exact) {                                  // 4 words per pixel, coalesced over the task's pixels
-            if (lane < npx * 4) P.accum_exact[(size_t)base * 4 + lane] = part[warp][lane >> 2][lane & 3];
-            if (lane + 32 < npx * 4) P.accum_exact[(size_t)base * 4 + lane + 32] = part[warp][(lane + 32) >> 2][(lane + 32) & 3];
+            if (lane < npx * 4) P.accum_exact[(size_t)tile_to_global(base + (lane >> 2), band_px, P.tile_mod, P.tile_rem) * 4 + (lane & 3)] = part[warp][lane >> 2][lane & 3];
+            if (lane + 32 < npx * 4) P.accum_exact[(size_t)tile_to_global(base + ((lane + 32) >> 2), band_px, P.tile_mod, P.tile_rem) * 4 + (lane & 3)] = part[warp][(lane + 32) >> 2][(lane + 32) & 3];
         } else if (lane < npx)
-            P.accum[base + lane] = fx_resolve((long long)part[warp][lane][0], (long long)part[warp][lane][1], (long long)part[warp][lane][2], part[warp][lane][3]);
+            P.accum[tile_to_global(base + lane, band_px, P.tile_mod, P.tile_rem)] = fx_resolve((long long)part[warp][lane][0], (long long)part[warp][lane][1], (long long)part[warp][lane][2], part[warp][lane][3]);
         __syncwarp();
         for (int off = 16; off > 0; off >>= 1) { n_seg += __shfl_xor_sync(full, n_seg, off); n_smp += __shfl_xor_sync(full, n_smp, off); }
         if (lane == 0) { atomicAdd(P.counters, (unsigned long long)n_seg); atomicAdd(P.counters + 1, (unsigned long long)n_smp); }

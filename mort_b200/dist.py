@@ -26,6 +26,16 @@ def sample_split(rank: int, world: int):
     return world, rank
 
 
+def tile_split(rank: int, world: int):
+    """(tile_mod, tile_rem) for mort_render_opts: rank r renders the 8-row bands b with b % world == r (round robin, so sky
+    and geometry are spread over all ranks) into an otherwise untouched — caller-zeroed — full-frame buffer; the same SUM
+    reduce (or a gather of the bands) assembles the frame.  Every pixel comes from exactly one rank: the assembled frame is
+    bit-identical to the single-GPU frame even for the float accumulation image."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return world, rank
+
+
 def rows_of_rank(sqrt_spp: int, rank: int, world: int) -> int:
     return len(range(rank, sqrt_spp, world))
 

@@ -134,6 +134,37 @@ def test_exact_accumulation_makes_any_sample_split_bit_identical(renderer):
         renderer.render_device(full.data_ptr(), exact_accum=1, mode=MODE_WAVEFRONT)
 
 
+def test_tile_split_assembles_the_same_frame(renderer):
+    """8-row bands dealt round-robin to N virtual ranks; each pixel is rendered by exactly one rank -> bit-identical frame"""
+    import torch
+    from mort_b200 import dist as D
+    renderer.build_scene(1).override_camera(width=100, spp=16, depth=20).commit()      # 100 x 56: the last band is partial
+    st = renderer.stats
+    H, W = st["height"], st["width"]
+    full = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
+    renderer.render_device(full.data_ptr(), seed=8)
+    for world in (2, 3, 8):
+        tot = torch.zeros_like(full)
+        seen = torch.zeros(H, dtype=torch.int32)
+        for r in range(world):
+            part = torch.zeros_like(full)
+            mod, rem = D.tile_split(r, world)
+            renderer.render_device(part.data_ptr(), seed=8, tile_mod=mod, tile_rem=rem)
+            torch.cuda.synchronize()
+            rows = (part.abs().sum(dim=(1, 2)) > 0).cpu()
+            want = torch.tensor([(y // 8) % world == r for y in range(H)])
+            assert bool((rows <= want).all()), "a rank wrote outside its bands"
+            seen += rows.int()
+            tot += part
+        torch.cuda.synchronize()
+        assert torch.equal(torch.nan_to_num(tot, nan=-1.0), torch.nan_to_num(full, nan=-1.0)), f"{world}-way tile split differs"
+    from mort_b200.api import MortError, MODE_WAVEFRONT
+    with pytest.raises(MortError):
+        renderer.render_device(full.data_ptr(), tile_mod=2, tile_rem=2)
+    with pytest.raises(MortError):
+        renderer.render_device(full.data_ptr(), tile_mod=2, tile_rem=1, mode=MODE_WAVEFRONT)
+
+
 def test_staging_and_launch_shapes_do_not_change_the_image(renderer):
     renderer.build_scene(1).override_camera(width=96, spp=25, depth=50).commit()
     base = renderer.render(seed=9).accum
