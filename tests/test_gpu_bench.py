@@ -40,5 +40,9 @@ def test_reference_arm_json_line():
         assert d["impl"] == "reference" and "unavailable" in d
         return
     d = _run("--impl", "reference", "--steps", "1", "--warmup", "1")
+    if "unavailable" in d:                       # the reference kernel itself is not ours to fix: report why, try once more
+        print("reference arm unavailable:", d["unavailable"])
+        d = _run("--impl", "reference", "--steps", "1", "--warmup", "1")
+    assert "unavailable" not in d, d
     assert BASE_KEYS <= set(d) and d["impl"] == "reference" and d["metric"] == "Msamples/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
