@@ -288,6 +288,9 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     int PT = p.n_subset > 0 ? (task_samples + p.n_subset - 1) / p.n_subset : 1;
     PT = std::max(1, std::min(16, PT));
     p.lanes_per_pixel = PT;
+    // guided tail: tasks shrink to >= 256 samples (8 per lane) in the last round of the frame
+    p.min_task_px = p.n_subset > 0 ? std::max(1, std::min(PT, (256 + p.n_subset - 1) / p.n_subset)) : PT;
+    if (const char* e = getenv("MORT_TAIL")) { if (atoi(e) == 0) p.min_task_px = PT; }                    // experiments only
     if (o.exact_accum && o.mode != MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render: exact_accum is a megakernel feature");
     p.accum = o.exact_accum ? nullptr : reinterpret_cast<float4*>(d_accum);
     p.accum_exact = o.exact_accum ? reinterpret_cast<unsigned long long*>(d_accum) : nullptr;

@@ -40,6 +40,18 @@ __device__ __forceinline__ float4 fx_resolve(long long r, long long g, long long
     return o;
 }
 
+// 64-bit add into shared memory as two native 32-bit atomics.  atomicAdd(unsigned long long*) on shared memory compiles to a
+// compare-and-swap spin loop (ATOMS.CAST.SPIN.64; 5 % of the stall samples on scene 1).  The low words wrap exactly
+// floor(sum / 2^32) times whatever the order, so carrying each wrap into the high word keeps the sum exact mod 2^64.
+__device__ __forceinline__ void smem_add64(unsigned long long* p, unsigned long long v) {
+    if (v == 0ull) return;
+    unsigned* w = reinterpret_cast<unsigned*>(p);
+    const unsigned lo = (unsigned)v;
+    const unsigned old = atomicAdd(w, lo);
+    const unsigned hi = (unsigned)(v >> 32) + ((old + lo) < lo ? 1u : 0u);
+    if (hi) atomicAdd(w + 1, hi);
+}
+
 // kMinBlocks = occupancy target handed to ptxas (register cap 65536 / (128 * kMinBlocks)): 4 -> 128 regs,
 // 6 -> 80, 8 -> 64.  Which one wins is a measurement (profiles/), selectable through mort_render_opts.blocks_per_sm.
 // tile split: the rank's pixels are its 8-row bands packed back to back; local index -> frame index
@@ -74,12 +86,23 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
     // A warp task = PT consecutive pixels = PT * n_subset samples in pixel-major order.  Lanes pull the next
     // sample the moment their path ends (ballot + prefix count: deterministic, no atomics), so the warp only
     // idles in the last few iterations of a task instead of after every lane's private quota.
+    // Guided hand-out: once fewer than one full task per warp is left, tasks shrink with the remaining work (down to
+    // P.min_task_px pixels) so the last round of the frame is spread over every warp instead of leaving most of
+    // them idle behind the few that drew a late full-size task.  The peek is racy on purpose: any chunk size is
+    // valid, and the exact accumulation makes the frame independent of how pixels were grouped into tasks.
+    const int n_warps = (int)gridDim.x * (int)(blockDim.x >> 5);
     for (;;) {
-        int base = 0;
-        if (lane == 0) base = (int)atomicAdd(P.work_counter, (unsigned)PT);
-        base = __shfl_sync(full, base, 0);
+        int base = 0, chunk = PT;
+        if (lane == 0) {
+            if (P.min_task_px < PT) {
+                const int left = P.n_pixels - (int)*reinterpret_cast<volatile unsigned int*>(P.work_counter);
+                if (left < n_warps * PT) chunk = max(P.min_task_px, min(PT, left / n_warps));
+            }
+            base = (int)atomicAdd(P.work_counter, (unsigned)chunk);
+        }
+        base = __shfl_sync(full, base, 0); chunk = __shfl_sync(full, chunk, 0);
         if (base >= P.n_pixels) break;
-        const int npx = min(PT, P.n_pixels - base);
+        const int npx = min(chunk, P.n_pixels - base);
         const int items = npx * n_subset;
         if (lane < npx * 4) part[warp][lane >> 2][lane & 3] = 0ull;
         if (lane + 32 < npx * 4) part[warp][(lane + 32) >> 2][(lane + 32) & 3] = 0ull;
@@ -101,7 +124,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
                     if (p != cur_p) {
                         if (cur_p >= 0) {                 // pixel switch: hand the finished partial sums over
 #pragma unroll
-                            for (int c = 0; c < 4; c++) { atomicAdd(&part[warp][cur_p][c], lacc[warp][c][lane]); lacc[warp][c][lane] = 0ull; }
+                            for (int c = 0; c < 4; c++) { smem_add64(&part[warp][cur_p][c], lacc[warp][c][lane]); lacc[warp][c][lane] = 0ull; }
                         }
                         cur_p = p;
                     }
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
         }
         if (cur_p >= 0) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) atomicAdd(&part[warp][cur_p][c], lacc[warp][c][lane]);
+            for (int c = 0; c < 4; c++) smem_add64(&part[warp][cur_p][c], lacc[warp][c][lane]);
         }
         __syncwarp();
         if (P.accum_exact) {                                  // 4 words per pixel, coalesced over the task's pixels

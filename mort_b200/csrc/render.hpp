@@ -16,6 +16,7 @@ struct FrameParams {
     int32_t n_rows;                 // strata rows this call renders
     int32_t n_subset;               // samples per pixel this call renders = n_rows * sqrt_spp
     int32_t lanes_per_pixel;        // megakernel: pixels per warp task (1..16)
+    int32_t min_task_px;            // megakernel: smallest task the guided tail hands out (== lanes_per_pixel: fixed-size tasks)
     int32_t n_pixels;               // pixels THIS call renders (all of them, or the rank's 8-row bands)
     int32_t tile_mod, tile_rem;     // tile split: local pixel index -> global pixel through 8-row bands b = k * tile_mod + tile_rem
     int32_t n_staged;               // BVH nodes copied to shared memory per block

@@ -357,7 +357,7 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
             for (int k = 0; k < 4; k++) {
                 float tnear = fmaxf(fmaxf(fmaf(nxa[k], idx, -oix), fmaf(nya[k], idy, -oiy)), fmaxf(fmaf(nza[k], idz, -oiz), tmin));
                 float tfar = fminf(fminf(fmaf(fxa[k], idx, -oix), fmaf(fya[k], idy, -oiy)), fminf(fmaf(fza[k], idz, -oiz), best.t));
-                bool h = (tnear <= tfar) && (cw[k] != MORT_CHILD_EMPTY);
+                bool h = tnear <= tfar;                         // empty slots carry an inverted box (lo = +inf, hi = -inf): never hit
                 tn[k] = h ? tnear : INFINITY;
                 cw[k] = h ? cw[k] : MORT_CHILD_EMPTY;
             }
@@ -368,7 +368,7 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
             // push far-to-near, continue with the nearest; nothing hit -> pop
 #pragma unroll
             for (int k = 3; k >= 1; k--)
-                if (cw[k] != MORT_CHILD_EMPTY && sp < MORT_STACK) { stack_c[sp] = cw[k]; stack_t[sp] = tn[k]; sp++; }
+                if (cw[k] != MORT_CHILD_EMPTY) { stack_c[sp] = cw[k]; stack_t[sp] = tn[k]; sp++; }   // depth * 3 <= MORT_STACK is checked at commit
             uint32_t next = cw[0];
             if (next == MORT_CHILD_EMPTY) {
                 // entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit
