@@ -104,7 +104,9 @@ typedef struct {
     int32_t exact_accum;           /* 1: d_accum receives W*H x 4 uint64 (exact fixed-point sums, see mort_resolve_exact_device) */
     int32_t tile_mod, tile_rem;    /* tile-split across GPUs (megakernel): this call renders the 8-row bands b with b % mod == rem and leaves
                                       every other pixel of d_accum untouched (0,0 or 1,0 = whole frame) */
-    int32_t reserved[4];
+    int32_t accumulate;            /* exact_accum only: 1 = ADD this call's sums to the contents of d_accum (progressive rendering:
+                                      render frame 0 with 0, frames 1.. with 1, a new `frame` each time), 0 = overwrite */
+    int32_t reserved[3];
 } mort_render_opts;
 void mort_default_render_opts(mort_render_opts* o);
 
@@ -118,6 +120,30 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts, void* d_accu
  * added in ANY order (e.g. by an int64 SUM all-reduce) and the N-GPU frame equals the 1-GPU frame bit for bit.
  * mort_resolve_exact_device turns it into the float4 accumulation image described above. */
 int mort_resolve_exact_device(mort_ctx* ctx, const void* d_exact, void* d_accum);
+/* ---- progressive accumulation + checkpoint / resume --------------------------------------------------------
+ * The reference renders the same frame again on every idle callback and shows the latest one (mort.cu:99-119,
+ * gpu_anim.h) — nothing accumulates and nothing survives the process.  Here frames with different `frame` keys are
+ * independent sample sets of the same image, and their exact sums add in any order, so a long render can be split
+ * into frames, stopped, saved and resumed without changing a bit of the result.
+ * Limits of the flag word when many frames are added: 2^20-1 NaN samples and 2^14-1 +inf samples per channel per pixel. */
+/* d_sum += d_frame (both W*H x 4 uint64, device).  Also merges partial frames rendered elsewhere. */
+int mort_accumulate_exact_device(mort_ctx* ctx, void* d_sum, const void* d_frame);
+/* 64-bit fingerprint of the committed scene + camera (what a checkpoint is only valid for) */
+int mort_scene_fingerprint(mort_ctx* ctx, uint64_t* out);
+/* Checkpoint file = {magic, version, W, H, samples per pixel per frame, frames_done, seed, fingerprint} + the exact sums.
+ * Load verifies W, H, samples per frame and the fingerprint against the committed scene (MORT_ERR_STATE on mismatch). */
+int mort_save_checkpoint(mort_ctx* ctx, const char* path, const void* d_sum, uint32_t seed, uint32_t frames_done);
+int mort_load_checkpoint(mort_ctx* ctx, const char* path, void* d_sum, uint32_t* seed, uint32_t* frames_done);
+/* Host-buffer progressive render: adds n_frames more frames (frame keys frames_done .. frames_done + n_frames - 1) to a
+ * context-owned exact image and returns the mean over ALL frames so far, tone-mapped (rgba8_out, may be NULL) and as float
+ * sums (accum_out, may be NULL; divide by samples_per_pixel * *frames_total).  checkpoint_path (may be NULL): with
+ * resume != 0 an existing file is loaded first (its seed must equal opts->seed), and the file is rewritten after the last
+ * frame.  Rendering k frames, stopping, and resuming for the rest gives the same bits as rendering them in one call. */
+int mort_render_progressive(mort_ctx* ctx, const mort_render_opts* opts, int n_frames, const char* checkpoint_path, int resume,
+                            uint8_t* rgba8_out, float* accum_out, uint32_t* frames_total);
+/* forget the running image (it also restarts by itself when the scene, the camera, the frame size or the seed changes) */
+int mort_reset_progressive(mort_ctx* ctx);
+
 /* Tone pipeline of camera.cuh:194-207 on device: mean over n_samples, NaN flush, gamma 2, quantise to RGBA8
  * (w=255).  d_rgba8 is a device pointer to W*H*4 bytes. */
 int mort_tonemap_device(mort_ctx* ctx, const void* d_accum, int samples_per_pixel_total, void* d_rgba8);

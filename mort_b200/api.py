@@ -47,7 +47,7 @@ class CameraDesc(C.Structure):
 class RenderOpts(C.Structure):
     _fields_ = [("seed", C.c_uint32), ("frame", C.c_uint32), ("mode", C.c_int32), ("sample_mod", C.c_int32),
                 ("sample_rem", C.c_int32), ("stage_nodes", C.c_int32), ("threads_per_block", C.c_int32),
-                ("blocks_per_sm", C.c_int32), ("wavefront_paths", C.c_int32), ("exact_accum", C.c_int32), ("tile_mod", C.c_int32), ("tile_rem", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("blocks_per_sm", C.c_int32), ("wavefront_paths", C.c_int32), ("exact_accum", C.c_int32), ("tile_mod", C.c_int32), ("tile_rem", C.c_int32), ("accumulate", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Stats(C.Structure):
@@ -75,6 +75,8 @@ ABI_SYMBOLS = [
     "mort_host_rand",
     "mort_get_camera", "mort_set_camera", "mort_override_camera", "mort_get_camera_record",
     "mort_commit", "mort_default_render_opts", "mort_render_device", "mort_resolve_exact_device", "mort_tonemap_device", "mort_render",
+    "mort_accumulate_exact_device", "mort_scene_fingerprint", "mort_save_checkpoint", "mort_load_checkpoint",
+    "mort_render_progressive", "mort_reset_progressive",
     "mort_trace", "mort_get_stats",
 ]
 
@@ -108,6 +110,10 @@ def load_library():
         "mort_override_camera": [P, I, Fl, I, I], "mort_get_camera_record": [P, P],
         "mort_commit": [P], "mort_default_render_opts": [C.POINTER(RenderOpts)],
         "mort_render_device": [P, C.POINTER(RenderOpts), P], "mort_resolve_exact_device": [P, P, P], "mort_tonemap_device": [P, P, I, P],
+        "mort_accumulate_exact_device": [P, P, P], "mort_scene_fingerprint": [P, C.POINTER(C.c_uint64)],
+        "mort_save_checkpoint": [P, C.c_char_p, P, C.c_uint32, C.c_uint32],
+        "mort_load_checkpoint": [P, C.c_char_p, P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
+        "mort_render_progressive": [P, C.POINTER(RenderOpts), I, C.c_char_p, I, P, P, C.POINTER(C.c_uint32)], "mort_reset_progressive": [P],
         "mort_render": [P, C.POINTER(RenderOpts), P, P], "mort_trace": [P, P, I, P, P, I], "mort_get_stats": [P, C.POINTER(Stats)],
     }
     for name, args in sig.items():
@@ -278,6 +284,42 @@ class Renderer:
     def resolve_exact_device(self, d_exact_ptr: int, d_accum_ptr: int):
         """(H, W, 4) uint64 exact sums (render_device(..., exact_accum=1)) -> (H, W, 4) float32 accumulation image."""
         self._ck(self._L.mort_resolve_exact_device(self._h, C.c_void_p(d_exact_ptr), C.c_void_p(d_accum_ptr)))
+
+    # -- progressive accumulation + checkpoint / resume --
+    def accumulate_exact_device(self, d_sum_ptr: int, d_frame_ptr: int):
+        """d_sum += d_frame over (H, W, 4) uint64 exact sums (merging partial frames; order never matters)."""
+        self._ck(self._L.mort_accumulate_exact_device(self._h, C.c_void_p(d_sum_ptr), C.c_void_p(d_frame_ptr)))
+
+    @property
+    def scene_fingerprint(self) -> int:
+        v = C.c_uint64(0)
+        self._ck(self._L.mort_scene_fingerprint(self._h, C.byref(v)))
+        return v.value
+
+    def save_checkpoint(self, path, d_sum_ptr: int, seed: int, frames_done: int):
+        self._ck(self._L.mort_save_checkpoint(self._h, os.fsencode(path), C.c_void_p(d_sum_ptr), int(seed), int(frames_done)))
+
+    def load_checkpoint(self, path, d_sum_ptr: int):
+        """-> (seed, frames_done); MortError if the file belongs to another scene, camera or frame size."""
+        seed, done = C.c_uint32(0), C.c_uint32(0)
+        self._ck(self._L.mort_load_checkpoint(self._h, os.fsencode(path), C.c_void_p(d_sum_ptr), C.byref(seed), C.byref(done)))
+        return seed.value, done.value
+
+    def render_progressive(self, n_frames: int, checkpoint=None, resume=False, want_rgba8=True, want_accum=True, **opts):
+        """Adds n_frames frames to the context's running image (mort_render_progressive).
+        -> (Frame, frames_total): Frame.accum holds float SUMS over all frames so far (divide by spp * frames_total)."""
+        st = self.stats
+        H, W = st["height"], st["width"]
+        rgba = np.empty((H, W, 4), dtype=np.uint8) if want_rgba8 else None
+        acc = np.empty((H, W, 4), dtype=np.float32) if want_accum else None
+        total = C.c_uint32(0)
+        o = self.opts(**opts)
+        self._ck(self._L.mort_render_progressive(self._h, C.byref(o), int(n_frames), os.fsencode(checkpoint) if checkpoint else None, int(bool(resume)),
+                                                 rgba.ctypes.data if rgba is not None else None, acc.ctypes.data if acc is not None else None, C.byref(total)))
+        return Frame(acc, rgba, self.stats), total.value
+
+    def reset_progressive(self):
+        self._ck(self._L.mort_reset_progressive(self._h))
 
     def tonemap_device(self, d_accum_ptr: int, samples_per_pixel_total: int, d_rgba8_ptr: int):
         self._ck(self._L.mort_tonemap_device(self._h, C.c_void_p(d_accum_ptr), int(samples_per_pixel_total), C.c_void_p(d_rgba8_ptr)))

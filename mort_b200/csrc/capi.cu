@@ -60,12 +60,21 @@ struct mort_ctx {
     std::string err;
     mort_stats stats;
     double upload_ms = 0;
+    uint64_t geometry_hash = 0;
+    unsigned long long* d_prog = nullptr; size_t prog_pixels = 0;   // progressive exact image (mort_render_progressive)
+    uint64_t prog_fingerprint = 0; uint32_t prog_frames = 0, prog_seed = 0;
 };
 
 #define CTX_CHECK(c) do { if (!(c)) return MORT_ERR_ARG; } while (0)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MORT_ERR_CUDA; } } while (0)
 
 static int fail(mort_ctx* ctx, int code, const std::string& m) { ctx->err = m; return code; }
+static uint64_t fingerprint(const mort_ctx* ctx) {      // committed geometry + current camera (FNV-1a 64)
+    uint64_t h = ctx->geometry_hash;
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(&ctx->flat.cam);
+    for (size_t i = 0; i < sizeof(ctx->flat.cam); i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
 static Handle H(mort_handle h) { return Handle{h.type, h.idx}; }
 static void put(mort_handle* out, Handle h) { if (out) { out->type = h.type; out->idx = h.idx; } }
 static V3 v3(const float* p) { return V3(p[0], p[1], p[2]); }
@@ -100,7 +109,7 @@ int mort_destroy(mort_ctx* ctx) {
     cudaDeviceSynchronize();
     ctx->arena.release();
     wavefront_free(ctx->wave);
-    cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_mat_offsets); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgba);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_mat_offsets); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgba); cudaFree(ctx->d_prog);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -239,6 +248,15 @@ int mort_commit(mort_ctx* ctx) {
     off[3] = off[2] + (int32_t)s.metals.size(); off[4] = off[3] + (int32_t)s.dielectrics.size(); off[5] = off[4] + (int32_t)s.lights.size();
     CU(cudaMemcpy(ctx->d_mat_offsets, off, sizeof(off), cudaMemcpyHostToDevice));
     ctx->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    // fingerprint of everything the kernels read (FNV-1a 64): ties a checkpoint to its scene and camera
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+    auto mixv = [&mix](const auto& v) { uint64_t n = v.size(); mix(&n, sizeof(n)); if (n) mix(v.data(), n * sizeof(v[0])); };
+    mixv(f.nodes); mixv(f.spheres); mixv(f.sphere_info); mixv(f.quads); mixv(f.instances); mixv(f.materials); mixv(f.textures);
+    mixv(f.noises); mixv(f.media); mixv(f.boundary); mixv(f.lights);
+    for (const ImageRec& im : ctx->scene.images) { int32_t wh[2] = {im.width, im.height}; mix(wh, sizeof(wh)); mixv(im.rgb); }
+    int32_t fl[5] = {f.light_kind, f.post_media_order, f.two_pass, f.empty, f.linear}; mix(fl, sizeof(fl));
+    ctx->geometry_hash = h;                              // the camera is mixed in on demand: it may move without a new commit
     ctx->committed = true;
     return MORT_OK;
 }
@@ -292,6 +310,8 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     p.min_task_px = p.n_subset > 0 ? std::max(1, std::min(PT, (256 + p.n_subset - 1) / p.n_subset)) : PT;
     if (const char* e = getenv("MORT_TAIL")) { if (atoi(e) == 0) p.min_task_px = PT; }                    // experiments only
     if (o.exact_accum && o.mode != MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render: exact_accum is a megakernel feature");
+    if (o.accumulate && !o.exact_accum) return fail(ctx, MORT_ERR_ARG, "mort_render: accumulate needs exact_accum (float sums are not order-independent)");
+    p.accumulate = o.accumulate ? 1 : 0;
     p.accum = o.exact_accum ? nullptr : reinterpret_cast<float4*>(d_accum);
     p.accum_exact = o.exact_accum ? reinterpret_cast<unsigned long long*>(d_accum) : nullptr;
     p.counters = ctx->d_counters; p.work_counter = ctx->d_work;
@@ -347,6 +367,139 @@ int mort_resolve_exact_device(mort_ctx* ctx, const void* d_exact, void* d_accum)
     const CameraParams& cam = ctx->flat.cam;
     CU(resolve_exact_launch(reinterpret_cast<const unsigned long long*>(d_exact), cam.width * cam.height, reinterpret_cast<float4*>(d_accum), ctx->stream));
     ctx->stats.last_kernel_launches += 1;
+    return MORT_OK;
+}
+
+// ---- progressive accumulation + checkpoint / resume -------------------------------------------------------
+int mort_accumulate_exact_device(mort_ctx* ctx, void* d_sum, const void* d_frame) {
+    CTX_CHECK(ctx && d_sum && d_frame);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "scene not committed");
+    const CameraParams& cam = ctx->flat.cam;
+    CU(accumulate_exact_launch(reinterpret_cast<unsigned long long*>(d_sum), reinterpret_cast<const unsigned long long*>(d_frame), cam.width * cam.height, ctx->stream));
+    ctx->stats.last_kernel_launches += 1;
+    return MORT_OK;
+}
+
+int mort_scene_fingerprint(mort_ctx* ctx, uint64_t* out) {
+    CTX_CHECK(ctx && out);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "scene not committed");
+    *out = fingerprint(ctx);
+    return MORT_OK;
+}
+
+namespace {
+struct CheckpointHeader {            // 64 bytes, little endian
+    char magic[4]; uint32_t version; int32_t width, height, samples_per_frame; uint32_t frames_done, seed, pad0;
+    uint64_t fingerprint, payload_bytes; uint64_t reserved[2];
+};
+static_assert(sizeof(CheckpointHeader) == 64, "checkpoint header layout");
+}  // namespace
+
+int mort_save_checkpoint(mort_ctx* ctx, const char* path, const void* d_sum, uint32_t seed, uint32_t frames_done) {
+    CTX_CHECK(ctx && path && d_sum);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "scene not committed");
+    const CameraParams& cam = ctx->flat.cam;
+    const size_t bytes = (size_t)cam.width * cam.height * 4 * sizeof(unsigned long long);
+    std::vector<unsigned long long> host((size_t)cam.width * cam.height * 4);
+    CU(cudaMemcpyAsync(host.data(), d_sum, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CheckpointHeader hd; memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, "MCKP", 4); hd.version = 1; hd.width = cam.width; hd.height = cam.height; hd.samples_per_frame = cam.sqrt_spp * cam.sqrt_spp;
+    hd.frames_done = frames_done; hd.seed = seed; hd.fingerprint = fingerprint(ctx); hd.payload_bytes = bytes;
+    // write to a sibling file and rename: a crash mid-write never destroys the previous checkpoint
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(ctx, MORT_ERR_IO, "cannot write " + tmp);
+    bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 && fwrite(host.data(), 1, bytes, f) == bytes;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return fail(ctx, MORT_ERR_IO, std::string("cannot write ") + path); }
+    return MORT_OK;
+}
+
+int mort_load_checkpoint(mort_ctx* ctx, const char* path, void* d_sum, uint32_t* seed, uint32_t* frames_done) {
+    CTX_CHECK(ctx && path && d_sum);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "scene not committed");
+    const CameraParams& cam = ctx->flat.cam;
+    const size_t bytes = (size_t)cam.width * cam.height * 4 * sizeof(unsigned long long);
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(ctx, MORT_ERR_IO, std::string("cannot read ") + path);
+    CheckpointHeader hd;
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "MCKP", 4) != 0 || hd.version != 1) { fclose(f); return fail(ctx, MORT_ERR_IO, std::string(path) + ": not a mort checkpoint"); }
+    if (hd.width != cam.width || hd.height != cam.height || hd.samples_per_frame != cam.sqrt_spp * cam.sqrt_spp || hd.fingerprint != fingerprint(ctx) || hd.payload_bytes != bytes) {
+        fclose(f);
+        return fail(ctx, MORT_ERR_STATE, std::string(path) + ": checkpoint belongs to a different scene, camera or frame size");
+    }
+    std::vector<unsigned long long> host((size_t)cam.width * cam.height * 4);
+    const bool ok = fread(host.data(), 1, bytes, f) == bytes;
+    fclose(f);
+    if (!ok) return fail(ctx, MORT_ERR_IO, std::string(path) + ": truncated checkpoint");
+    CU(cudaMemcpyAsync(d_sum, host.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (seed) *seed = hd.seed;
+    if (frames_done) *frames_done = hd.frames_done;
+    return MORT_OK;
+}
+
+int mort_reset_progressive(mort_ctx* ctx) { CTX_CHECK(ctx); ctx->prog_frames = 0; ctx->prog_fingerprint = 0; return MORT_OK; }
+
+int mort_render_progressive(mort_ctx* ctx, const mort_render_opts* opts, int n_frames, const char* checkpoint_path, int resume,
+                            uint8_t* rgba8_out, float* accum_out, uint32_t* frames_total) {
+    CTX_CHECK(ctx);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "mort_render_progressive: scene not committed (call mort_commit)");
+    if (n_frames < 0) return fail(ctx, MORT_ERR_ARG, "mort_render_progressive: n_frames < 0");
+    CU(cudaSetDevice(ctx->device));
+    const CameraParams& cam = ctx->flat.cam;
+    const size_t npix = (size_t)cam.width * cam.height;
+    int rc = ensure_accum(ctx, npix);
+    if (rc != MORT_OK) return rc;
+    mort_render_opts o; if (opts) o = *opts; else mort_default_render_opts(&o);
+    if (o.mode != MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render_progressive: megakernel only (exact sums)");
+    // the running image restarts when the scene, the camera, the frame size or the seed changed
+    const uint64_t fp = fingerprint(ctx);
+    if (ctx->prog_pixels != npix || ctx->prog_fingerprint != fp || ctx->prog_seed != o.seed || !ctx->d_prog) {
+        if (ctx->prog_pixels != npix || !ctx->d_prog) {
+            cudaFree(ctx->d_prog); ctx->d_prog = nullptr; ctx->prog_pixels = 0;
+            CU(cudaMalloc(&ctx->d_prog, npix * 4 * sizeof(unsigned long long))); ctx->prog_pixels = npix;
+        }
+        ctx->prog_fingerprint = fp; ctx->prog_seed = o.seed; ctx->prog_frames = 0;
+    }
+    if (checkpoint_path && resume) {
+        FILE* probe = fopen(checkpoint_path, "rb");
+        if (probe) {
+            fclose(probe);
+            uint32_t seed = 0, done = 0;
+            rc = mort_load_checkpoint(ctx, checkpoint_path, ctx->d_prog, &seed, &done);
+            if (rc != MORT_OK) return rc;
+            if (seed != o.seed) return fail(ctx, MORT_ERR_STATE, std::string(checkpoint_path) + ": checkpoint was rendered with a different seed");
+            ctx->prog_frames = done;
+        }
+    }
+    double ms = 0; uint64_t segs = 0, smps = 0, launches = 0;
+    for (int f = 0; f < n_frames; f++) {
+        o.exact_accum = 1; o.accumulate = ctx->prog_frames > 0 ? 1 : 0; o.frame = ctx->prog_frames;
+        rc = mort_render_device(ctx, &o, ctx->d_prog);
+        if (rc != MORT_OK) return rc;
+        ctx->prog_frames++;
+        ms += ctx->stats.last_render_ms; segs += ctx->stats.last_segments; smps += ctx->stats.last_samples; launches += ctx->stats.last_kernel_launches;
+    }
+    if (ctx->prog_frames == 0) return fail(ctx, MORT_ERR_STATE, "mort_render_progressive: no frame rendered or resumed yet");
+    if (checkpoint_path && (n_frames > 0 || !resume)) {
+        rc = mort_save_checkpoint(ctx, checkpoint_path, ctx->d_prog, o.seed, ctx->prog_frames);
+        if (rc != MORT_OK) return rc;
+    }
+    rc = mort_resolve_exact_device(ctx, ctx->d_prog, ctx->d_accum);
+    if (rc != MORT_OK) return rc;
+    if (rgba8_out) {
+        const long long spp_total = (long long)cam.sqrt_spp * cam.sqrt_spp * ctx->prog_frames;
+        if (spp_total > 0x7FFFFFFF) return fail(ctx, MORT_ERR_ARG, "mort_render_progressive: more than 2^31 samples per pixel");
+        rc = mort_tonemap_device(ctx, ctx->d_accum, (int)spp_total, ctx->d_rgba);
+        if (rc != MORT_OK) return rc;
+        CU(cudaMemcpyAsync(rgba8_out, ctx->d_rgba, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (accum_out) CU(cudaMemcpyAsync(accum_out, ctx->d_accum, npix * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n_frames > 0) { ctx->stats.last_render_ms = ms; ctx->stats.last_segments = segs; ctx->stats.last_samples = smps; ctx->stats.last_kernel_launches = launches + 2; }
+    if (frames_total) *frames_total = ctx->prog_frames;
     return MORT_OK;
 }
 

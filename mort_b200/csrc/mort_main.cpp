@@ -2,6 +2,8 @@
 // window and re-rendering forever (gpu_anim.h, out of scope on a headless B200 box) it renders `--frames`
 // frames through the C ABI, prints the reference's "Avg. time per frame" line (mort.cu:116-119) and writes
 // the image as PPM (top-down; the frame itself is bottom-up like the reference's, camera.cuh:70-78).
+// `--accumulate` turns the frame loop into a progressive render (every frame adds a new sample set to the same
+// image; `--checkpoint FILE [--resume]` saves / continues it), `--load FILE.mscn` renders a dumped scene.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -12,13 +14,15 @@
 
 static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
                             "            [--mode mega|wave] [--stage N] [--bps blocks/SM] [--tpb threads] [--field G [--fieldcam 0|1]]\n"
-                            "            [--assets DIR] [--out image.ppm] [--hdr image.pfm] [--device K]\n"); return -1; }
+                            "            [--assets DIR] [--out image.ppm] [--hdr image.pfm] [--device K] [--load scene.mscn] [--dump scene.mscn]\n"
+                            "            [--accumulate [--checkpoint FILE [--resume]]]\n"); return -1; }
 
 int main(int argc, char** argv) {
     if (argc < 2) return usage();                       // mort.cu:638-641
     int scene = atoi(argv[1]);
     int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = -1, mode = MORT_MODE_MEGAKERNEL, bps = 0, tpb = 0, field = 0, fieldcam = 0;
-    float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr;
+    float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr, load, dump, ckpt;
+    bool accumulate = false, resume = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         auto nx = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(-1); } return argv[++i]; };
@@ -27,6 +31,8 @@ int main(int argc, char** argv) {
         else if (a == "--seed") seed = (unsigned)strtoul(nx(), 0, 10); else if (a == "--frames") frames = atoi(nx());
         else if (a == "--assets") assets = nx(); else if (a == "--out") out = nx(); else if (a == "--hdr") hdr = nx(); else if (a == "--device") device = atoi(nx());
         else if (a == "--stage") stage = atoi(nx());
+        else if (a == "--load") load = nx(); else if (a == "--dump") dump = nx();
+        else if (a == "--accumulate") accumulate = true; else if (a == "--checkpoint") ckpt = nx(); else if (a == "--resume") resume = true;
         else if (a == "--bps") bps = atoi(nx()); else if (a == "--tpb") tpb = atoi(nx());
         else if (a == "--field") field = atoi(nx()); else if (a == "--fieldcam") fieldcam = atoi(nx());
         else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : MORT_MODE_MEGAKERNEL; }
@@ -35,15 +41,31 @@ int main(int argc, char** argv) {
     mort_ctx* ctx = nullptr;
     if (mort_create(device, &ctx) != MORT_OK) { fprintf(stderr, "mort: no usable CUDA device %d (this renderer has no CPU path)\n", device); return 2; }
     auto die = [&](const char* what) { fprintf(stderr, "mort: %s: %s\n", what, mort_last_error(ctx)); mort_destroy(ctx); return 3; };
-    if (field > 0) { if (mort_build_sphere_field(ctx, field, 69420, fieldcam) != MORT_OK) return die("sphere field"); }
+    if (!load.empty()) { if (mort_load_scene(ctx, load.c_str(), assets.c_str()) != MORT_OK) return die("load"); }
+    else if (field > 0) { if (mort_build_sphere_field(ctx, field, 69420, fieldcam) != MORT_OK) return die("sphere field"); }
     else if (mort_build_scene(ctx, scene, assets.c_str()) != MORT_OK) return die("scene");
     if (mort_override_camera(ctx, width, aspect, spp, depth) != MORT_OK) return die("camera");
+    if (!dump.empty() && mort_dump_scene(ctx, dump.c_str()) != MORT_OK) return die("dump");
     if (mort_commit(ctx) != MORT_OK) return die("commit");
     mort_stats st; mort_get_stats(ctx, &st);
     std::vector<uint8_t> img((size_t)st.width * st.height * 4);
     std::vector<float> acc(hdr.empty() ? 0 : (size_t)st.width * st.height * 4);
     mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.stage_nodes = stage; o.blocks_per_sm = bps; o.threads_per_block = tpb;
     double total = 0;
+    uint32_t frames_total = 1;                         // frames averaged into the written image
+    if (accumulate) {
+        // one call per frame so the reference's running "Avg. time per frame" line keeps its meaning; the checkpoint
+        // (if any) is read before the first frame and rewritten after every frame
+        for (int f = 0; f < frames; f++) {
+            const bool last = f + 1 == frames;
+            if (mort_render_progressive(ctx, &o, 1, ckpt.empty() ? nullptr : ckpt.c_str(), (resume || f > 0) ? 1 : 0, last ? img.data() : nullptr,
+                                        (last && !acc.empty()) ? acc.data() : nullptr, &frames_total) != MORT_OK) return die("render");
+            mort_get_stats(ctx, &st);
+            total += st.last_render_ms;
+            printf("Avg. time per frame: %3.1f ms\n", total / (f + 1));
+        }
+        printf("{\"frames_accumulated\":%u,\"spp_total\":%lld}\n", frames_total, (long long)frames_total * st.sqrt_spp * st.sqrt_spp);
+    } else
     for (int f = 0; f < frames; f++) {
         o.frame = (uint32_t)f;
         if (mort_render(ctx, &o, img.data(), acc.empty() ? nullptr : acc.data()) != MORT_OK) return die("render");
@@ -67,7 +89,7 @@ int main(int argc, char** argv) {
         FILE* f = fopen(hdr.c_str(), "wb");
         if (!f) { perror(hdr.c_str()); mort_destroy(ctx); return 4; }
         fprintf(f, "PF\n%d %d\n-1.0\n", st.width, st.height);
-        const float inv = 1.0f / (float)(st.sqrt_spp * st.sqrt_spp);
+        const float inv = (float)(1.0 / ((double)st.sqrt_spp * st.sqrt_spp * frames_total));
         for (size_t i = 0; i < (size_t)st.width * st.height; i++) { float px[3] = {acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv}; fwrite(px, 4, 3, f); }
         fclose(f);
     }

@@ -157,8 +157,17 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
         }
         __syncwarp();
         if (P.accum_exact) {                                  // 4 words per pixel, coalesced over the task's pixels
-            if (lane < npx * 4) P.accum_exact[(size_t)tile_to_global(base + (lane >> 2), band_px, P.tile_mod, P.tile_rem) * 4 + (lane & 3)] = part[warp][lane >> 2][lane & 3];
-            if (lane + 32 < npx * 4) P.accum_exact[(size_t)tile_to_global(base + ((lane + 32) >> 2), band_px, P.tile_mod, P.tile_rem) * 4 + (lane & 3)] = part[warp][(lane + 32) >> 2][(lane + 32) & 3];
+            // every pixel belongs to exactly one task of a launch, so the progressive "+=" needs no atomics
+#pragma unroll
+            for (int h = 0; h < 64; h += 32) {
+                const int l = lane + h;
+                if (l < npx * 4) {
+                    unsigned long long* dst = P.accum_exact + (size_t)tile_to_global(base + (l >> 2), band_px, P.tile_mod, P.tile_rem) * 4 + (l & 3);
+                    unsigned long long v = part[warp][l >> 2][l & 3];
+                    if (P.accumulate) v += *dst;
+                    *dst = v;
+                }
+            }
         } else if (lane < npx)
             P.accum[tile_to_global(base + lane, band_px, P.tile_mod, P.tile_rem)] = fx_resolve((long long)part[warp][lane][0], (long long)part[warp][lane][1], (long long)part[warp][lane][2], part[warp][lane][3]);
         __syncwarp();
@@ -255,6 +264,20 @@ __global__ void __launch_bounds__(256) resolve_exact_kernel(const unsigned long 
     if (i >= n) return;
     const ulonglong2 a = reinterpret_cast<const ulonglong2*>(ex)[2 * (size_t)i], b = reinterpret_cast<const ulonglong2*>(ex)[2 * (size_t)i + 1];
     out[i] = fx_resolve((long long)a.x, (long long)a.y, (long long)b.x, b.y);
+}
+// progressive accumulation / merging partial frames: sum += frame, word by word (the sums are integers: any order, any grouping)
+__global__ void __launch_bounds__(256) accumulate_exact_kernel(ulonglong2* __restrict__ sum, const ulonglong2* __restrict__ frame, size_t n2) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    ulonglong2 a = sum[i]; const ulonglong2 b = frame[i];
+    a.x += b.x; a.y += b.y;
+    sum[i] = a;
+}
+cudaError_t accumulate_exact_launch(unsigned long long* d_sum, const unsigned long long* d_frame, int n_pixels, cudaStream_t st) {
+    if (n_pixels <= 0) return cudaSuccess;
+    const size_t n2 = (size_t)n_pixels * 2;
+    accumulate_exact_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(reinterpret_cast<ulonglong2*>(d_sum), reinterpret_cast<const ulonglong2*>(d_frame), n2);
+    return cudaGetLastError();
 }
 cudaError_t resolve_exact_launch(const unsigned long long* d_exact, int n_pixels, float4* d_accum, cudaStream_t st) {
     if (n_pixels <= 0) return cudaSuccess;

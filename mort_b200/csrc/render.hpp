@@ -20,6 +20,7 @@ struct FrameParams {
     int32_t n_pixels;               // pixels THIS call renders (all of them, or the rank's 8-row bands)
     int32_t tile_mod, tile_rem;     // tile split: local pixel index -> global pixel through 8-row bands b = k * tile_mod + tile_rem
     int32_t n_staged;               // BVH nodes copied to shared memory per block
+    int32_t accumulate;             // exact frames only: add this call's sums to what accum_exact already holds
     float4* accum;                  // W*H (null when accum_exact is used)
     unsigned long long* accum_exact;// W*H x 4 (r, g, b fixed point, flags) or null
     unsigned long long* counters;   // [0] segments, [1] samples
@@ -42,6 +43,7 @@ cudaError_t wavefront_render(const FrameParams& p, WavefrontBuffers* buf, int n_
 // parity hook + tone pipeline (render.cu)
 cudaError_t trace_launch(const DeviceScene& sc, const float* d_rays, int n, mhit_record* d_out, mhit_medium_probe* d_probes,
                          int brute_force, const int32_t* d_mat_offsets, cudaStream_t st);
+cudaError_t accumulate_exact_launch(unsigned long long* d_sum, const unsigned long long* d_frame, int n_pixels, cudaStream_t st);
 cudaError_t resolve_exact_launch(const unsigned long long* d_exact, int n_pixels, float4* d_accum, cudaStream_t st);
 cudaError_t tonemap_launch(const float4* d_accum, int n_pixels, float scale, uint8_t* d_rgba8, cudaStream_t st);
 
