@@ -48,6 +48,11 @@ int mort_build_scene(mort_ctx* ctx, int scene_id, const char* asset_dir);
 int mort_build_sphere_field(mort_ctx* ctx, int G, uint64_t seed, int camera_kind);
 int mort_load_scene(mort_ctx* ctx, const char* mscn_path, const char* asset_dir);
 int mort_dump_scene(mort_ctx* ctx, const char* mscn_path);
+/* Scene text (grammar: mort_b200/csrc/scene_text.cpp): one builder call per statement, so user scenes and the synthetic
+ * fields need no recompile (the reference's scenes are C++ functions, mort.cu:129-631).  Dump writes the journal of the
+ * builder calls this context received + the camera; loading it back rebuilds the same arrays slot for slot. */
+int mort_load_scene_text(mort_ctx* ctx, const char* path, const char* asset_dir);
+int mort_dump_scene_text(mort_ctx* ctx, const char* path);
 int mort_clear_scene(mort_ctx* ctx);                                        /* world::clear, world.cuh:92-96 */
 
 /* textures.cuh:20,42,79,164 + world.cuh:76-90 */

@@ -67,7 +67,7 @@ class Stats(C.Structure):
 # every symbol include/mort_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
     "mort_create", "mort_destroy", "mort_last_error", "mort_set_stream",
-    "mort_build_scene", "mort_build_sphere_field", "mort_load_scene", "mort_dump_scene", "mort_clear_scene",
+    "mort_build_scene", "mort_build_sphere_field", "mort_load_scene", "mort_dump_scene", "mort_load_scene_text", "mort_dump_scene_text", "mort_clear_scene",
     "mort_add_solid", "mort_add_checker", "mort_add_image", "mort_add_noise",
     "mort_add_lambertian", "mort_add_metal", "mort_add_dielectric", "mort_add_diffuse_light", "mort_add_isotropic",
     "mort_add_sphere", "mort_add_moving_sphere", "mort_add_quad", "mort_add_translate", "mort_add_rotate_y",
@@ -98,6 +98,7 @@ def load_library():
         "mort_create": [I, C.POINTER(P)], "mort_destroy": [P], "mort_set_stream": [P, P],
         "mort_build_scene": [P, I, C.c_char_p], "mort_build_sphere_field": [P, I, C.c_uint64, I],
         "mort_load_scene": [P, C.c_char_p, C.c_char_p], "mort_dump_scene": [P, C.c_char_p], "mort_clear_scene": [P],
+        "mort_load_scene_text": [P, C.c_char_p, C.c_char_p], "mort_dump_scene_text": [P, C.c_char_p],
         "mort_add_solid": [P, Fl, Fl, Fl, HP], "mort_add_checker": [P, Fl, H, H, HP], "mort_add_image": [P, P, I, I, HP],
         "mort_add_noise": [P, Fl, HP], "mort_add_lambertian": [P, H, HP], "mort_add_metal": [P, Fl, Fl, Fl, Fl, HP],
         "mort_add_dielectric": [P, Fl, HP], "mort_add_diffuse_light": [P, H, HP], "mort_add_isotropic": [P, H, HP],
@@ -188,6 +189,14 @@ class Renderer:
     def load_scene(self, path, asset_dir: str = ASSET_DIR):
         self._ck(self._L.mort_load_scene(self._h, str(path).encode(), asset_dir.encode()))
         return self
+
+    def load_scene_text(self, path, asset_dir: str = ASSET_DIR):
+        """Scene text file: one builder call per statement (grammar in mort_b200/csrc/scene_text.cpp)."""
+        self._ck(self._L.mort_load_scene_text(self._h, str(path).encode(), asset_dir.encode()))
+        return self
+
+    def dump_scene_text(self, path):
+        self._ck(self._L.mort_dump_scene_text(self._h, str(path).encode()))
 
     def dump_scene(self, path):
         self._ck(self._L.mort_dump_scene(self._h, str(path).encode()))

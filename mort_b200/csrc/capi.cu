@@ -143,6 +143,18 @@ int mort_load_scene(mort_ctx* ctx, const char* path, const char* asset_dir) {
     }
     return MORT_OK;
 }
+int mort_load_scene_text(mort_ctx* ctx, const char* path, const char* asset_dir) {
+    CTX_CHECK(ctx && path); invalidate(ctx);
+    std::string e;
+    ctx->rng.reseed(1);                                   // a scene file starts from the unseeded host stream, like a fresh process
+    if (!load_scene_text(ctx->scene, ctx->rng, path, asset_dir ? asset_dir : ".", &e)) return fail(ctx, MORT_ERR_SCENE, e);
+    return MORT_OK;
+}
+int mort_dump_scene_text(mort_ctx* ctx, const char* path) {
+    CTX_CHECK(ctx && path);
+    std::string e;
+    return dump_scene_text(ctx->scene, path, &e) ? MORT_OK : fail(ctx, MORT_ERR_IO, e);
+}
 int mort_dump_scene(mort_ctx* ctx, const char* path) { CTX_CHECK(ctx && path); return ctx->scene.dump(path) ? MORT_OK : fail(ctx, MORT_ERR_IO, std::string("cannot write ") + path); }
 int mort_clear_scene(mort_ctx* ctx) { CTX_CHECK(ctx); invalidate(ctx); ctx->scene.clear(); ctx->rng.reseed(1); return MORT_OK; }
 

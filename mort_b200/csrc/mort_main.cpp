@@ -15,13 +15,14 @@
 static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
                             "            [--mode mega|wave] [--stage N] [--bps blocks/SM] [--tpb threads] [--field G [--fieldcam 0|1]]\n"
                             "            [--assets DIR] [--out image.ppm] [--hdr image.pfm] [--device K] [--load scene.mscn] [--dump scene.mscn]\n"
+                            "            [--scene-file scene.txt] [--dump-text scene.txt]\n"
                             "            [--accumulate [--checkpoint FILE [--resume]]]\n"); return -1; }
 
 int main(int argc, char** argv) {
     if (argc < 2) return usage();                       // mort.cu:638-641
     int scene = atoi(argv[1]);
     int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = -1, mode = MORT_MODE_MEGAKERNEL, bps = 0, tpb = 0, field = 0, fieldcam = 0;
-    float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr, load, dump, ckpt;
+    float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr, load, dump, ckpt, text_in, text_out;
     bool accumulate = false, resume = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
@@ -32,6 +33,7 @@ int main(int argc, char** argv) {
         else if (a == "--assets") assets = nx(); else if (a == "--out") out = nx(); else if (a == "--hdr") hdr = nx(); else if (a == "--device") device = atoi(nx());
         else if (a == "--stage") stage = atoi(nx());
         else if (a == "--load") load = nx(); else if (a == "--dump") dump = nx();
+        else if (a == "--scene-file") text_in = nx(); else if (a == "--dump-text") text_out = nx();
         else if (a == "--accumulate") accumulate = true; else if (a == "--checkpoint") ckpt = nx(); else if (a == "--resume") resume = true;
         else if (a == "--bps") bps = atoi(nx()); else if (a == "--tpb") tpb = atoi(nx());
         else if (a == "--field") field = atoi(nx()); else if (a == "--fieldcam") fieldcam = atoi(nx());
@@ -41,11 +43,13 @@ int main(int argc, char** argv) {
     mort_ctx* ctx = nullptr;
     if (mort_create(device, &ctx) != MORT_OK) { fprintf(stderr, "mort: no usable CUDA device %d (this renderer has no CPU path)\n", device); return 2; }
     auto die = [&](const char* what) { fprintf(stderr, "mort: %s: %s\n", what, mort_last_error(ctx)); mort_destroy(ctx); return 3; };
-    if (!load.empty()) { if (mort_load_scene(ctx, load.c_str(), assets.c_str()) != MORT_OK) return die("load"); }
+    if (!text_in.empty()) { if (mort_load_scene_text(ctx, text_in.c_str(), assets.c_str()) != MORT_OK) return die("scene file"); }
+    else if (!load.empty()) { if (mort_load_scene(ctx, load.c_str(), assets.c_str()) != MORT_OK) return die("load"); }
     else if (field > 0) { if (mort_build_sphere_field(ctx, field, 69420, fieldcam) != MORT_OK) return die("sphere field"); }
     else if (mort_build_scene(ctx, scene, assets.c_str()) != MORT_OK) return die("scene");
     if (mort_override_camera(ctx, width, aspect, spp, depth) != MORT_OK) return die("camera");
     if (!dump.empty() && mort_dump_scene(ctx, dump.c_str()) != MORT_OK) return die("dump");
+    if (!text_out.empty() && mort_dump_scene_text(ctx, text_out.c_str()) != MORT_OK) return die("dump-text");
     if (mort_commit(ctx) != MORT_OK) return die("commit");
     mort_stats st; mort_get_stats(ctx, &st);
     std::vector<uint8_t> img((size_t)st.width * st.height * 4);

@@ -27,10 +27,11 @@ void HostRng::reseed(uint32_t seed) {
     for (int i = 34; i < 344; i++) r[i] = (int32_t)((uint32_t)r[i - 31] + (uint32_t)r[i - 3]);
     // keep the last 34 values as a ring; next output index is 344
     for (int i = 0; i < 34; i++) r_[i] = r[344 - 34 + i];
-    f_ = 0; b_ = 0;
+    f_ = 0; b_ = 0; draws_ = 0;
 }
 
 int HostRng::next() {
+    draws_++;
     // ring of 34: position p holds o[k-34+p]; o[k] = o[k-31] + o[k-3]
     int32_t v = (int32_t)((uint32_t)r_[(f_ + 3) % 34] + (uint32_t)r_[(f_ + 31) % 34]);
     r_[f_] = v;
@@ -123,20 +124,41 @@ uint32_t fnv1a32(const uint8_t* p, size_t n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// journal (scene text statements, scene_text.cpp)
+// ------------------------------------------------------------------------------------------------
+std::string handle_token(Handle h, char category) {
+    static const char* obj[] = {"?", "sph", "qd", "tr", "ry", "med", "list", "bvh"};
+    static const char* mat[] = {"?", "lam", "met", "die", "lgt", "iso"};
+    static const char* tex[] = {"?", "sol", "chk", "img", "noi"};
+    const char* const* tab = category == 'o' ? obj : (category == 'm' ? mat : tex);
+    const int n = category == 'o' ? 8 : (category == 'm' ? 6 : 5);
+    if (h.type < 1 || h.type >= n || h.idx < 0) return "none";
+    return std::string(tab[h.type]) + std::to_string(h.idx);
+}
+static std::string fs(float v) { char b[48]; snprintf(b, sizeof(b), "%.9g", (double)v); return b; }
+static std::string fs3(V3 v) { return fs(v.x) + " " + fs(v.y) + " " + fs(v.z); }
+static void jlog(Scene& s, const std::string& line) { if (s.journal_mute == 0) s.journal.push_back(line); }
+static const char* hid(bool skip) { return skip ? " hidden" : ""; }
+
+// ------------------------------------------------------------------------------------------------
 // textures / materials
 // ------------------------------------------------------------------------------------------------
 Handle Scene::add_solid(V3 c) {
+    jlog(*this, "solid " + fs3(c));
     mscn_solid s; put3(s.color, c); solids.push_back(s);
     return Handle{MORT_TEX_SOLID, (int)solids.size() - 1};
 }
 Handle Scene::add_checker(float scale, Handle even, Handle odd) {
+    jlog(*this, "checker " + fs(scale) + " " + handle_token(even, 't') + " " + handle_token(odd, 't'));
     mscn_checker c; c.inv_scale = (float)(1.0 / scale);                       // textures.cuh:43
     c.even_type = even.type; c.even_idx = even.idx; c.odd_type = odd.type; c.odd_idx = odd.idx;
     checkers.push_back(c);
     return Handle{MORT_TEX_CHECKER, (int)checkers.size() - 1};
 }
-Handle Scene::add_image(const uint8_t* rgb, int width, int height) {
+Handle Scene::add_image(const uint8_t* rgb, int width, int height, const char* source) {
     ImageRec im; im.width = width; im.height = height;
+    if (source) im.source = source;
+    jlog(*this, source ? std::string("image ") + source : "image @" + std::to_string(images.size()));
     if (rgb && width > 0 && height > 0) {
         im.rgb.assign(rgb, rgb + (size_t)width * height * 3);
         im.fnv1a = fnv1a32(im.rgb.data(), im.rgb.size());
@@ -149,6 +171,7 @@ Handle Scene::add_noise(float scale, HostRng& rng) {
     // reference's host compiler: z is drawn first.
     mscn_noise n; memset(&n, 0, sizeof(n));
     n.scale = scale;
+    jlog(*this, "noise " + fs(scale) + " at " + std::to_string(rng.draws()));
     for (int i = 0; i < MORT_PERLIN_POINTS; i++) {
         float z = rng.random_float(-1, 1), y = rng.random_float(-1, 1), x = rng.random_float(-1, 1);
         put3(n.ranvec[i], unit(V3(x, y, z)));
@@ -166,28 +189,34 @@ Handle Scene::add_noise(float scale, HostRng& rng) {
     return Handle{MORT_TEX_NOISE, (int)noises.size() - 1};
 }
 Handle Scene::add_noise_tables(const mscn_noise& n) {
+    journal_complete = false;                            // explicit tables have no text form
     noises.push_back(n);
     return Handle{MORT_TEX_NOISE, (int)noises.size() - 1};
 }
 
 Handle Scene::add_lambertian(Handle tex) {
+    jlog(*this, "lambertian " + handle_token(tex, 't'));
     lambertians.push_back(mscn_lambertian{tex.type, tex.idx});
     return Handle{MORT_MAT_LAMBERTIAN, (int)lambertians.size() - 1};
 }
 Handle Scene::add_metal(V3 albedo, float fuzz) {
+    jlog(*this, "metal " + fs3(albedo) + " " + fs(fuzz));
     mscn_metal m; put3(m.albedo, albedo); m.fuzz = fuzz; metals.push_back(m);
     return Handle{MORT_MAT_METAL, (int)metals.size() - 1};
 }
 Handle Scene::add_dielectric(float ior) {
+    jlog(*this, "dielectric " + fs(ior));
     mscn_dielectric d; d.ior = ior; d.inv_ior = (float)(1.0 / ior); d.albedo[0] = d.albedo[1] = d.albedo[2] = 1.0f;
     dielectrics.push_back(d);
     return Handle{MORT_MAT_DIELECTRIC, (int)dielectrics.size() - 1};
 }
 Handle Scene::add_diffuse_light(Handle tex) {
+    jlog(*this, "light " + handle_token(tex, 't'));
     lights.push_back(mscn_diffuse_light{tex.type, tex.idx});
     return Handle{MORT_MAT_DIFFUSE_LIGHT, (int)lights.size() - 1};
 }
 Handle Scene::add_isotropic(Handle tex) {
+    jlog(*this, "isotropic " + handle_token(tex, 't'));
     isotropics.push_back(mscn_isotropic{tex.type, tex.idx});
     return Handle{MORT_MAT_ISOTROPIC, (int)isotropics.size() - 1};
 }
@@ -196,6 +225,7 @@ Handle Scene::add_isotropic(Handle tex) {
 // hittables
 // ------------------------------------------------------------------------------------------------
 Handle Scene::add_sphere(V3 c, float r, Handle mat, bool skip) {
+    jlog(*this, "sphere " + fs3(c) + " " + fs(r) + " " + handle_token(mat, 'm') + hid(skip));
     mscn_sphere s; memset(&s, 0, sizeof(s));
     put3(s.center, c); s.radius = r; s.moves = 0; s.mat_type = mat.type; s.mat_idx = mat.idx; s.skip = skip ? 1 : 0;
     V3 rv(r, r, r);
@@ -204,6 +234,7 @@ Handle Scene::add_sphere(V3 c, float r, Handle mat, bool skip) {
     return Handle{MORT_OBJ_SPHERE, (int)spheres.size() - 1};
 }
 Handle Scene::add_moving_sphere(V3 c1, V3 c2, float r, Handle mat, bool skip) {
+    jlog(*this, "moving_sphere " + fs3(c1) + " " + fs3(c2) + " " + fs(r) + " " + handle_token(mat, 'm') + hid(skip));
     mscn_sphere s; memset(&s, 0, sizeof(s));
     put3(s.center, c1); s.radius = r; s.moves = 1; put3(s.center_vec, c2 - c1);
     s.mat_type = mat.type; s.mat_idx = mat.idx; s.skip = skip ? 1 : 0;
@@ -214,6 +245,7 @@ Handle Scene::add_moving_sphere(V3 c1, V3 c2, float r, Handle mat, bool skip) {
     return Handle{MORT_OBJ_SPHERE, (int)spheres.size() - 1};
 }
 Handle Scene::add_quad(V3 Q, V3 u, V3 v, Handle mat, bool skip) {
+    jlog(*this, "quad " + fs3(Q) + " " + fs3(u) + " " + fs3(v) + " " + handle_token(mat, 'm') + hid(skip));
     mscn_quad q; memset(&q, 0, sizeof(q));
     V3 n = cross(u, v);                                                       // objects.cuh:173-184
     V3 normal = unit(n);
@@ -229,11 +261,13 @@ Handle Scene::add_quad(V3 Q, V3 u, V3 v, Handle mat, bool skip) {
     return Handle{MORT_OBJ_QUAD, (int)quads.size() - 1};
 }
 Handle Scene::add_translate(Handle obj, V3 offset, bool skip) {
+    jlog(*this, "translate " + handle_token(obj, 'o') + " " + fs3(offset) + hid(skip));
     mscn_translate t; t.obj_type = obj.type; t.obj_idx = obj.idx; put3(t.offset, offset); t.skip = skip ? 1 : 0;
     translates.push_back(t);
     return Handle{MORT_OBJ_TRANSLATE, (int)translates.size() - 1};
 }
 Handle Scene::add_rotate_y(Handle obj, float theta_deg, bool skip) {
+    jlog(*this, "rotate_y " + handle_token(obj, 'o') + " " + fs(theta_deg) + hid(skip));
     mscn_rotate_y r; r.obj_type = obj.type; r.obj_idx = obj.idx; r.skip = skip ? 1 : 0;
     float radians = (float)(theta_deg * 3.1415926535897932385 / 180.0);      // objects.cuh:297-299
     r.sin_theta = sinf(radians); r.cos_theta = cosf(radians);
@@ -241,6 +275,7 @@ Handle Scene::add_rotate_y(Handle obj, float theta_deg, bool skip) {
     return Handle{MORT_OBJ_ROTATE_Y, (int)rotates.size() - 1};
 }
 Handle Scene::add_constant_medium(Handle boundary, float density, Handle mat, bool skip) {
+    jlog(*this, "medium " + handle_token(boundary, 'o') + " " + fs(density) + " " + handle_token(mat, 'm') + hid(skip));
     mscn_medium m; memset(&m, 0, sizeof(m));
     m.obj_type = boundary.type; m.obj_idx = boundary.idx;
     m.neg_inv_density = -(1.0 / density);                                     // objects.cuh:387 (double)
@@ -249,12 +284,14 @@ Handle Scene::add_constant_medium(Handle boundary, float density, Handle mat, bo
     return Handle{MORT_OBJ_CONSTANT_MEDIUM, (int)media.size() - 1};
 }
 Handle Scene::add_list(bool skip) {
+    jlog(*this, std::string("list") + hid(skip));
     ListRec l; l.skip = skip ? 1 : 0; lists.push_back(l);
     return Handle{MORT_OBJ_HITTABLE_LIST, (int)lists.size() - 1};
 }
 int Scene::list_add(Handle list, Handle obj) {
     if (list.type != MORT_OBJ_HITTABLE_LIST || list.idx < 0 || list.idx >= (int)lists.size()) return -1;
     lists[list.idx].items.push_back(obj);
+    jlog(*this, "add " + handle_token(list, 'o') + " " + handle_token(obj, 'o'));
     return 0;
 }
 
@@ -269,6 +306,7 @@ bool Scene::bbox_of(Handle h, float out[6]) const {
 // which array slot — i.e. which primitive id — every sphere ends up in.  The node arrays it produces are
 // kept for the scene dump; rendering uses the SAH wide BVH of bvh_build.cpp instead.
 Handle Scene::add_bvh(Handle list, bool skip) {
+    jlog(*this, "bvh " + handle_token(list, 'o') + hid(skip));
     BvhRec B; B.skip = skip ? 1 : 0; B.list_idx = list.idx;
     if (list.type != MORT_OBJ_HITTABLE_LIST || list.idx < 0 || list.idx >= (int)lists.size()) {
         error = "add_bvh: not a list"; bvhs.push_back(B); bvh_mode = true;
@@ -421,6 +459,7 @@ template <class T> static bool getv(FILE* f, std::vector<T>& v, int n) {
 
 bool Scene::load(const std::string& path, std::string* err) {
     clear();
+    journal_complete = false;                            // arrays come from the dump, not from builder calls
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) { if (err) *err = "cannot open " + path; return false; }
     mscn_header h;

@@ -48,9 +48,12 @@ public:
     int next();                                         // rand()
     float random_float();                               // rng.cuh:44-47
     float random_float(float lo, float hi);             // rng.cuh:49-53
+    uint64_t draws() const { return draws_; }           // rand() calls since the last reseed (scene text files pin noise tables to it)
+    void skip(uint64_t n) { while (n--) next(); }
 private:
     int32_t r_[34];
     int f_, b_;
+    uint64_t draws_ = 0;
 };
 
 struct Handle { int type; int idx; };
@@ -78,14 +81,14 @@ struct Camera {                                        // camera.cuh:12-45 (defa
 
 struct ListRec { int skip = 0; std::vector<Handle> items; float bbox[6] = {0, 0, 0, 0, 0, 0}; bool has_bbox = false; };
 struct BvhRec { int skip = 0; int list_idx = -1; std::vector<mscn_bvh_node> nodes; };
-struct ImageRec { int width = 0, height = 0; std::vector<uint8_t> rgb; uint32_t fnv1a = 0; };
+struct ImageRec { int width = 0, height = 0; std::vector<uint8_t> rgb; uint32_t fnv1a = 0; std::string source; /* file name inside the asset dir, if any */ };
 
 class Scene {
 public:
     // ---- textures (textures.cuh) ----
     Handle add_solid(V3 c);
     Handle add_checker(float scale, Handle even, Handle odd);
-    Handle add_image(const uint8_t* rgb, int width, int height);     // RGB8, rows top-down (stb order)
+    Handle add_image(const uint8_t* rgb, int width, int height, const char* source = nullptr);   // RGB8, rows top-down (stb order)
     Handle add_noise(float scale, HostRng& rng);                     // draws 3*256 + 3*255 host randoms
     Handle add_noise_tables(const mscn_noise& n);                    // explicit tables (scene files / tests)
     // ---- materials (materials.cuh) ----
@@ -134,6 +137,11 @@ public:
     bool bvh_mode = false;
     Camera cam;
     std::string error;
+    // Journal of the builder calls in the order they were made, one scene-text statement each (scene_text.cpp).
+    // Replaying it rebuilds the same arrays slot for slot; scenes loaded from a binary dump have none.
+    std::vector<std::string> journal;
+    bool journal_complete = true;
+    int journal_mute = 0;                                // > 0 inside helpers that log themselves
 };
 
 // The ten shipped scenes (mort.cu:129-631, dispatch mort.cu:649-689).  `asset_dir` holds earthmap.ppm.
@@ -142,6 +150,11 @@ bool build_reference_scene(Scene& s, int scene_id, const std::string& asset_dir)
 // camera_kind 0 = book view (13,2,3) vfov 20; 1 = aerial.
 bool build_sphere_field(Scene& s, int G, uint64_t seed, int camera_kind);
 bool load_ppm(const std::string& path, ImageRec& out);
+// scene_text.cpp — line-oriented scene description, one mort_add_* call per statement (grammar in the file header)
+bool load_scene_text(Scene& s, HostRng& rng, const std::string& path, const std::string& asset_dir, std::string* err);
+bool dump_scene_text(const Scene& s, const std::string& path, std::string* err);
+// canonical handle spelling: kind prefix + array slot ("sph12", "lam0", "sol3"); category 'o' object, 'm' material, 't' texture
+std::string handle_token(Handle h, char category);
 uint32_t fnv1a32(const uint8_t* p, size_t n);
 
 }  // namespace mort

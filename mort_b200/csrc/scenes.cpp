@@ -106,7 +106,7 @@ static void out_of_order_spheres(Scene& s, HostRng& g, int n) {   // mort.cu:255
 static bool earth(Scene& s, const std::string& assets) {           // mort.cu:292-313
     ImageRec im;
     if (!load_ppm(assets + "/earthmap.ppm", im)) { s.error = "cannot load " + assets + "/earthmap.ppm"; return false; }
-    Handle tex = s.add_image(im.rgb.data(), im.width, im.height);
+    Handle tex = s.add_image(im.rgb.data(), im.width, im.height, "earthmap.ppm");
     s.add_sphere(V3(0, 0, 0), 2, s.add_lambertian(tex));
     Camera& cam = s.cam;
     cam.aspect_ratio = (float)(16.0 / 9.0); cam.image_width = 1200; cam.samples_per_pixel = 100; cam.bounce_limit = 50;
@@ -228,7 +228,7 @@ static bool final_scene(Scene& s, HostRng& g, const std::string& assets, int ima
 
     ImageRec im;
     if (!load_ppm(assets + "/earthmap.ppm", im)) { s.error = "cannot load " + assets + "/earthmap.ppm"; return false; }
-    s.add_sphere(V3(400, 200, 400), 100, s.add_lambertian(s.add_image(im.rgb.data(), im.width, im.height)));
+    s.add_sphere(V3(400, 200, 400), 100, s.add_lambertian(s.add_image(im.rgb.data(), im.width, im.height, "earthmap.ppm")));
 
     s.add_sphere(V3(220, 280, 300), 80, s.add_lambertian(s.add_noise(0.1f, g)));
 

@@ -39,7 +39,7 @@ def hostsim():
     """Test-only host build of the product's per-ray code (tests/hostsim)."""
     out = os.path.join(ROOT, "tests", "hostsim", "hostsim.bin")
     src = [os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")] + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in
-                                                                      ("scene.cpp", "scenes.cpp", "flatten.cpp", "bvh_build.cpp")]
+                                                                      ("scene.cpp", "scenes.cpp", "scene_text.cpp", "flatten.cpp", "bvh_build.cpp")]
     deps = src + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in ("rt_core.cuh", "device_types.h", "flatten.hpp", "scene.hpp")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "mort_b200", "csrc"),

@@ -37,7 +37,10 @@ int main(int argc, char** argv) {
     if (argc < 4) { fprintf(stderr, "hostsim <scene 1-10 | file.mscn> <assets> trace in.mhit out.mhit [brute]\n        ... render W SPP DEPTH SEED out.mimg\n"); return 1; }
     Scene s; std::string assets = argv[2];
     std::string a1 = argv[1];
-    if (a1.rfind("field:", 0) == 0) {
+    if (a1.rfind("text:", 0) == 0) {
+        HostRng g(1); std::string err;
+        if (!load_scene_text(s, g, a1.substr(5), assets, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+    } else if (a1.rfind("field:", 0) == 0) {
         if (!build_sphere_field(s, atoi(a1.c_str() + 6), 69420, 0)) { fprintf(stderr, "field: %s\n", s.error.c_str()); return 2; }
     } else if (a1.size() > 5 && a1.substr(a1.size() - 5) == ".mscn") {
         std::string err; if (!s.load(a1, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
@@ -45,6 +48,7 @@ int main(int argc, char** argv) {
     } else if (!build_reference_scene(s, atoi(argv[1]), assets)) { fprintf(stderr, "scene: %s\n", s.error.c_str()); return 2; }
     std::string mode = argv[3];
     if (mode == "dump") { return s.dump(argv[4]) ? 0 : 3; }
+    if (mode == "dumptext") { std::string err; if (!dump_scene_text(s, argv[4], &err)) { fprintf(stderr, "%s\n", err.c_str()); return 3; } return 0; }
     if (mode == "rand") { HostRng g(1); int n = atoi(argv[4]); for (int i = 0; i < n; i++) fprintf(stderr, "%d\n", g.next()); return 0; }
     if (mode == "render") {
         int W = atoi(argv[4]), spp = atoi(argv[5]), depth = atoi(argv[6]);

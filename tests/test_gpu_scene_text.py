@@ -1,0 +1,82 @@
+"""GPU: scene text files through the C ABI (mort_load_scene_text / mort_dump_scene_text)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("sc,w,spp", [(6, 64, 16), (2, 64, 16), (7, 48, 16), (10, 64, 9)])
+def test_text_round_trip_renders_the_same_bits(sc, w, spp, tmp_path):
+    import torch
+    from mort_b200.api import Renderer
+    txt = str(tmp_path / f"s{sc}.txt")
+
+    def exact(r):
+        st = r.stats
+        t = torch.zeros((st["height"], st["width"], 4), dtype=torch.int64, device="cuda:0")
+        r.render_device(t.data_ptr(), exact_accum=1, seed=3)
+        torch.cuda.synchronize()
+        return t.cpu()
+
+    with Renderer(0) as r:
+        r.build_scene(sc)
+        r.dump_scene_text(txt)
+        r.override_camera(width=w, spp=spp).commit()
+        want, fp = exact(r), r.scene_fingerprint
+    with Renderer(0) as r:
+        r.load_scene_text(txt).override_camera(width=w, spp=spp).commit()
+        assert r.scene_fingerprint == fp
+        assert torch.equal(exact(r), want)
+
+
+def test_hand_written_scene_matches_the_oracle(tmp_path):
+    import oracle_binding as O
+    from mort_b200.api import Renderer
+    from test_scene_text import HAND_WRITTEN
+    txt, dump = tmp_path / "room.txt", str(tmp_path / "room.mscn")
+    txt.write_text(HAND_WRITTEN)
+    with Renderer(0) as r:
+        r.load_scene_text(str(txt)).commit()
+        r.dump_scene(dump)
+        osc = O.OracleScene(dump)
+        rng = np.random.default_rng(8)
+        rays = np.concatenate([np.tile([2, 2, -6], (3000, 1)), rng.normal(size=(3000, 3)) * [0.3, 0.3, 0.0] + [0, 0, 1], rng.random((3000, 1))], 1).astype(np.float32)
+        hits, probes = r.trace(rays)
+        ref_hits, ref_probes = osc.trace(rays)
+        b = ref_hits["hit"] == 1
+        assert b.mean() > 0.3
+        assert (hits["hit"] == ref_hits["hit"]).all() and (hits["t"].view(np.uint32)[b] == ref_hits["t"].view(np.uint32)[b]).all()
+        assert ((hits["leaf_type"] == ref_hits["leaf_type"]) & (hits["leaf_idx"] == ref_hits["leaf_idx"]))[b].all()
+        assert (probes["hit2"] == ref_probes["hit2"]).all()
+        fr = r.render(seed=21)
+        hdr, _, st = osc.render(seed=21)
+        ok = (fr.accum[..., 3] == 0) & (hdr[..., 3] == 0) & np.isfinite(fr.accum[..., :3]).all(-1) & np.isfinite(hdr[..., :3]).all(-1)
+        rel = np.abs(fr.accum[..., :3][ok] - hdr[..., :3][ok]).max(-1) / (np.abs(hdr[..., :3][ok]).max(-1) + 0.16)
+        assert ok.mean() > 0.95 and (rel > 1e-3).mean() <= 0.05
+        assert fr.stats["last_samples"] == st["samples"]
+
+
+def test_bad_scene_file_is_an_error_not_a_crash(tmp_path):
+    from mort_b200.api import MortError, Renderer
+    bad = tmp_path / "bad.txt"
+    bad.write_text("m = lambertian 1 1 1\nsphere 0 0 0 1 nosuch\n")
+    with Renderer(0) as r:
+        with pytest.raises(MortError, match=r"bad\.txt:2: unknown handle 'nosuch'"):
+            r.load_scene_text(str(bad))
+        with pytest.raises(MortError):
+            r.load_scene_text(str(tmp_path / "missing.txt"))
+        r.build_scene(6).override_camera(width=32, spp=4).commit()      # the context is still usable
+        assert r.render().rgba8.shape == (32, 32, 4)
+
+
+def test_cli_scene_file(tmp_path):
+    exe = os.path.join(ROOT, "mort_b200", "mort")
+    txt, a, b = str(tmp_path / "s3.txt"), str(tmp_path / "a.ppm"), str(tmp_path / "b.ppm")
+    subprocess.run([exe, "3", "--width", "64", "--spp", "16", "--dump-text", txt, "--out", a], check=True, capture_output=True, cwd=ROOT)
+    subprocess.run([exe, "0", "--scene-file", txt, "--width", "64", "--spp", "16", "--out", b], check=True, capture_output=True, cwd=ROOT)
+    assert open(a, "rb").read() == open(b, "rb").read()
