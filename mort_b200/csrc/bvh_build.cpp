@@ -11,8 +11,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <limits>
 #include <queue>
+#include <thread>
 
 #include "flatten.hpp"
 
@@ -37,11 +39,15 @@ constexpr int kBins = 16;
 constexpr float kTrav = 1.0f;
 inline float prim_cost(int type) { return type == MORT_OBJ_QUAD ? 1.3f : 1.0f; }
 
+// Subtrees over disjoint index ranges are independent, so the top `par_levels` levels hand their left child to another
+// thread and splice the two node arrays afterwards.  The tree (and therefore the 4-wide layout, which is rebuilt
+// breadth-first from the child links) does not depend on the thread count.
+constexpr int kParallelMinPrims = 1 << 14;
+
 struct Builder {
     const std::vector<BuildPrim>& prims;
     std::vector<int> idx;
     std::vector<Node2> nodes;
-    int max_depth = 0;
     int max_leaf = MORT_MAX_LEAF;
     explicit Builder(const std::vector<BuildPrim>& p) : prims(p) {
         if (const char* e = getenv("MORT_MAX_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) max_leaf = v; }   // experiments only
@@ -51,8 +57,13 @@ struct Builder {
     }
     float centroid(int i, int a) const { return 0.5f * (prims[i].lo[a] + prims[i].hi[a]); }
 
-    int build(int b, int e, int depth) {
-        max_depth = std::max(max_depth, depth);
+    static void splice(std::vector<Node2>& dst, const std::vector<Node2>& src) {
+        const int off = (int)dst.size();
+        for (Node2 n : src) { if (n.left >= 0) n.left += off; if (n.right >= 0) n.right += off; dst.push_back(n); }
+    }
+
+    // builds the subtree over idx[b, e) into `nodes` (appending); returns its root's index in `nodes`
+    int build(std::vector<Node2>& nodes, int b, int e, int par_levels) {
         int me = (int)nodes.size();
         nodes.emplace_back();
         Box box, cbox; box.reset(); cbox.reset();
@@ -115,8 +126,18 @@ struct Builder {
             mid = b + n / 2;      // coincident centroids: any balanced split
         }
         if (mid <= b || mid >= e) mid = b + n / 2;
-        int l = build(b, mid, depth + 1);
-        int r = build(mid, e, depth + 1);
+        if (par_levels > 0 && n >= kParallelMinPrims) {
+            std::vector<Node2> L, R;
+            auto left = std::async(std::launch::async, [&] { return build(L, b, mid, par_levels - 1); });
+            const int r = build(R, mid, e, par_levels - 1);
+            const int l = left.get();
+            const int off_l = (int)nodes.size(); splice(nodes, L);
+            const int off_r = (int)nodes.size(); splice(nodes, R);
+            nodes[me].left = off_l + l; nodes[me].right = off_r + r;
+            return me;
+        }
+        int l = build(nodes, b, mid, 0);
+        int r = build(nodes, mid, e, 0);
         nodes[me].left = l; nodes[me].right = r;
         return me;
     }
@@ -137,7 +158,11 @@ void build_bvh4(const std::vector<BuildPrim>& prims, std::vector<Bvh4Node>& out,
     if (prims.empty()) { Bvh4Node n; clear_node(n); out.push_back(n); stats.n_nodes = 1; return; }
 
     Builder B(prims);
-    int root = B.build(0, (int)prims.size(), 0);
+    // 2^levels concurrent subtrees at most; MORT_BUILD_THREADS=1 forces the serial build
+    unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 1;
+    if (const char* e = getenv("MORT_BUILD_THREADS")) { int v = atoi(e); if (v >= 1) hw = (unsigned)v; }
+    int levels = 0; while ((1u << levels) < hw && levels < 6) levels++;
+    int root = B.build(B.nodes, 0, (int)prims.size(), levels);
     order_out = B.idx;
     stats.n_bvh2_nodes = (int)B.nodes.size();
 

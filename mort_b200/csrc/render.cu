@@ -45,7 +45,17 @@ __device__ __forceinline__ float4 fx_resolve(long long r, long long g, long long
 // 64-bit add into shared memory as two native 32-bit atomics.  atomicAdd(unsigned long long*) on shared memory compiles to a
 // compare-and-swap spin loop (ATOMS.CAST.SPIN.64; 5 % of the stall samples on scene 1).  The low words wrap exactly
 // floor(sum / 2^32) times whatever the order, so carrying each wrap into the high word keeps the sum exact mod 2^64.
+#ifndef MORT_EXP_FLUSH
+#define MORT_EXP_FLUSH 0
+#endif
+#if MORT_EXP_FLUSH == 1
+__device__ __noinline__ void smem_add64(unsigned long long* p, unsigned long long v) {
+#else
 __device__ __forceinline__ void smem_add64(unsigned long long* p, unsigned long long v) {
+#endif
+#if MORT_EXP_FLUSH == 2
+    atomicAdd(p, v); return;
+#endif
     if (v == 0ull) return;
     unsigned* w = reinterpret_cast<unsigned*>(p);
     const unsigned lo = (unsigned)v;
@@ -92,19 +102,22 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
     // P.min_task_px pixels) so the last round of the frame is spread over every warp instead of leaving most of
     // them idle behind the few that drew a late full-size task.  The peek is racy on purpose: any chunk size is
     // valid, and the exact accumulation makes the frame independent of how pixels were grouped into tasks.
-    const int n_warps = (int)gridDim.x * (int)(blockDim.x >> 5);
     for (;;) {
-        int base = 0, chunk = PT;
+        int base = 0, npx = 0;
         if (lane == 0) {
+            int chunk = PT;
+#ifndef MORT_EXP_NOTAIL
             if (P.min_task_px < PT) {
+                const int n_warps = (int)gridDim.x * (int)(blockDim.x >> 5);
                 const int left = P.n_pixels - (int)*reinterpret_cast<volatile unsigned int*>(P.work_counter);
                 if (left < n_warps * PT) chunk = max(P.min_task_px, min(PT, left / n_warps));
             }
+#endif
             base = (int)atomicAdd(P.work_counter, (unsigned)chunk);
+            npx = min(chunk, P.n_pixels - base);
         }
-        base = __shfl_sync(full, base, 0); chunk = __shfl_sync(full, chunk, 0);
-        if (base >= P.n_pixels) break;
-        const int npx = min(chunk, P.n_pixels - base);
+        base = __shfl_sync(full, base, 0); npx = __shfl_sync(full, npx, 0);
+        if (npx <= 0) break;
         const int items = npx * n_subset;
         if (lane < npx * 4) part[warp][lane >> 2][lane & 3] = 0ull;
         if (lane + 32 < npx * 4) part[warp][(lane + 32) >> 2][(lane + 32) & 3] = 0ull;

@@ -64,6 +64,14 @@ int main(int argc, char** argv) {
     fprintf(stderr, "leaves %d nodes %d (bvh2 %d) depth %d sah %.2f pad %g build %.2f ms two_pass %d media %d lights %d kind %d\n", f.stats.n_leaves, f.stats.n_nodes,
             f.stats.n_bvh2_nodes, f.stats.max_depth, f.stats.sah_cost, f.stats.pad, f.stats.build_ms, f.two_pass, d.n_media, d.n_lights, d.light_kind);
     if (mode == "checkbvh") {
+        {   // FNV-1a over the node array and the primitive records: identifies the tree and the leaf order
+            uint64_t h = 1469598103934665603ull;
+            auto mix = [&h](const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+            if (!f.nodes.empty()) mix(f.nodes.data(), f.nodes.size() * sizeof(f.nodes[0]));
+            if (!f.spheres.empty()) mix(f.spheres.data(), f.spheres.size() * sizeof(f.spheres[0]));
+            if (!f.quads.empty()) mix(f.quads.data(), f.quads.size() * sizeof(f.quads[0]));
+            fprintf(stderr, "tree hash %016llx\n", (unsigned long long)h);
+        }
         // structural invariants of the 4-wide BVH: each primitive record referenced exactly once, leaves
         // type-homogeneous by construction of the child word, un-instanced primitives inside their leaf box,
         // children boxes inside the box their parent holds for them

@@ -72,3 +72,15 @@ def test_bvh_builder_invariants(hostsim, tmp_path):
     assert "bvh ok" in txt, txt
     txt = run(hostsim, "field:40", ASSETS, "checkbvh")
     assert "bvh ok" in txt, txt
+
+
+def test_parallel_bvh_build_gives_the_serial_tree(hostsim, tmp_path):
+    """subtrees are built on several threads above 16 k primitives; the tree must not depend on the thread count"""
+    import re
+    outs = []
+    for threads in ("1", "8"):
+        env = dict(os.environ, MORT_BUILD_THREADS=threads)
+        p = subprocess.run([hostsim, "field:100", ASSETS, "checkbvh"], check=True, capture_output=True, text=True, env=env)
+        assert "bvh ok" in p.stderr and "tree hash" in p.stderr
+        outs.append(re.sub(r"build [0-9.]+ ms", "build X ms", p.stderr))
+    assert outs[0] == outs[1]

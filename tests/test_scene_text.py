@@ -56,7 +56,6 @@ smoke = isotropic 0.9 0.9 0.9
 medium fog_shell 0.8 smoke
 lights = list hidden
 add lights top
-add lights ball
 camera width 64 aspect 1 spp 16 depth 8 vfov 40
 camera lookfrom 2 2 -6 lookat 2 2 0 vup 0 1 0 background 0 0 0 light lights
 """
@@ -72,7 +71,7 @@ def test_hand_written_scene_builds_expected_arrays(hostsim, tmp_path):
     assert len(sc["lambertians"]) == 3 and len(sc["solids"]) == 2 + 1 + 1     # white, red, lamp colour, smoke colour
     assert len(sc["diffuse_lights"]) == 1 and len(sc["dielectrics"]) == 1 and len(sc["isotropics"]) == 1 and len(sc["checkers"]) == 1
     assert len(sc["media"]) == 1 and len(sc["translates"]) == 1 and len(sc["rotates"]) == 1
-    assert [len(l["items"]) for l in sc["lists"]] == [6, 2]                    # the crate's sides, then the light list
+    assert [len(l["items"]) for l in sc["lists"]] == [6, 1]                    # the crate's sides, then the light list
     assert sc["spheres"]["skip"].tolist() == [0, 1]
     cam = sc["camera"]
     assert int(cam["image_width"]) == 64 and int(cam["image_height"]) == 64 and int(cam["sqrt_spp"]) == 4
