@@ -334,7 +334,7 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     // comparison in profiles/)
     int n_staged = o.stage_nodes;
     const int max_stage = (int)((ctx->prop.sharedMemPerBlockOptin > 2048 ? ctx->prop.sharedMemPerBlockOptin - 2048 : 0) / sizeof(Bvh4Node));
-    if (n_staged < 0) n_staged = 0;
+    if (n_staged < 0 || ctx->flat.linear) n_staged = 0;     // nothing to stage for a linear-scan scene
     n_staged = std::min(n_staged, std::min(max_stage, (int)ctx->flat.nodes.size()));
     p.n_staged = n_staged;
 
@@ -347,7 +347,7 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         // measured (profiles/r01_v4_variants.jsonl): 6 blocks/SM (80 regs) wins for the lockstep linear scan, 8 (64 regs) for the
         // larger BVH scenes; the spread between 6 and 8 is <= 3 % everywhere
         const int min_blocks = o.blocks_per_sm > 0 ? o.blocks_per_sm : (ctx->flat.linear ? 6 : 8);   // selects the register-capped variant
-        CU(mega_query(threads, n_staged, min_blocks, &occ, &regs));
+        CU(mega_query(threads, n_staged, min_blocks, ctx->flat.linear != 0, &occ, &regs));
         if (occ < 1) return fail(ctx, MORT_ERR_CUDA, "megakernel does not fit on an SM with this configuration");
         int bps = o.blocks_per_sm > 0 ? std::min(o.blocks_per_sm, occ) : occ;
         LaunchShape sh; sh.threads = threads; sh.blocks = bps * ctx->prop.multiProcessorCount; sh.smem_bytes = n_staged * (int)sizeof(Bvh4Node);

@@ -73,7 +73,8 @@ __device__ __forceinline__ int tile_to_global(int li, int band_px, int mod, int 
     return (bl * mod + rem) * band_px + (li - bl * band_px);
 }
 
-template <bool kStaged, int kMinBlocks>
+// kLinear: 1 = scenes scanned linearly (no tree code, no traversal stack in the kernel), 0 = tree scenes
+template <bool kStaged, int kMinBlocks, int kLinear>
 __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long part[4][MEGA_PMAX][4];                    // per warp: per task pixel: r, g, b, flags
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
             if (__ballot_sync(full, alive) == 0u) break;
             if (alive) {
                 f3 col; bool traced;
-                const int st = path_segment<kStaged>(P.sc, P.cam, staged, P.n_staged, path, g, col, traced);
+                const int st = path_segment<kStaged, kLinear>(P.sc, P.cam, staged, P.n_staged, path, g, col, traced);
                 n_seg += traced ? 1u : 0u;
                 if (st == SEG_DONE) {
                     unsigned long long af = 0ull;
@@ -193,13 +194,19 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
 }
 
 typedef void (*MegaFn)(const FrameParams);
-static MegaFn mega_variant(bool staged, int min_blocks) {
-    if (staged) return min_blocks >= 7 ? (MegaFn)mega_kernel<true, 8> : (min_blocks >= 5 ? (MegaFn)mega_kernel<true, 6> : (MegaFn)mega_kernel<true, 4>);
-    return min_blocks >= 7 ? (MegaFn)mega_kernel<false, 8> : (min_blocks >= 5 ? (MegaFn)mega_kernel<false, 6> : (MegaFn)mega_kernel<false, 4>);
+static MegaFn mega_variant(bool staged, int min_blocks, bool linear) {
+#if defined(MORT_EXP_NO_SPECIALISE)
+    if (staged) return min_blocks >= 7 ? (MegaFn)mega_kernel<true, 8, -1> : (min_blocks >= 5 ? (MegaFn)mega_kernel<true, 6, -1> : (MegaFn)mega_kernel<true, 4, -1>);
+    return min_blocks >= 7 ? (MegaFn)mega_kernel<false, 8, -1> : (min_blocks >= 5 ? (MegaFn)mega_kernel<false, 6, -1> : (MegaFn)mega_kernel<false, 4, -1>);
+#else
+    if (linear) return min_blocks >= 7 ? (MegaFn)mega_kernel<false, 8, 1> : (min_blocks >= 5 ? (MegaFn)mega_kernel<false, 6, 1> : (MegaFn)mega_kernel<false, 4, 1>);
+    if (staged) return min_blocks >= 7 ? (MegaFn)mega_kernel<true, 8, 0> : (min_blocks >= 5 ? (MegaFn)mega_kernel<true, 6, 0> : (MegaFn)mega_kernel<true, 4, 0>);
+    return min_blocks >= 7 ? (MegaFn)mega_kernel<false, 8, 0> : (min_blocks >= 5 ? (MegaFn)mega_kernel<false, 6, 0> : (MegaFn)mega_kernel<false, 4, 0>);
+#endif
 }
 
-cudaError_t mega_query(int threads, int n_staged, int min_blocks, int* max_blocks_per_sm, int* regs) {
-    MegaFn fn = mega_variant(n_staged > 0, min_blocks);
+cudaError_t mega_query(int threads, int n_staged, int min_blocks, bool linear, int* max_blocks_per_sm, int* regs) {
+    MegaFn fn = mega_variant(n_staged > 0, min_blocks, linear);
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, (const void*)fn);
     if (e != cudaSuccess) return e;
@@ -213,7 +220,7 @@ cudaError_t mega_query(int threads, int n_staged, int min_blocks, int* max_block
 }
 
 cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, int min_blocks, cudaStream_t st) {
-    MegaFn fn = mega_variant(p.n_staged > 0, min_blocks);
+    MegaFn fn = mega_variant(p.n_staged > 0, min_blocks, p.sc.linear != 0);
     if (p.n_staged > 0) {
         cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, shape.smem_bytes);
         if (e != cudaSuccess) return e;

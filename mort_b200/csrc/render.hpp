@@ -30,7 +30,7 @@ struct FrameParams {
 struct LaunchShape { int threads, blocks, smem_bytes; };
 
 // megakernel (render.cu)
-cudaError_t mega_query(int threads, int n_staged, int min_blocks, int* max_blocks_per_sm, int* regs);
+cudaError_t mega_query(int threads, int n_staged, int min_blocks, bool linear, int* max_blocks_per_sm, int* regs);
 cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, int min_blocks, cudaStream_t st);
 
 // wavefront (wavefront.cu)

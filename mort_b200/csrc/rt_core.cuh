@@ -123,6 +123,23 @@ MORT_HD R4 rng_block(Rng& g) {
     R4 r = {(float)(o.x >> 8) * s, (float)(o.y >> 8) * s, (float)(o.z >> 8) * s, (float)(o.w >> 8) * s};
     return r;
 }
+#if defined(MORT_EXP_PHILOX_INLINE)
+__device__ __forceinline__ R4 rng_block_inline(Rng& g) {
+    uint32_t c0 = g.pixel, c1 = g.sample, c2 = g.block, c3 = 0u, k0 = g.k0, k1 = g.k1;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    g.block++;
+    const float s = 1.0f / 16777216.0f;
+    R4 o = {(float)(c0 >> 8) * s, (float)(c1 >> 8) * s, (float)(c2 >> 8) * s, (float)(c3 >> 8) * s};
+    return o;
+}
+#endif
 MORT_HD int rnd_int_from(float u, int lo, int hi) {                                             // rng.cuh:30-42
     float r = 1.0f - u;                                  // curand_uniform is (0,1] = 1 - [0,1)
     r = r * (float)(hi - lo + 0.999999);                 // the reference multiplies in double; same index except exactly on a bin edge
@@ -228,6 +245,7 @@ MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3
 // closest hit over the 4-wide BVH
 // ---------------------------------------------------------------------------------------------------
 #define MORT_STACK 48
+struct alignas(8) StackEntry { uint32_t child; float t; };
 #define MORT_PRIM_NONE 0xFFFFFFFFu
 
 struct Hit { float t; uint32_t prim; float a, b; };      // prim = leaf-word type bits | record index ; (a,b) = quad alpha/beta
@@ -312,19 +330,21 @@ MORT_HD float safe_rcp_dir(float d) {
 
 // kStaged: the first n_staged nodes (breadth-first prefix = top levels) are read from a shared-memory copy,
 // the rest from global memory, through generic 128-bit loads; otherwise every node is a read-only LDG.128.
-template <bool kStaged>
+// kLinear: -1 = sc.linear decides at run time, 1 / 0 = the caller's kernel is specialised for linear-scan / tree scenes
+// (the other traversal is not even compiled into it).
+template <bool kStaged, int kLinear = -1>
 MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, const Ray& r, float tmin, float tmax, Hit& best,
                          int order_lo = 0, int order_hi = 0x7FFFFFFF) {
     best.t = tmax; best.prim = MORT_PRIM_NONE; best.a = best.b = 0.f;
     if (sc.empty) return false;
-    if (sc.linear) { closest_hit_linear(sc, r, tmin, best, order_lo, order_hi); return best.prim != MORT_PRIM_NONE; }
+    if (kLinear == 1 || (kLinear < 0 && sc.linear)) { closest_hit_linear(sc, r, tmin, best, order_lo, order_hi); return best.prim != MORT_PRIM_NONE; }
     const float idx = safe_rcp_dir(r.d.x), idy = safe_rcp_dir(r.d.y), idz = safe_rcp_dir(r.d.z);
     const float oix = r.o.x * idx, oiy = r.o.y * idy, oiz = r.o.z * idz;
     // per-ray octant: which of the node's lo/hi planes is the entry ("near") plane on each axis.  Picking the
     // rows by address replaces 12 of the 18 min/max per child (float offsets into Bvh4Node: lo rows at 0/4/8, hi at 12/16/20).
     const int nxo = idx < 0.f ? 12 : 0, nyo = idy < 0.f ? 16 : 4, nzo = idz < 0.f ? 20 : 8;
     const int fxo = 12 - nxo, fyo = 20 - nyo, fzo = 28 - nzo;
-    uint32_t stack_c[MORT_STACK]; float stack_t[MORT_STACK];
+    StackEntry stack[MORT_STACK];                        // one 64-bit local store / load per push / pop
     int sp = 0;
     uint32_t cur = 0;                                   // root; MORT_CHILD_EMPTY (leaf bit set) = traversal finished
     // "while-while" (Aila & Laine): an inner loop that only descends internal nodes, then one leaf step.  The
@@ -368,18 +388,18 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
             // push far-to-near, continue with the nearest; nothing hit -> pop
 #pragma unroll
             for (int k = 3; k >= 1; k--)
-                if (cw[k] != MORT_CHILD_EMPTY) { stack_c[sp] = cw[k]; stack_t[sp] = tn[k]; sp++; }   // depth * 3 <= MORT_STACK is checked at commit
+                if (cw[k] != MORT_CHILD_EMPTY) { StackEntry e; e.child = cw[k]; e.t = tn[k]; stack[sp] = e; sp++; }   // depth * 3 <= MORT_STACK is checked at commit
             uint32_t next = cw[0];
             if (next == MORT_CHILD_EMPTY) {
                 // entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit
-                while (sp > 0 && next == MORT_CHILD_EMPTY) { sp--; if (stack_t[sp] <= best.t) next = stack_c[sp]; }
+                while (sp > 0 && next == MORT_CHILD_EMPTY) { sp--; const StackEntry e = stack[sp]; if (e.t <= best.t) next = e.child; }
             }
             cur = next;
         }
         if (cur != MORT_CHILD_EMPTY) {
             leaf_intersect(sc, cur, r, tmin, best, order_lo, order_hi);
             uint32_t next = MORT_CHILD_EMPTY;
-            while (sp > 0 && next == MORT_CHILD_EMPTY) { sp--; if (stack_t[sp] <= best.t) next = stack_c[sp]; }
+            while (sp > 0 && next == MORT_CHILD_EMPTY) { sp--; const StackEntry e = stack[sp]; if (e.t <= best.t) next = e.child; }
             cur = next;
         }
     }
@@ -510,13 +530,13 @@ MORT_HD_NOINLINE MediaOut media_scan(const DeviceScene& sc, Ray r, float tmin, f
 #define MORT_PRIM_MEDIUM 0xFFFFFFFEu
 struct SegHit { Hit h; };                         // h.prim == MORT_PRIM_NONE: miss; == MORT_PRIM_MEDIUM: medium event, h.a = medium index bits
 
-template <bool kStaged>
+template <bool kStaged, int kLinear = -1>
 MORT_HD void segment_trace(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, const Ray& r, Rng& g, SegHit& out) {
     const float tmin = 0.001f;
     Hit h;
     // one traversal; only when media and top-level lists coexist (no shipped scene) is the visit-order window
     // narrower than everything and a second, out-of-line pass needed
-    bool any = closest_hit<kStaged>(sc, staged, n_staged, r, tmin, INFINITY, h, 0, sc.two_pass ? sc.post_media_order : 0x7FFFFFFF);
+    bool any = closest_hit<kStaged, kLinear>(sc, staged, n_staged, r, tmin, INFINITY, h, 0, sc.two_pass ? sc.post_media_order : 0x7FFFFFFF);
     float closest = any ? h.t : INFINITY;
     int med = -1; float tmed = 0.f;
     if (sc.n_media > 0) {                                   // cold for most scenes: kept out of line
@@ -859,7 +879,7 @@ MORT_HD bool path_exhausted(const CameraParams& cam, const Path& P, f3& color) {
 MORT_HD bool ray_is_nan(const Ray& r) { return isnan3(r.d) || isnan3(r.o); }
 
 // Megakernel form: one whole segment.  `traced` is set when a closest-hit query was issued (the unit of Mrays/s).
-template <bool kStaged>
+template <bool kStaged, int kLinear = -1>
 MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const Bvh4Node* staged, int n_staged, Path& P, Rng& g, f3& color, bool& traced) {
     traced = false;
     if (path_exhausted(cam, P, color)) return SEG_DONE;
@@ -867,9 +887,13 @@ MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const B
     traced = true;
     // the bounce's stage block is generated here, by every live lane together, whether or not the shading
     // below ends up drawing from it (one convergent Philox call instead of one per divergent material branch)
+#if defined(MORT_EXP_PHILOX_INLINE) && defined(__CUDA_ARCH__)
+    const R4 sb = rng_block_inline(g);
+#else
     const R4 sb = rng_block(g);
+#endif
     SegHit sh;
-    segment_trace<kStaged>(sc, staged, n_staged, P.ray, g, sh);
+    segment_trace<kStaged, kLinear>(sc, staged, n_staged, P.ray, g, sh);
     return segment_shade<CLASS_ANY>(sc, cam, sh, P, g, sb, color);
 }
 
