@@ -45,17 +45,9 @@ __device__ __forceinline__ float4 fx_resolve(long long r, long long g, long long
 // 64-bit add into shared memory as two native 32-bit atomics.  atomicAdd(unsigned long long*) on shared memory compiles to a
 // compare-and-swap spin loop (ATOMS.CAST.SPIN.64; 5 % of the stall samples on scene 1).  The low words wrap exactly
 // floor(sum / 2^32) times whatever the order, so carrying each wrap into the high word keeps the sum exact mod 2^64.
-#ifndef MORT_EXP_FLUSH
-#define MORT_EXP_FLUSH 0
-#endif
-#if MORT_EXP_FLUSH == 1
-__device__ __noinline__ void smem_add64(unsigned long long* p, unsigned long long v) {
-#else
+// (Out of line it costs 28 % of Cornell's throughput — the call forces the caller's live state through the ABI — so it is
+// force-inlined; profiles/r01_ab_bisect.jsonl, variant v1.)
 __device__ __forceinline__ void smem_add64(unsigned long long* p, unsigned long long v) {
-#endif
-#if MORT_EXP_FLUSH == 2
-    atomicAdd(p, v); return;
-#endif
     if (v == 0ull) return;
     unsigned* w = reinterpret_cast<unsigned*>(p);
     const unsigned lo = (unsigned)v;
@@ -73,7 +65,7 @@ __device__ __forceinline__ int tile_to_global(int li, int band_px, int mod, int 
     return (bl * mod + rem) * band_px + (li - bl * band_px);
 }
 
-// kLinear: 1 = scenes scanned linearly (no tree code, no traversal stack in the kernel), 0 = tree scenes
+// kLinear: -1 = the scene's linear flag decides at run time (the shipped configuration), 1 / 0 = specialised builds
 template <bool kStaged, int kMinBlocks, int kLinear>
 __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -107,13 +99,11 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
         int base = 0, npx = 0;
         if (lane == 0) {
             int chunk = PT;
-#ifndef MORT_EXP_NOTAIL
             if (P.min_task_px < PT) {
                 const int n_warps = (int)gridDim.x * (int)(blockDim.x >> 5);
                 const int left = P.n_pixels - (int)*reinterpret_cast<volatile unsigned int*>(P.work_counter);
                 if (left < n_warps * PT) chunk = max(P.min_task_px, min(PT, left / n_warps));
             }
-#endif
             base = (int)atomicAdd(P.work_counter, (unsigned)chunk);
             npx = min(chunk, P.n_pixels - base);
         }
@@ -194,15 +184,14 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
 }
 
 typedef void (*MegaFn)(const FrameParams);
+// Specialising the kernel for linear-scan vs tree scenes (kLinear = 1 / 0: the other traversal is not compiled in) was
+// measured and rejected: ptxas allocates the 80-register linear kernel worse without the tree code in it (268 / 428 B of
+// spill stores / loads instead of 212 / 372) and Cornell drops from 1559 to 1458 Msamples/s, scenes 1 and 8 do not move
+// (profiles/r01_ab_specialise.jsonl).  The template parameter stays for experiments; every variant decides at run time.
 static MegaFn mega_variant(bool staged, int min_blocks, bool linear) {
-#if defined(MORT_EXP_NO_SPECIALISE)
+    (void)linear;
     if (staged) return min_blocks >= 7 ? (MegaFn)mega_kernel<true, 8, -1> : (min_blocks >= 5 ? (MegaFn)mega_kernel<true, 6, -1> : (MegaFn)mega_kernel<true, 4, -1>);
     return min_blocks >= 7 ? (MegaFn)mega_kernel<false, 8, -1> : (min_blocks >= 5 ? (MegaFn)mega_kernel<false, 6, -1> : (MegaFn)mega_kernel<false, 4, -1>);
-#else
-    if (linear) return min_blocks >= 7 ? (MegaFn)mega_kernel<false, 8, 1> : (min_blocks >= 5 ? (MegaFn)mega_kernel<false, 6, 1> : (MegaFn)mega_kernel<false, 4, 1>);
-    if (staged) return min_blocks >= 7 ? (MegaFn)mega_kernel<true, 8, 0> : (min_blocks >= 5 ? (MegaFn)mega_kernel<true, 6, 0> : (MegaFn)mega_kernel<true, 4, 0>);
-    return min_blocks >= 7 ? (MegaFn)mega_kernel<false, 8, 0> : (min_blocks >= 5 ? (MegaFn)mega_kernel<false, 6, 0> : (MegaFn)mega_kernel<false, 4, 0>);
-#endif
 }
 
 cudaError_t mega_query(int threads, int n_staged, int min_blocks, bool linear, int* max_blocks_per_sm, int* regs) {

@@ -89,12 +89,18 @@ struct Rng { uint32_t k0, k1, pixel, sample, block; };
 struct U4 { uint32_t x, y, z, w; };
 struct R4 { float x, y, z, w; };
 
+#if !defined(MORT_PHILOX_UNROLL)
+#define MORT_PHILOX_UNROLL 10
+#endif
+constexpr int kPhiloxUnroll = MORT_PHILOX_UNROLL;
 // One Philox block.  Deliberately NOT inlined: a path draws at many sites, and inlined copies of the 10-round
 // block (28 copies, ~2.8 k SASS instructions in the first version) pushed the megakernel out of the
-// instruction cache (profiles/r01_mega_cornell_v1.md: 72 % of stall samples were `no_inst`).
+// instruction cache (profiles/r01_mega_cornell_v1.md: 72 % of stall samples were `no_inst`).  The single
+// out-of-line copy is fully unrolled: +40 SASS instructions, no loop counter / branch per round (Cornell +2 %,
+// scene 1 +2 %, 1 M field +2 %, scene 8 -3 % against the rolled loop, profiles/r01_ab_variants2.jsonl).
 MORT_HD_NOINLINE U4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) {
     uint32_t c3 = 0u;
-#pragma unroll 1
+#pragma unroll (kPhiloxUnroll)
     for (int r = 0; r < 10; r++) {
 #if defined(__CUDA_ARCH__)
         uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -123,23 +129,6 @@ MORT_HD R4 rng_block(Rng& g) {
     R4 r = {(float)(o.x >> 8) * s, (float)(o.y >> 8) * s, (float)(o.z >> 8) * s, (float)(o.w >> 8) * s};
     return r;
 }
-#if defined(MORT_EXP_PHILOX_INLINE)
-__device__ __forceinline__ R4 rng_block_inline(Rng& g) {
-    uint32_t c0 = g.pixel, c1 = g.sample, c2 = g.block, c3 = 0u, k0 = g.k0, k1 = g.k1;
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
-        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    g.block++;
-    const float s = 1.0f / 16777216.0f;
-    R4 o = {(float)(c0 >> 8) * s, (float)(c1 >> 8) * s, (float)(c2 >> 8) * s, (float)(c3 >> 8) * s};
-    return o;
-}
-#endif
 MORT_HD int rnd_int_from(float u, int lo, int hi) {                                             // rng.cuh:30-42
     float r = 1.0f - u;                                  // curand_uniform is (0,1] = 1 - [0,1)
     r = r * (float)(hi - lo + 0.999999);                 // the reference multiplies in double; same index except exactly on a bin edge
@@ -226,6 +215,8 @@ MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3
     const float num = xsub(nD.w, xdot(n, o));
     // a ray leaving a surface has its origin on that surface's plane: num ~ 0, and the IEEE division would take its
     // slow path.  |num| < tmin/2 * |denom| implies |t| < tmin, i.e. the reference rejects it (t < t_min) as well.
+    // (Deciding every out-of-range plane with an approximate quotient first was measured and rejected: Cornell
+    // 1584 -> 1499 Msamples/s, profiles/r01_ab_variants3.jsonl — the lanes that pass pay for both divisions.)
     if (tmin > 0.f && fabsf(num) < 0.5f * tmin * fabsf(denom)) return false;
     float t = xdiv(num, denom);
     if (t < tmin || t > tmax) return false;
@@ -381,9 +372,12 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
                 tn[k] = h ? tnear : INFINITY;
                 cw[k] = h ? cw[k] : MORT_CHILD_EMPTY;
             }
-            // sort the 4 (tn, child) pairs ascending: 5-comparator network (misses carry EMPTY + inf and sink)
 #define MORT_CSWAP(i, j) { bool sw = tn[j] < tn[i]; float ta = sw ? tn[j] : tn[i], tb = sw ? tn[i] : tn[j]; uint32_t ca = sw ? cw[j] : cw[i], cb = sw ? cw[i] : cw[j]; tn[i] = ta; tn[j] = tb; cw[i] = ca; cw[j] = cb; }
-            MORT_CSWAP(0, 1) MORT_CSWAP(2, 3) MORT_CSWAP(0, 2) MORT_CSWAP(1, 3) MORT_CSWAP(1, 2)
+            // Only the nearest hit is brought to slot 0 (3 comparators); the other hits are pushed in slot order and
+            // culled by their entry distance when popped.  Measured against the full 5-comparator sort
+            // (profiles/r01_ab_variants2.jsonl): scene 1 +3.6 %, 1 M-sphere field +4.5 %, scene 8 +1 % — most node
+            // visits hit at most two children, where the two orders coincide.
+            MORT_CSWAP(0, 1) MORT_CSWAP(2, 3) MORT_CSWAP(0, 2)
 #undef MORT_CSWAP
             // push far-to-near, continue with the nearest; nothing hit -> pop
 #pragma unroll
@@ -887,11 +881,7 @@ MORT_HD int path_segment(const DeviceScene& sc, const CameraParams& cam, const B
     traced = true;
     // the bounce's stage block is generated here, by every live lane together, whether or not the shading
     // below ends up drawing from it (one convergent Philox call instead of one per divergent material branch)
-#if defined(MORT_EXP_PHILOX_INLINE) && defined(__CUDA_ARCH__)
-    const R4 sb = rng_block_inline(g);
-#else
     const R4 sb = rng_block(g);
-#endif
     SegHit sh;
     segment_trace<kStaged, kLinear>(sc, staged, n_staged, P.ray, g, sh);
     return segment_shade<CLASS_ANY>(sc, cam, sh, P, g, sb, color);
