@@ -90,14 +90,15 @@ struct U4 { uint32_t x, y, z, w; };
 struct R4 { float x, y, z, w; };
 
 #if !defined(MORT_PHILOX_UNROLL)
-#define MORT_PHILOX_UNROLL 10
+#define MORT_PHILOX_UNROLL 2
 #endif
 constexpr int kPhiloxUnroll = MORT_PHILOX_UNROLL;
 // One Philox block.  Deliberately NOT inlined: a path draws at many sites, and inlined copies of the 10-round
 // block (28 copies, ~2.8 k SASS instructions in the first version) pushed the megakernel out of the
 // instruction cache (profiles/r01_mega_cornell_v1.md: 72 % of stall samples were `no_inst`).  The single
-// out-of-line copy is fully unrolled: +40 SASS instructions, no loop counter / branch per round (Cornell +2 %,
-// scene 1 +2 %, 1 M field +2 %, scene 8 -3 % against the rolled loop, profiles/r01_ab_variants2.jsonl).
+// out-of-line copy is unrolled by 2.  Same-box A/B of the unroll factor (profiles/r01_ab_final.jsonl, Msamples/s on
+// Cornell / scene 1 / scene 8 / 1 M field): factor 10: 1585 / 2623 / 354 / 885, factor 2: 1578 / 2588 / 371 / 905 —
+// the fully unrolled block costs the scenes whose hot code already overflows the instruction cache.
 MORT_HD_NOINLINE U4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) {
     uint32_t c3 = 0u;
 #pragma unroll (kPhiloxUnroll)

@@ -48,10 +48,11 @@ floor = lambertian chk
 quad 0 0 0  4 0 0  0 0 4  floor
 quad 0 0 0  0 4 0  0 0 4  red
 top = quad 1 3.99 1  2 0 0  0 0 2  lamp
-ball = sphere 2 1 2 0.7 glass
+steel = metal 0.8 0.85 0.88 0.05
+ball = sphere 3 0.7 2.5 0.7 steel
 box 0.2 0 0.2  1.0 0.8 1.0  white
 crate = rotated_box 1 1 1  2.5 0 0.5  30 white
-fog_shell = sphere 2 1 2 0.5 glass hidden
+fog_shell = sphere 1.2 1.2 2.5 0.6 glass hidden
 smoke = isotropic 0.9 0.9 0.9
 medium fog_shell 0.8 smoke
 lights = list hidden
@@ -69,7 +70,7 @@ def test_hand_written_scene_builds_expected_arrays(hostsim, tmp_path):
     sc = F.read_scene(str(out))
     assert len(sc["spheres"]) == 2 and len(sc["quads"]) == 3 + 6 + 6
     assert len(sc["lambertians"]) == 3 and len(sc["solids"]) == 2 + 1 + 1     # white, red, lamp colour, smoke colour
-    assert len(sc["diffuse_lights"]) == 1 and len(sc["dielectrics"]) == 1 and len(sc["isotropics"]) == 1 and len(sc["checkers"]) == 1
+    assert len(sc["diffuse_lights"]) == 1 and len(sc["dielectrics"]) == 1 and len(sc["metals"]) == 1 and len(sc["isotropics"]) == 1 and len(sc["checkers"]) == 1
     assert len(sc["media"]) == 1 and len(sc["translates"]) == 1 and len(sc["rotates"]) == 1
     assert [len(l["items"]) for l in sc["lists"]] == [6, 1]                    # the crate's sides, then the light list
     assert sc["spheres"]["skip"].tolist() == [0, 1]
