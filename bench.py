@@ -172,8 +172,13 @@ def run_mort(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — mort_b200 has no CPU path")
     torch.cuda.set_device(local)
+    json_fd = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL logs its banner to stdout)
+        # stdout carries exactly one JSON line: NCCL prints its version banner to fd 1 when the communicator is created (with
+        # NCCL_DEBUG set on the box, NCCL_DEBUG_FILE notwithstanding), so fd 1 points at stderr until the result is written
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -324,7 +329,11 @@ def run_mort(a):
                 res["cpu_baseline"] = cpu_baseline(a)
             except Exception as ex:  # the baseline is a report, never a gate
                 res["cpu_baseline"] = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
-        print(json.dumps(res))
+        if json_fd is not None:
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(res) + "\n").encode())
+        else:
+            print(json.dumps(res))
     r.close()
     if world > 1:
         dist.destroy_process_group()
