@@ -57,24 +57,57 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    """SM clock + throttle reasons DURING the timed region.  NVML in-process (one nvmlInit before the timed region, then a
+    few microseconds per query); spawning nvidia-smi every 200 ms instead re-initialises the driver's management interface
+    each time and was measured to slow the running kernel by ~2 % (profiles/r01_clock_sampler_ab.jsonl).  Falls back to
+    nvidia-smi when the NVML binding is missing.  MORT_BENCH_CLOCKS=smi|nvml|off overrides (experiments)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index=0):
         self.rows, self.stop, self.gpu = [], threading.Event(), gpu_index
+        self.how = os.environ.get("MORT_BENCH_CLOCKS", "nvml")
+        self.nv = self.handle = None
+        if self.how == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(ids[gpu_index] if ids and gpu_index < len(ids) else gpu_index)
+                self.nv = pynvml
+            except Exception:
+                self.how = "smi"
         self.t = threading.Thread(target=self._run, daemon=True)
 
+    def _sample_nvml(self):
+        nv, h = self.nv, self.handle
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        row = [str(self.gpu), str(sm), str(mx), "", hex(mask)] + ["Active" if mask & b else "Not Active" for b in self.BITS.values()]
+        self.rows.append(row)
+
     def _run(self):
+        if self.how == "off":
+            return
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                if self.how == "nvml":
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05 if self.how == "nvml" else 0.2)
 
     def __enter__(self):
         self.t.start()
@@ -94,7 +127,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": self.how}
 
 
 def run_reference(a):

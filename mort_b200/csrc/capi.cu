@@ -18,7 +18,6 @@
 
 using namespace mort;
 
-#define MORT_DEFAULT_BLOCKS_PER_SM 4      // megakernel occupancy target (register-capped variant); see profiles/
 
 namespace {
 
