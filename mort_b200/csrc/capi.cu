@@ -60,6 +60,7 @@ struct mort_ctx {
     mort_stats stats;
     double upload_ms = 0;
     uint64_t geometry_hash = 0;
+    int stack_fix = 1;
     unsigned long long* d_prog = nullptr; size_t prog_pixels = 0;   // progressive exact image (mort_render_progressive)
     uint64_t prog_fingerprint = 0; uint32_t prog_frames = 0, prog_seed = 0;
 };
@@ -78,6 +79,18 @@ static Handle H(mort_handle h) { return Handle{h.type, h.idx}; }
 static void put(mort_handle* out, Handle h) { if (out) { out->type = h.type; out->idx = h.idx; } }
 static V3 v3(const float* p) { return V3(p[0], p[1], p[2]); }
 static void invalidate(mort_ctx* ctx) { ctx->committed = false; }
+
+// The reference sets cudaLimitStackSize itself (8192 B, mort.cu:703).  The megakernel's frame is < 1 KB, so the default
+// limit would do — but re-sizing the context's local-memory pool is measurably worth it: inside a process whose CUDA context
+// was created by a host framework (torch), the Cornell frame takes 242.7 ms with the pool as found and 234.5 ms after the
+// limit was changed to 2048 B (profiles/r01_process_probe.jsonl; bench.py 1516 -> 1566 Msamples/s, profiles/r01_stack_limit_ab.jsonl); the spilled registers
+// of 888 resident blocks live there.
+// A larger limit set by the host is never lowered.
+static void raise_stack_limit() {
+    size_t cur = 0;
+    if (cudaDeviceGetLimit(&cur, cudaLimitStackSize) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cur < 2048 && cudaDeviceSetLimit(cudaLimitStackSize, 2048) != cudaSuccess) cudaGetLastError();
+}
 
 extern "C" {
 
@@ -98,6 +111,9 @@ int mort_create(int cuda_device, mort_ctx** out) {
         delete ctx; return MORT_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    const char* fix = getenv("MORT_STACK_FIX");            // experiments: create (default) | render | off
+    ctx->stack_fix = fix ? (strcmp(fix, "off") == 0 ? 0 : (strcmp(fix, "render") == 0 ? 2 : 1)) : 1;
+    if (ctx->stack_fix == 1) raise_stack_limit();
     *out = ctx;
     return MORT_OK;
 }
@@ -337,6 +353,7 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     n_staged = std::min(n_staged, std::min(max_stage, (int)ctx->flat.nodes.size()));
     p.n_staged = n_staged;
 
+    if (ctx->stack_fix == 2) { raise_stack_limit(); ctx->stack_fix = 0; }
     CU(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
     uint64_t launches = 0;
