@@ -568,8 +568,13 @@ MORT_HD void segment_record(const DeviceScene& sc, const Ray& r, const SegHit& s
 // ---------------------------------------------------------------------------------------------------
 // textures (textures.cuh)
 // ---------------------------------------------------------------------------------------------------
+// Both loops stay rolled: unrolled, the 7 octaves x 8 lattice corners were 1282 SASS instructions (20 KB) streaming through
+// the instruction cache on every marble hit of scene 8 — a kernel that is instruction-fetch bound there
+// (profiles/r01_scene8_fetch_bound.md).  The corner weights are selects (di ? uu : 1 - uu), bit-identical to the reference's
+// di*uu + (1-di)*(1-uu) for finite uu.
 MORT_HD_NOINLINE float perlin_turb(const NoiseTables* N, f3 p) {                      // textures.cuh:174-196, 232-265
     double accum = 0.0, weight = 1.0;
+#pragma unroll 1
     for (int oct = 0; oct < 7; oct++) {
         float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
         float u = p.x - fx, v = p.y - fy, w = p.z - fz;
@@ -578,12 +583,14 @@ MORT_HD_NOINLINE float perlin_turb(const NoiseTables* N, f3 p) {                
         double du = u, dv = v, dw = w;
         double uu = du * du * (3 - 2 * du), vv = dv * dv * (3 - 2 * dv), ww = dw * dw * (3 - 2 * dw);
         double acc = 0.0;
-        for (int di = 0; di < 2; di++) for (int dj = 0; dj < 2; dj++) for (int dk = 0; dk < 2; dk++) {
+#pragma unroll 1
+        for (int c = 0; c < 8; c++) {
+            const int di = c >> 2, dj = (c >> 1) & 1, dk = c & 1;
             int idx = (int)(ldu8(N->perm_x + ((i + di) & 255)) ^ ldu8(N->perm_y + ((j + dj) & 255)) ^ ldu8(N->perm_z + ((k + dk) & 255)));
-            F4 c = ld4(&N->ranvec[idx][0]);
+            F4 cv = ld4(&N->ranvec[idx][0]);
             f3 wv = mk3((float)(du - di), (float)(dv - dj), (float)(dw - dk));
-            float dt = xfma(c.z, wv.z, xfma(c.x, wv.x, xmul(c.y, wv.y)));
-            acc += (di * uu + (1 - di) * (1 - uu)) * (dj * vv + (1 - dj) * (1 - vv)) * (dk * ww + (1 - dk) * (1 - ww)) * (double)dt;
+            float dt = xfma(cv.z, wv.z, xfma(cv.x, wv.x, xmul(cv.y, wv.y)));
+            acc += (di ? uu : 1 - uu) * (dj ? vv : 1 - vv) * (dk ? ww : 1 - ww) * (double)dt;
         }
         accum += weight * (double)(float)acc;
         weight *= 0.5;
