@@ -144,14 +144,22 @@ def run_reference(a):
            "--frames", str(a.steps), "--warmup", str(a.warmup)]
     if a.aspect > 0:
         cmd += ["--aspect", str(a.aspect)]
-    with ClockSampler(0) as cs:
-        out = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(exe), timeout=1500)
-    line = None
-    for l in out.stdout.splitlines():
-        if '"timing":"renderKernel"' in l:
-            line = json.loads(l)
+    # The unmodified reference kernel dies now and then with "invalid program counter" (2 of ~12 launches of this very command
+    # on B200; its device-side new/delete, recursion and unchecked indices are SURVEY.md App. A material): a crashed attempt is
+    # repeated, up to 3 times, and the number of attempts is reported.
+    line, attempts, failures = None, 0, []
+    while line is None and attempts < 3:
+        attempts += 1
+        with ClockSampler(0) as cs:
+            out = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(exe), timeout=1500)
+        for l in out.stdout.splitlines():
+            if '"timing":"renderKernel"' in l:
+                line = json.loads(l)
+        if line is None:
+            failures.append(f"rc={out.returncode}: {out.stderr.strip()[-160:]}")
+            print(f"bench.py: reference attempt {attempts} failed: {failures[-1]}", file=sys.stderr)
     if line is None:
-        print(json.dumps({"impl": "reference", "unavailable": f"reference harness failed rc={out.returncode}: {out.stderr[-200:]}"}))
+        print(json.dumps({"impl": "reference", "unavailable": f"reference harness failed {attempts} times: {failures[-1]}"}))
         return 0
     total_ms = line["ms_total_timed"]
     samples = line["samples_per_frame"] * line["frames_timed"]
@@ -163,7 +171,7 @@ def run_reference(a):
                             "sample": f"the reference's own CUDA renderKernel on 1 B200 (it has no CPU renderer): {line['frames_timed']} frames of "
                                       f"{a.width}x{a.width} at {REF_SPP} spp"},
            "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
+           "gpu_launches": 0, "attempts": attempts}
     print(json.dumps(res))
     return 0
 

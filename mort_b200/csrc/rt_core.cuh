@@ -568,10 +568,11 @@ MORT_HD void segment_record(const DeviceScene& sc, const Ray& r, const SegHit& s
 // ---------------------------------------------------------------------------------------------------
 // textures (textures.cuh)
 // ---------------------------------------------------------------------------------------------------
-// Both loops stay rolled: unrolled, the 7 octaves x 8 lattice corners were 1282 SASS instructions (20 KB) streaming through
-// the instruction cache on every marble hit of scene 8 — a kernel that is instruction-fetch bound there
-// (profiles/r01_scene8_fetch_bound.md).  The corner weights are selects (di ? uu : 1 - uu), bit-identical to the reference's
-// di*uu + (1-di)*(1-uu) for finite uu.
+// The octave loop stays rolled: fully unrolled, the 7 octaves x 8 lattice corners were 1282 SASS instructions (20 KB)
+// streaming through the instruction cache on every marble hit of scene 8 — a kernel that is instruction-fetch bound there
+// (profiles/r01_scene8_fetch_bound.md; scene 8 397 -> 437 Msamples/s with everything rolled).  The 8 corners are unrolled
+// again (their index bits fold into the code): with them rolled too the noise-only scene 4 lost a third of its speed.
+// The corner weights are selects (di ? uu : 1 - uu), bit-identical to the reference's di*uu + (1-di)*(1-uu) for finite uu.
 MORT_HD_NOINLINE float perlin_turb(const NoiseTables* N, f3 p) {                      // textures.cuh:174-196, 232-265
     double accum = 0.0, weight = 1.0;
 #pragma unroll 1
@@ -583,7 +584,7 @@ MORT_HD_NOINLINE float perlin_turb(const NoiseTables* N, f3 p) {                
         double du = u, dv = v, dw = w;
         double uu = du * du * (3 - 2 * du), vv = dv * dv * (3 - 2 * dv), ww = dw * dw * (3 - 2 * dw);
         double acc = 0.0;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 8; c++) {
             const int di = c >> 2, dj = (c >> 1) & 1, dk = c & 1;
             int idx = (int)(ldu8(N->perm_x + ((i + di) & 255)) ^ ldu8(N->perm_y + ((j + dj) & 255)) ^ ldu8(N->perm_z + ((k + dk) & 255)));
