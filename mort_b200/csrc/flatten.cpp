@@ -165,27 +165,45 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
     // ---- visible leaves in world::hit order (world.cuh:110-168) ----
     std::vector<Chain> chains;
     int top_type = 0, top_idx = 0;
+    // gate = intersection of the reference-BVH node boxes above a leaf (everything for leaves outside a bvh): the product
+    // ignores those boxes, which is only right while they contain what hangs below them (checked after the world boxes
+    // are known)
+    struct Gate { float lo[3], hi[3]; };
+    Gate open_gate; for (int a = 0; a < 3; a++) { open_gate.lo[a] = -INFINITY; open_gate.hi[a] = INFINITY; }
+    Gate cur_gate = open_gate;
+    std::vector<Gate> gates;
     auto emit = [&](int type, int idx, const Chain& c) {
         LeafRef L; L.type = type; L.idx = idx; L.inst = F.instance_of(c); L.order = (int)out.leaves.size(); L.top_type = top_type; L.top_idx = top_idx;
-        out.leaves.push_back(L); chains.push_back(c);
+        out.leaves.push_back(L); chains.push_back(c); gates.push_back(cur_gate);
     };
     Chain none;
     for (size_t b = 0; b < s.bvhs.size(); b++) {
         if (s.bvhs[b].skip || s.bvhs[b].nodes.empty()) continue;
         top_type = MORT_OBJ_BVH; top_idx = (int)b;
-        // depth-first, left before right: the order bvh::hit (objects.cuh:664-723) tests the leaves in
-        std::vector<int> stack; stack.push_back(0);
+        // depth-first, left before right: the order bvh::hit (objects.cuh:664-723) tests the leaves in.
+        // A node whose box has no thickness along an axis (an axis-aligned quad alone in a leaf: the reference does not pad
+        // boxes) can never be entered — aabb::hit rejects t_max <= t_min (aabb.cuh:38-59) — so everything below it is
+        // invisible in the reference and is left out here.  Every other box contains its objects, and culling by it
+        // changes nothing (tests/test_host_scene.py checks the shipped BVH scenes against the reference's hits).
+        struct Visit { int node; bool dead; Gate gate; };
+        std::vector<Visit> stack; stack.push_back(Visit{0, false, open_gate});
         while (!stack.empty()) {
-            int n = stack.back(); stack.pop_back();
+            const int n = stack.back().node; bool dead = stack.back().dead; Gate g = stack.back().gate; stack.pop_back();
             if (n < 0 || n >= (int)s.bvhs[b].nodes.size()) return fail("bvh node index out of range");
             const mscn_bvh_node& nd = s.bvhs[b].nodes[n];
-            if (nd.is_internal) { stack.push_back(nd.right_idx); stack.push_back(nd.left_idx); }
-            else {
+            for (int a = 0; a < 3; a++) {
+                dead = dead || !(nd.bbox[2 * a + 1] > nd.bbox[2 * a]);
+                g.lo[a] = fmaxf(g.lo[a], nd.bbox[2 * a]); g.hi[a] = fminf(g.hi[a], nd.bbox[2 * a + 1]);
+            }
+            cur_gate = g;
+            if (nd.is_internal) { stack.push_back(Visit{nd.right_idx, dead, g}); stack.push_back(Visit{nd.left_idx, dead, g}); }
+            else if (!dead) {
                 F.collect(nd.left_type, nd.left_idx, none, 0, emit);
                 if (nd.right_type != nd.left_type || nd.right_idx != nd.left_idx) F.collect(nd.right_type, nd.right_idx, none, 0, emit);
             }
         }
     }
+    cur_gate = open_gate;
     if (!s.bvh_mode) {                       // world.cuh:118-120: with a BVH in the world nothing else is visible
         for (size_t i = 0; i < s.spheres.size(); i++) if (!s.spheres[i].skip) { top_type = MORT_OBJ_SPHERE; top_idx = (int)i; F.collect(MORT_OBJ_SPHERE, (int)i, none, 0, emit); }
         for (size_t i = 0; i < s.quads.size(); i++) if (!s.quads[i].skip) { top_type = MORT_OBJ_QUAD; top_idx = (int)i; F.collect(MORT_OBJ_QUAD, (int)i, none, 0, emit); }
@@ -257,6 +275,15 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
         F.leaf_world_box(out.leaves[i].type, out.leaves[i].idx, chains[i], p.lo, p.hi);
         p.type = out.leaves[i].type; p.ref = (int)i;
         for (int a = 0; a < 3; a++) { M = fmaxf(M, fabsf(p.lo[a])); M = fmaxf(M, fabsf(p.hi[a])); }
+        // The reference's BVH boxes stop containing an object when its bubble sort physically swapped something a wrapper
+        // points at, or a list grew after it was wrapped (objects.cuh:630-661, 463-469): the reference then culls that object
+        // view-dependently.  That is not reproducible without running its BVH; refuse instead of rendering something else.
+        for (int a = 0; a < 3; a++) {
+            const float tol = 1e-4f * fmaxf(1.0f, fmaxf(fabsf(p.lo[a]), fabsf(p.hi[a])));
+            if (p.lo[a] < gates[i].lo[a] - tol || p.hi[a] > gates[i].hi[a] + tol)
+                return fail("a bvh node box of the reference's build does not contain an object below it (a wrapper's target was moved by the "
+                            "build's in-place sort, or a list grew after it was wrapped): the reference culls it view-dependently; not reproducible");
+        }
     }
     // The slab test runs in float with one FMA per plane; its error is a few ulp of the largest coordinate
     // in play.  Boxes are padded by 2e-6 * M so the BVH can never cull a hit the exact primitive test accepts

@@ -264,6 +264,10 @@ Handle Scene::add_translate(Handle obj, V3 offset, bool skip) {
     jlog(*this, "translate " + handle_token(obj, 'o') + " " + fs3(offset) + hid(skip));
     mscn_translate t; t.obj_type = obj.type; t.obj_idx = obj.idx; put3(t.offset, offset); t.skip = skip ? 1 : 0;
     translates.push_back(t);
+    Box6 bb; float c[6];                                                     // objects.cuh:264: child's box + displacement
+    if (!bbox_of(obj, c)) memset(c, 0, sizeof(c));
+    for (int a = 0; a < 3; a++) { bb.b[2 * a] = c[2 * a] + offset[a]; bb.b[2 * a + 1] = c[2 * a + 1] + offset[a]; }
+    translate_bbox.push_back(bb);
     return Handle{MORT_OBJ_TRANSLATE, (int)translates.size() - 1};
 }
 Handle Scene::add_rotate_y(Handle obj, float theta_deg, bool skip) {
@@ -272,6 +276,17 @@ Handle Scene::add_rotate_y(Handle obj, float theta_deg, bool skip) {
     float radians = (float)(theta_deg * 3.1415926535897932385 / 180.0);      // objects.cuh:297-299
     r.sin_theta = sinf(radians); r.cos_theta = cosf(radians);
     rotates.push_back(r);
+    Box6 bb; float c[6];                                                     // objects.cuh:304-329: box of the 8 rotated corners
+    if (!bbox_of(obj, c)) memset(c, 0, sizeof(c));
+    float pmin[3] = {HUGE_VALF, HUGE_VALF, HUGE_VALF}, pmax[3] = {-HUGE_VALF, -HUGE_VALF, -HUGE_VALF};
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+        float x = i * c[1] + (1 - i) * c[0], y = j * c[3] + (1 - j) * c[2], z = k * c[5] + (1 - k) * c[4];
+        float nx = r.cos_theta * x + r.sin_theta * z, nz = -r.sin_theta * x + r.cos_theta * z;
+        float t[3] = {nx, y, nz};
+        for (int a = 0; a < 3; a++) { pmin[a] = fminf(pmin[a], t[a]); pmax[a] = fmaxf(pmax[a], t[a]); }
+    }
+    box_from_points(bb.b, V3(pmin[0], pmin[1], pmin[2]), V3(pmax[0], pmax[1], pmax[2]));
+    rotate_bbox.push_back(bb);
     return Handle{MORT_OBJ_ROTATE_Y, (int)rotates.size() - 1};
 }
 Handle Scene::add_constant_medium(Handle boundary, float density, Handle mat, bool skip) {
@@ -281,6 +296,9 @@ Handle Scene::add_constant_medium(Handle boundary, float density, Handle mat, bo
     m.neg_inv_density = -(1.0 / density);                                     // objects.cuh:387 (double)
     m.mat_type = mat.type; m.mat_idx = mat.idx; m.skip = skip ? 1 : 0;
     media.push_back(m);
+    Box6 bb;                                                                 // objects.cuh:392: the boundary's box
+    if (!bbox_of(boundary, bb.b)) memset(bb.b, 0, sizeof(bb.b));
+    medium_bbox.push_back(bb);
     return Handle{MORT_OBJ_CONSTANT_MEDIUM, (int)media.size() - 1};
 }
 Handle Scene::add_list(bool skip) {
@@ -290,14 +308,26 @@ Handle Scene::add_list(bool skip) {
 }
 int Scene::list_add(Handle list, Handle obj) {
     if (list.type != MORT_OBJ_HITTABLE_LIST || list.idx < 0 || list.idx >= (int)lists.size()) return -1;
-    lists[list.idx].items.push_back(obj);
+    ListRec& L = lists[list.idx];
+    float b[6];                                                              // objects.cuh:463-469: first item's box, then unions
+    if (!bbox_of(obj, b)) memset(b, 0, sizeof(b));
+    if (L.items.empty()) memcpy(L.bbox, b, sizeof(b));
+    else { float u[6]; box_union(u, L.bbox, b); memcpy(L.bbox, u, sizeof(u)); }
+    L.has_bbox = true;
+    L.items.push_back(obj);
     jlog(*this, "add " + handle_token(list, 'o') + " " + handle_token(obj, 'o'));
     return 0;
 }
 
+// host_getBboxInfo (objects.cuh:918-945); any other handle type falls off the reference's switch (garbage there, zeros here)
 bool Scene::bbox_of(Handle h, float out[6]) const {
-    if (h.type == MORT_OBJ_SPHERE && h.idx >= 0 && h.idx < (int)spheres.size()) { memcpy(out, spheres[h.idx].bbox, 24); return true; }
-    if (h.type == MORT_OBJ_QUAD && h.idx >= 0 && h.idx < (int)quads.size()) { memcpy(out, quads[h.idx].bbox, 24); return true; }
+    auto in = [&](size_t n) { return h.idx >= 0 && (size_t)h.idx < n; };
+    if (h.type == MORT_OBJ_SPHERE && in(spheres.size())) { memcpy(out, spheres[h.idx].bbox, 24); return true; }
+    if (h.type == MORT_OBJ_QUAD && in(quads.size())) { memcpy(out, quads[h.idx].bbox, 24); return true; }
+    if (h.type == MORT_OBJ_TRANSLATE && in(translate_bbox.size())) { memcpy(out, translate_bbox[h.idx].b, 24); return true; }
+    if (h.type == MORT_OBJ_ROTATE_Y && in(rotate_bbox.size())) { memcpy(out, rotate_bbox[h.idx].b, 24); return true; }
+    if (h.type == MORT_OBJ_CONSTANT_MEDIUM && in(medium_bbox.size())) { memcpy(out, medium_bbox[h.idx].b, 24); return true; }
+    if (h.type == MORT_OBJ_HITTABLE_LIST && in(lists.size())) { memcpy(out, lists[h.idx].bbox, 24); return true; }
     return false;
 }
 
@@ -325,9 +355,9 @@ Handle Scene::add_bvh(Handle list, bool skip) {
     auto swap_objs = [&](Handle a, Handle b) {
         if (a.type == MORT_OBJ_SPHERE) std::swap(spheres[a.idx], spheres[b.idx]);
         else if (a.type == MORT_OBJ_QUAD) std::swap(quads[a.idx], quads[b.idx]);
-        else if (a.type == MORT_OBJ_TRANSLATE) std::swap(translates[a.idx], translates[b.idx]);
-        else if (a.type == MORT_OBJ_ROTATE_Y) std::swap(rotates[a.idx], rotates[b.idx]);
-        else if (a.type == MORT_OBJ_CONSTANT_MEDIUM) std::swap(media[a.idx], media[b.idx]);
+        else if (a.type == MORT_OBJ_TRANSLATE) { std::swap(translates[a.idx], translates[b.idx]); std::swap(translate_bbox[a.idx], translate_bbox[b.idx]); }
+        else if (a.type == MORT_OBJ_ROTATE_Y) { std::swap(rotates[a.idx], rotates[b.idx]); std::swap(rotate_bbox[a.idx], rotate_bbox[b.idx]); }
+        else if (a.type == MORT_OBJ_CONSTANT_MEDIUM) { std::swap(media[a.idx], media[b.idx]); std::swap(medium_bbox[a.idx], medium_bbox[b.idx]); }
     };
     struct Span { int b, e; };
     std::vector<Span> spans; spans.push_back(Span{0, (int)it.size()});
@@ -489,6 +519,8 @@ bool Scene::load(const std::string& path, std::string* err) {
     ok = ok && fread(&c, sizeof(c), 1, f) == 1;
     fclose(f);
     if (!ok) { if (err) *err = "malformed scene file " + path; clear(); return false; }
+    Box6 zero; memset(&zero, 0, sizeof(zero));           // the dump does not carry the wrappers' boxes (only a later add_bvh would read them)
+    translate_bbox.assign(translates.size(), zero); rotate_bbox.assign(rotates.size(), zero); medium_bbox.assign(media.size(), zero);
     bvh_mode = h.bvh_mode != 0;
     cam.aspect_ratio = c.aspect_ratio; cam.image_width = c.image_width; cam.image_height = c.image_height;
     cam.samples_per_pixel = c.samples_per_pixel; cam.pixel_samples_scale = c.pixel_samples_scale;

@@ -123,6 +123,10 @@ public:
     std::vector<mscn_translate> translates;
     std::vector<mscn_rotate_y> rotates;
     std::vector<mscn_medium> media;
+    // bounding boxes the reference computes in the wrappers' constructors (objects.cuh:258-266, 296-330, 384-393); they are not part
+    // of the scene dump and only matter to the reference's own BVH build (node boxes, sort order) when a wrapper is put in a bvh
+    struct Box6 { float b[6]; };
+    std::vector<Box6> translate_bbox, rotate_bbox, medium_bbox;
     std::vector<ListRec> lists;
     std::vector<BvhRec> bvhs;
     std::vector<mscn_lambertian> lambertians;

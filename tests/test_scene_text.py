@@ -105,3 +105,82 @@ def test_malformed_files_fail_with_line_numbers(hostsim, tmp_path, body, needle)
 def test_scene_loaded_from_a_binary_dump_has_no_text_form(hostsim, tmp_path):
     p = run(hostsim, golden_scene_path(1), ASSETS, "dumptext", tmp_path / "s.txt", ok=False)
     assert p.returncode != 0 and "no text form" in p.stderr
+
+
+def _random_scene_text(rng):
+    """A random but valid scene file: every statement kind, forward references only to things that exist."""
+    lines, tex, mat, obj, lists = [], [], [], [], []
+    f = lambda lo=-5.0, hi=5.0: f"{rng.uniform(lo, hi):.6g}"
+    v3 = lambda lo=-5.0, hi=5.0: " ".join(f(lo, hi) for _ in range(3))
+    for i in range(rng.integers(2, 5)):
+        lines.append(f"t{i} = solid {v3(0, 1)}"); tex.append(f"t{i}")
+    lines.append(f"tc = checker {f(0.1, 2)} {rng.choice(tex)} {rng.choice(tex)}"); tex.append("tc")
+    if rng.random() < 0.5:
+        lines.append(f"tn = noise {f(0.5, 4)} at {int(rng.integers(0, 5000))}"); tex.append("tn")
+    kinds = ["lambertian", "metal", "dielectric", "light", "isotropic"]
+    for i in range(rng.integers(3, 7)):
+        k = kinds[i] if i < 5 else str(rng.choice(kinds))
+        if k == "metal":
+            lines.append(f"m{i} = metal {v3(0, 1)} {f(0, 0.5)}")
+        elif k == "dielectric":
+            lines.append(f"m{i} = dielectric {f(1.1, 2.0)}")
+        else:
+            arg = str(rng.choice(tex)) if rng.random() < 0.6 else v3(0, 1)
+            lines.append(f"m{i} = {k} {arg}")
+        mat.append(f"m{i}")
+    depth, plain = {}, []                      # wrapper nesting per object; objects that are not media (media only exist at top level)
+    for i in range(rng.integers(4, 12)):
+        m, hid = rng.choice(mat), (" hidden" if rng.random() < 0.3 else "")
+        k = rng.integers(0, 6)
+        shallow = [o for o in plain if depth[o] < 3] if rng.random() < 0.9 else list(obj)   # mostly stay inside what the product supports
+        name, d, is_medium = f"o{i}", 0, False
+        if k == 0:
+            lines.append(f"{name} = sphere {v3()} {f(0.1, 2)} {m}{hid}")
+        elif k == 1:
+            lines.append(f"{name} = moving_sphere {v3()} {v3()} {f(0.1, 2)} {m}{hid}")
+        elif k == 2:
+            lines.append(f"{name} = quad {v3()} {f(0.5, 3)} 0 0  0 {f(0.5, 3)} 0 {m}{hid}")
+        elif k == 3 and shallow:
+            t = str(rng.choice(shallow)); d = depth.get(t, 0) + 1
+            lines.append(f"{name} = translate {t} {v3()}{hid}")
+        elif k == 4 and shallow:
+            t = str(rng.choice(shallow)); d = depth.get(t, 0) + 1
+            lines.append(f"{name} = rotate_y {t} {f(-90, 90)}{hid}")
+        elif k == 5 and shallow:
+            t = str(rng.choice(shallow)); is_medium = True
+            lines.append(f"{name} = medium {t} {f(0.01, 2)} {m}{hid}")
+        else:
+            lines.append(f"{name} = rotated_box {v3(0.5, 2)} {v3()} {f(-45, 45)} {m}"); d = 2
+        obj.append(name); depth[name] = d
+        if not is_medium:
+            plain.append(name)
+    if rng.random() < 0.7:
+        lines.append(f"box {v3()} {v3()} {rng.choice(mat)}")
+    for i in range(rng.integers(1, 3)):
+        lines.append(f"l{i} = list" + (" hidden" if rng.random() < 0.5 else ""))
+        pool = plain if rng.random() < 0.9 else obj
+        for o in rng.choice(pool, size=min(len(pool), int(rng.integers(1, 5))), replace=False):
+            lines.append(f"add l{i} {o}")
+        lists.append(f"l{i}")
+    if rng.random() < 0.4:
+        lines.append(f"b0 = bvh {lists[0]}")
+    if rng.random() < 0.3:
+        lines.append(f"host_rand_skip {int(rng.integers(0, 100))}")
+    lines.append(f"camera width {int(rng.integers(16, 200))} aspect {f(0.5, 2)} spp {int(rng.integers(1, 64))} depth {int(rng.integers(0, 30))} vfov {int(rng.integers(10, 90))}")
+    lines.append(f"camera lookfrom {v3()} lookat {v3()} vup 0 1 0 background {v3(0, 1)} defocus_angle {f(0, 2)} focus_dist {f(1, 20)}")
+    lines.append("camera light " + (str(rng.choice(obj + lists)) if rng.random() < 0.6 else "none"))
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_scene_files_round_trip(hostsim, seed, tmp_path):
+    """text -> arrays -> journal text -> arrays: same bytes, and the journal text is a fixed point"""
+    rng = np.random.default_rng(1000 + seed)
+    t0, a, t1, b, t2 = (tmp_path / n for n in ("s0.txt", "a.mscn", "s1.txt", "b.mscn", "s2.txt"))
+    t0.write_text(_random_scene_text(rng))
+    run(hostsim, f"text:{t0}", ASSETS, "dump", a)
+    run(hostsim, f"text:{t0}", ASSETS, "dumptext", t1)
+    run(hostsim, f"text:{t1}", ASSETS, "dump", b)
+    run(hostsim, f"text:{t1}", ASSETS, "dumptext", t2)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert open(t1).read() == open(t2).read()
