@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from conftest import bits
+from mort_b200 import formats as F
 from test_fuzz_parity import REFUSALS
 from test_scene_text import _random_scene_text
 
@@ -37,11 +38,15 @@ def test_random_scene_through_the_abi(seed, tmp_path):
             assert (hits[k][b] == ref[k][b]).all(), k
         assert (bits(hits["p"])[b] == bits(ref["p"])[b]).all() and (bits(hits["normal"])[b] == bits(ref["normal"])[b]).all()
         assert (hits["hit"] == brute["hit"]).all() and (bits(hits["t"]) == bits(brute["t"])).all() and (hits["leaf_idx"] == brute["leaf_idx"]).all()
-        if ref_probes.shape[1]:
-            assert probes.shape == ref_probes.shape
-            assert (probes["hit1"] == ref_probes["hit1"]).all() and (probes["hit2"] == ref_probes["hit2"]).all()
-            b1, b2 = ref_probes["hit1"] == 1, ref_probes["hit2"] == 1
-            assert (bits(probes["t1"])[b1] == bits(ref_probes["t1"])[b1]).all() and (bits(probes["t2"])[b2] == bits(ref_probes["t2"])[b2]).all()
+        # the product only keeps the media world::hit can reach: top-level (not hidden) ones, none at all once a bvh exists
+        sc = F.read_scene(dump)
+        vis = [] if len(sc["bvhs"]) else [i for i, m in enumerate(sc["media"]) if int(m["skip"]) == 0]
+        assert probes.shape[1] == len(vis)
+        for j, m in enumerate(vis):
+            mine, want = probes[:, j], ref_probes[:, m]
+            assert (mine["hit1"] == want["hit1"]).all() and (mine["hit2"] == want["hit2"]).all()
+            b1, b2 = want["hit1"] == 1, want["hit2"] == 1
+            assert (bits(mine["t1"])[b1] == bits(want["t1"])[b1]).all() and (bits(mine["t2"])[b2] == bits(want["t2"])[b2]).all()
         # a small frame against the oracle with the same stream
         r.override_camera(width=32, spp=9)
         fr = r.render(seed=5)
