@@ -120,7 +120,7 @@ void mort_default_render_opts(mort_render_opts* o);
  * w = number of samples that contained a NaN. */
 /* Device-resident frame: d_accum is a device pointer owned by the caller (e.g. a torch tensor). */
 int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts, void* d_accum);
-/* Exact accumulation image (opts.exact_accum = 1, megakernel only): W*H x 4 uint64 per pixel = Q31.32 fixed-point sums of
+/* Exact accumulation image (opts.exact_accum = 1, megakernel only): W*H x 4 uint64 per pixel = Q39.24 fixed-point sums of
  * r, g, b and a word of NaN / +inf sample counts.  Integer sums are associative, so partial frames of a sample split can be
  * added in ANY order (e.g. by an int64 SUM all-reduce) and the N-GPU frame equals the 1-GPU frame bit for bit.
  * mort_resolve_exact_device turns it into the float4 accumulation image described above. */

@@ -17,21 +17,22 @@
 namespace mort {
 
 // ------------------------------------------------------------------------------------------------------
-// Exact, order-independent accumulation.  A finished sample is added as Q31.32 fixed point into 64-bit
+// Exact, order-independent accumulation.  A finished sample is added as Q39.24 fixed point into 64-bit
 // integers (integer addition is associative: ANY distribution of a pixel's samples over lanes, warps, waves or
 // schedules gives the same bits), with NaN / +inf samples counted on the side so the frame keeps the IEEE
 // semantics of the reference's float sum (camera.cuh:190-198: one NaN sample poisons the pixel).
-//   word 0..2 : sum of r, g, b   (samples >= 2^30 are counted as +inf: they saturate the 8-bit frame anyway)
+//   word 0..2 : sum of r, g, b   (24 fractional bits = the resolution a float sample of magnitude ~1 has anyway; a pixel's sum may
+//               reach 2^39 = 5.5e11 — 4096 samples of radiance 1e8 — before it would wrap; single samples >= 2^38 are counted as +inf)
 //   word 3    : [0,20) NaN samples  [20,34) +inf in r  [34,48) +inf in g  [48,62) +inf in b
 // ------------------------------------------------------------------------------------------------------
 #define MEGA_PMAX 16
 __device__ __forceinline__ void fx_add(long long& acc, unsigned long long& flags, float v, int inf_shift) {
     if (v != v) return;                                                    // NaN: counted once per sample by the caller
-    if (!(fabsf(v) < 1073741824.0f)) { flags += 1ull << inf_shift; return; }
-    acc += __float2ll_rn(v * 4294967296.0f);
+    if (!(fabsf(v) < 274877906944.0f)) { flags += 1ull << inf_shift; return; }
+    acc += __float2ll_rn(v * 16777216.0f);
 }
 __device__ __forceinline__ float4 fx_resolve(long long r, long long g, long long b, unsigned long long flags) {
-    const float s = 1.0f / 4294967296.0f;
+    const float s = 1.0f / 16777216.0f;
     const unsigned nan_n = (unsigned)(flags & 0xFFFFFu);
     float4 o;
     o.x = __ll2float_rn(r) * s; o.y = __ll2float_rn(g) * s; o.z = __ll2float_rn(b) * s; o.w = (float)nan_n;

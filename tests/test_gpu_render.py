@@ -258,3 +258,27 @@ def test_wavefront_renders_the_same_frame_as_the_megakernel(renderer, sc, w, spp
     c = renderer.render(seed=21, mode=MODE_WAVEFRONT)
     d = renderer.render(seed=21, mode=MODE_WAVEFRONT)
     assert np.array_equal(c.accum, d.accum, equal_nan=True), "wavefront frames must be bit-reproducible"
+
+
+def test_bright_emitters_do_not_wrap_the_fixed_point_sums(renderer):
+    """1024 samples of radiance 3e6 sum to 3e9 per pixel: beyond a Q31.32 accumulator, well inside the Q39.24 one"""
+    import oracle_binding as O
+    r = renderer
+    r.clear_scene()
+    lamp = r.add_diffuse_light(r.add_solid(3e6, 2e6, 1e6))
+    r.add_quad((-1, -1, 0), (2, 0, 0), (0, 2, 0), lamp)            # faces the camera (normal +z), fills the view
+    cam = r.get_camera()
+    cam.aspect_ratio = 1.0; cam.image_width = 16; cam.samples_per_pixel = 1024; cam.bounce_limit = 4; cam.vfov = 20
+    cam.background[:] = (0, 0, 0); cam.lookfrom[:] = (0, 0, 3); cam.lookat[:] = (0, 0, 0); cam.vup[:] = (0, 1, 0)
+    cam.light_obj_type = -1
+    r.set_camera(cam)
+    r.commit()
+    fr = r.render(seed=3)
+    assert np.isfinite(fr.accum[..., :3]).all() and (fr.accum[..., 3] == 0).all()
+    centre = fr.accum[4:12, 4:12, :3] / 1024
+    assert np.allclose(centre, [3e6, 2e6, 1e6], rtol=1e-6)
+    assert (fr.rgba8[4:12, 4:12, :3] == 255).all()
+    path = "/tmp/mort_bright_scene.mscn"
+    r.dump_scene(path)
+    hdr, _, _ = O.OracleScene(path).render(seed=3, want_rgba8=False)
+    assert np.allclose(fr.accum[..., :3], hdr[..., :3], rtol=1e-4, atol=1.0)
