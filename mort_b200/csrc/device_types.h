@@ -6,7 +6,7 @@
 //   SphereGeom  32 B   {cx,cy,cz,r} {vx,vy,vz,inst}          hot: intersected during traversal
 //   PrimInfo    16 B   {mat_gid, obj_idx, order, 0}           cold: read once for the winning primitive / on ties
 //   QuadRec     96 B   {n,D} {Q,inst} {u,mat_gid} {v,order} {w,obj_idx} {area,top,-,-}; first 16 B decide most misses
-//   Instance    64 B   up to 4 ops (translate / rotate_y), outermost first
+//   Instance   128 B   up to 7 ops (translate / rotate_y), outermost first
 //   Material    32 B   Texture 32 B
 //
 // Child word of a Bvh4Node:  0xFFFFFFFF empty | internal: node index (bit31 = 0)
@@ -39,9 +39,10 @@ struct alignas(32) QuadRec {
 };
 
 enum { INST_OP_TRANSLATE = 1, INST_OP_ROTATE_Y = 2 };
+#define MORT_INSTANCE_OPS 7                 // 16 + 7 * 16 = 128 B; only the first nops rows are ever read
 struct alignas(32) Instance {
-    int32_t nops; int32_t pad[3];           // up to 3 ops: covers translate(rotate_y(x)) and one more level
-    float a[3][4];                          // translate: {x,y,z, kind} ; rotate_y: {sin, cos, 0, kind}  (kind as int bits)
+    int32_t nops; int32_t pad[3];           // up to MORT_INSTANCE_OPS nested wrappers, outermost first
+    float a[MORT_INSTANCE_OPS][4];                          // translate: {x,y,z, kind} ; rotate_y: {sin, cos, 0, kind}  (kind as int bits)
 };
 
 struct alignas(32) Material {               // gid = running index over lambertian|metal|dielectric|diffuse_light|isotropic

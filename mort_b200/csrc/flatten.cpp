@@ -11,7 +11,7 @@
 namespace mort {
 namespace {
 
-struct Chain { int n = 0; int kind[3]; int idx[3]; bool overflow = false;
+struct Chain { int n = 0; int kind[MORT_INSTANCE_OPS]; int idx[MORT_INSTANCE_OPS]; bool overflow = false;
     bool operator<(const Chain& o) const {
         if (n != o.n) return n < o.n;
         for (int i = 0; i < n; i++) { if (kind[i] != o.kind[i]) return kind[i] < o.kind[i]; if (idx[i] != o.idx[i]) return idx[i] < o.idx[i]; }
@@ -57,12 +57,12 @@ struct Flattener {
                 emit(type, idx, c); break;
             case MORT_OBJ_TRANSLATE:
                 if (idx < 0 || idx >= (int)s.translates.size()) { err = "translate handle out of range"; return; }
-                if (c.n >= 3) { err = "more than 3 nested translate/rotate_y wrappers are not supported"; return; }
+                if (c.n >= MORT_INSTANCE_OPS) { err = "more than 7 nested translate/rotate_y wrappers are not supported"; return; }
                 c.kind[c.n] = MORT_OBJ_TRANSLATE; c.idx[c.n++] = idx;
                 collect(s.translates[idx].obj_type, s.translates[idx].obj_idx, c, depth + 1, emit); break;
             case MORT_OBJ_ROTATE_Y:
                 if (idx < 0 || idx >= (int)s.rotates.size()) { err = "rotate_y handle out of range"; return; }
-                if (c.n >= 3) { err = "more than 3 nested translate/rotate_y wrappers are not supported"; return; }
+                if (c.n >= MORT_INSTANCE_OPS) { err = "more than 7 nested translate/rotate_y wrappers are not supported"; return; }
                 c.kind[c.n] = MORT_OBJ_ROTATE_Y; c.idx[c.n++] = idx;
                 collect(s.rotates[idx].obj_type, s.rotates[idx].obj_idx, c, depth + 1, emit); break;
             case MORT_OBJ_HITTABLE_LIST:

@@ -19,7 +19,7 @@ from mort_b200 import formats as F
 from test_scene_text import _random_scene_text
 
 REFUSALS = ("constant_medium nested inside another object is not supported",
-            "more than 3 nested translate/rotate_y wrappers are not supported",
+            "more than 7 nested translate/rotate_y wrappers are not supported",
             "a bvh node box of the reference's build does not contain an object below it")
 
 

@@ -132,7 +132,7 @@ def _random_scene_text(rng):
     for i in range(rng.integers(4, 12)):
         m, hid = rng.choice(mat), (" hidden" if rng.random() < 0.3 else "")
         k = rng.integers(0, 6)
-        shallow = [o for o in plain if depth[o] < 3] if rng.random() < 0.9 else list(obj)   # mostly stay inside what the product supports
+        shallow = [o for o in plain if depth[o] < 7] if rng.random() < 0.9 else list(obj)   # mostly stay inside what the product supports
         name, d, is_medium = f"o{i}", 0, False
         if k == 0:
             lines.append(f"{name} = sphere {v3()} {f(0.1, 2)} {m}{hid}")
