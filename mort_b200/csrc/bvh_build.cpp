@@ -36,7 +36,7 @@ struct Box {
 struct Node2 { Box box; int left = -1, right = -1, first = 0, count = 0, type = 0; };
 
 constexpr int kBins = 16;
-constexpr float kTrav = 1.0f;
+static float kTrav = 1.0f;                 // cost of one more (binary) node relative to one sphere test; MORT_KTRAV overrides (experiments)
 inline float prim_cost(int type) { return type == MORT_OBJ_QUAD ? 1.3f : 1.0f; }
 
 // Subtrees over disjoint index ranges are independent, so the top `par_levels` levels hand their left child to another
@@ -51,6 +51,7 @@ struct Builder {
     int max_leaf = MORT_MAX_LEAF;
     explicit Builder(const std::vector<BuildPrim>& p) : prims(p) {
         if (const char* e = getenv("MORT_MAX_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) max_leaf = v; }   // experiments only
+        if (const char* e = getenv("MORT_KTRAV")) { float v = (float)atof(e); if (v > 0) kTrav = v; }
         idx.resize(p.size());
         for (size_t i = 0; i < p.size(); i++) idx[i] = (int)i;
         nodes.reserve(p.size() * 2 + 1);

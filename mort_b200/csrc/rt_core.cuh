@@ -237,6 +237,13 @@ MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3
 // closest hit over the 4-wide BVH
 // ---------------------------------------------------------------------------------------------------
 #define MORT_STACK 48
+#if !defined(__CUDA_ARCH__) && defined(MORT_HOST_COUNTERS)      // tests/hostsim only: traversal work per query, to compare tree builders on the CPU
+struct HostCounters { unsigned long long queries, node_steps, leaf_visits, prim_tests; };
+static HostCounters g_host_counters = {0, 0, 0, 0};
+#define MORT_COUNT(field, n) (g_host_counters.field += (n))
+#else
+#define MORT_COUNT(field, n) ((void)0)
+#endif
 struct alignas(8) StackEntry { uint32_t child; float t; };
 #define MORT_PRIM_NONE 0xFFFFFFFFu
 
@@ -343,8 +350,10 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
     // loops are structured (no continue / break across them) so the compiler's convergence barriers sit at
     // the loop exits: the warp's lanes test nodes together and intersect leaves together instead of drifting
     // apart for the whole traversal (lane utilisation 6.6/32 with the former single loop).
+    MORT_COUNT(queries, 1);
     while (cur != MORT_CHILD_EMPTY) {
         while (!(cur & MORT_LEAF_BIT)) {
+            MORT_COUNT(node_steps, 1);
             F4 nx, ny, nz, fx, fy, fz, chf;
 #if defined(__CUDA_ARCH__)
             if (kStaged) {
@@ -392,6 +401,7 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
             cur = next;
         }
         if (cur != MORT_CHILD_EMPTY) {
+            MORT_COUNT(leaf_visits, 1); MORT_COUNT(prim_tests, ((cur >> 27) & 7u) + 1);
             leaf_intersect(sc, cur, r, tmin, best, order_lo, order_hi);
             uint32_t next = MORT_CHILD_EMPTY;
             while (sp > 0 && next == MORT_CHILD_EMPTY) { sp--; const StackEntry e = stack[sp]; if (e.t <= best.t) next = e.child; }

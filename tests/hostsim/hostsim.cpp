@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#define MORT_HOST_COUNTERS
 #include "flatten.hpp"
 #include "rt_core.cuh"
 #include "scene.hpp"
@@ -180,6 +181,10 @@ int main(int argc, char** argv) {
             hdr[4 * (size_t)pix] = sx; hdr[4 * (size_t)pix + 1] = sy; hdr[4 * (size_t)pix + 2] = sz; hdr[4 * (size_t)pix + 3] = (float)nan_n;
         }
         fprintf(stderr, "segments %llu\n", segs);
+        if (g_host_counters.queries)
+            fprintf(stderr, "tree queries %llu node_steps/query %.3f leaf_visits/query %.3f prim_tests/query %.3f\n", g_host_counters.queries,
+                    (double)g_host_counters.node_steps / g_host_counters.queries, (double)g_host_counters.leaf_visits / g_host_counters.queries,
+                    (double)g_host_counters.prim_tests / g_host_counters.queries);
         FILE* fo = fopen(argv[8], "wb"); uint32_t hd[5] = {0x474D494Du, (uint32_t)cam.width, (uint32_t)cam.height, 4, 1};
         fwrite(hd, 4, 5, fo); fwrite(hdr.data(), 4, hdr.size(), fo); fclose(fo);
     }
