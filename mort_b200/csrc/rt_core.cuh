@@ -238,8 +238,8 @@ MORT_HD bool quad_test(F4 nD, const float* rec /* QuadRec rows 1..4 */, f3 o, f3
 // ---------------------------------------------------------------------------------------------------
 #define MORT_STACK 48
 #if !defined(__CUDA_ARCH__) && defined(MORT_HOST_COUNTERS)      // tests/hostsim only: traversal work per query, to compare tree builders on the CPU
-struct HostCounters { unsigned long long queries, node_steps, leaf_visits, prim_tests; };
-static HostCounters g_host_counters = {0, 0, 0, 0};
+struct HostCounters { unsigned long long queries, node_steps, leaf_visits, prim_tests, pushes, push_at[MORT_STACK]; };
+static HostCounters g_host_counters = {};
 #define MORT_COUNT(field, n) (g_host_counters.field += (n))
 #else
 #define MORT_COUNT(field, n) ((void)0)
@@ -392,7 +392,7 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
             // push far-to-near, continue with the nearest; nothing hit -> pop
 #pragma unroll
             for (int k = 3; k >= 1; k--)
-                if (cw[k] != MORT_CHILD_EMPTY) { StackEntry e; e.child = cw[k]; e.t = tn[k]; stack[sp] = e; sp++; }   // depth * 3 <= MORT_STACK is checked at commit
+                if (cw[k] != MORT_CHILD_EMPTY) { MORT_COUNT(pushes, 1); MORT_COUNT(push_at[sp], 1); StackEntry e; e.child = cw[k]; e.t = tn[k]; stack[sp] = e; sp++; }   // depth * 3 <= MORT_STACK is checked at commit
             uint32_t next = cw[0];
             if (next == MORT_CHILD_EMPTY) {
                 // entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit

@@ -185,6 +185,12 @@ int main(int argc, char** argv) {
             fprintf(stderr, "tree queries %llu node_steps/query %.3f leaf_visits/query %.3f prim_tests/query %.3f\n", g_host_counters.queries,
                     (double)g_host_counters.node_steps / g_host_counters.queries, (double)g_host_counters.leaf_visits / g_host_counters.queries,
                     (double)g_host_counters.prim_tests / g_host_counters.queries);
+        if (g_host_counters.pushes) {
+            fprintf(stderr, "stack pushes/query %.3f; share of pushes at depth >= k:", (double)g_host_counters.pushes / g_host_counters.queries);
+            unsigned long long above = g_host_counters.pushes;
+            for (int k = 0; k < 16; k++) { fprintf(stderr, " %d:%.3f", k, (double)above / g_host_counters.pushes); above -= g_host_counters.push_at[k]; }
+            fprintf(stderr, "\n");
+        }
         FILE* fo = fopen(argv[8], "wb"); uint32_t hd[5] = {0x474D494Du, (uint32_t)cam.width, (uint32_t)cam.height, 4, 1};
         fwrite(hd, 4, 5, fo); fwrite(hdr.data(), 4, hdr.size(), fo); fclose(fo);
     }
