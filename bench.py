@@ -361,7 +361,11 @@ def run_mort(a):
                          "kernel_ms_per_launch": kernel_ms_per_launch,
                          "how": f"algorithmic {FLOP_PER_RAY:.0f} FLOP per path segment (SURVEY.md §8d, config 2) x segments per launch / CUDA-event kernel time; "
                                 f"peak = {st['sm_count']} SMs x 128 lanes x 2 x median SM clock under load (the path is neither HBM- nor tensor-bound)",
-                         "hbm_peak_gbs_measured": peaks.get("hbm_gbs")},
+                         "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
+                         # the same kernel against the HBM roofline (the contract's other bound): measured DRAM bytes per launch / kernel time
+                         "hbm": ({"achieved_gbs": traffic / (kernel_ms_per_launch * 1e6), "peak_gbs": peaks.get("hbm_gbs"),
+                                  "frac": traffic / (kernel_ms_per_launch * 1e6) / peaks["hbm_gbs"]}
+                                 if traffic and kernel_ms_per_launch and peaks.get("hbm_gbs") else None)},
             "kernel": {"regs": st2["regs_per_thread"], "threads_per_block": st2["threads_per_block"], "blocks_per_sm": st2["blocks_per_sm"],
                        "staged_nodes": st2["staged_nodes"], "bvh_nodes": st2["n_nodes"], "leaves": st2["n_leaves"], "linear_scan": st2["n_nodes"] == 1},
         }
