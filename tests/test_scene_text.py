@@ -184,3 +184,12 @@ def test_random_scene_files_round_trip(hostsim, seed, tmp_path):
     run(hostsim, f"text:{t1}", ASSETS, "dumptext", t2)
     assert open(a, "rb").read() == open(b, "rb").read()
     assert open(t1).read() == open(t2).read()
+
+
+@pytest.mark.parametrize("sc", [2, 6, 7])
+def test_example_files_are_the_shipped_scenes(hostsim, sc, tmp_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "e.mscn"
+    run(hostsim, "text:" + os.path.join(root, "examples", f"scene_{sc}.txt"), ASSETS, "dump", out)
+    assert open(out, "rb").read() == open(golden_scene_path(sc, str(tmp_path)), "rb").read()
+    assert open(os.path.join(root, "examples", "room_handwritten.txt")).read().strip() == HAND_WRITTEN.strip()
