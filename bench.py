@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--bps", type=int, default=0, help="megakernel blocks per SM (selects the register-capped variant)")
     ap.add_argument("--split", default="sample", choices=["sample", "tile"], help="how the frame is sharded over GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--field", type=int, default=0, help="BASELINE config 4: sphere field over cells [-G,G)^2 instead of --scene (G = 500: 1 M spheres)")
+    ap.add_argument("--fieldcam", type=int, default=0, choices=[0, 1], help="0 = book view, 1 = aerial")
     return ap.parse_args()
 
 
@@ -224,7 +226,11 @@ def run_mort(a):
     dev = torch.device("cuda", local)
 
     r = Renderer(local)
-    r.build_scene(a.scene).override_camera(width=a.width, aspect=a.aspect, spp=a.spp, depth=a.depth).commit()
+    if a.field > 0:
+        r.build_sphere_field(a.field, 69420, a.fieldcam)
+    else:
+        r.build_scene(a.scene)
+    r.override_camera(width=a.width, aspect=a.aspect, spp=a.spp, depth=a.depth).commit()
     st = r.stats
     H, W, n_spp = st["height"], st["width"], st["sqrt_spp"] ** 2
     stream = torch.cuda.current_stream()
@@ -339,14 +345,15 @@ def run_mort(a):
         traffic = None
         try:    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this config, from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if (a.scene, a.width, a.spp, a.depth, a.mode) == (6, 600, 1024, 50, "mega") and world == 1:
+            if (a.scene, a.width, a.spp, a.depth, a.mode, a.field) == (6, 600, 1024, 50, "mega", 0) and world == 1:
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
         res = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"mort scene {a.scene} ({'cornell_box' if a.scene == 6 else 'scene'}) {W}x{H}, {a.spp} spp ({n_spp} effective), max depth {a.depth}",
+            "config": {"workload": (f"sphere field G={a.field} ({st2['n_leaves']} leaves, camera {a.fieldcam})" if a.field > 0 else
+                                    f"mort scene {a.scene} ({'cornell_box' if a.scene == 6 else 'scene'})") + f" {W}x{H}, {a.spp} spp ({n_spp} effective), max depth {a.depth}",
                        "scene": a.scene, "width": W, "height": H, "spp": a.spp, "depth": a.depth, "mode": a.mode,
                        "parallelism": f"{a.split}-split x{world} + 1 NCCL int64 SUM reduce of the exact partial frames per frame" if world > 1 else "single GPU",
                        "l2": "192 MiB buffer written between timed iterations (L2 flush)"},
@@ -369,7 +376,7 @@ def run_mort(a):
             "kernel": {"regs": st2["regs_per_thread"], "threads_per_block": st2["threads_per_block"], "blocks_per_sm": st2["blocks_per_sm"],
                        "staged_nodes": st2["staged_nodes"], "bvh_nodes": st2["n_nodes"], "leaves": st2["n_leaves"], "linear_scan": st2["n_nodes"] == 1},
         }
-        if world == 1 and not a.no_cpu_baseline:
+        if world == 1 and not a.no_cpu_baseline and a.field == 0:
             try:
                 res["cpu_baseline"] = cpu_baseline(a)
             except Exception as ex:  # the baseline is a report, never a gate
