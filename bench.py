@@ -341,7 +341,9 @@ def run_mort(a):
         fp32_peak = st["sm_count"] * 128 * 2 * sm_clock / 1e12                    # TFLOP/s at the clock actually sustained
         kernel_ms_per_launch = ker_ms_max / a.steps
         per_gpu_rays_per_s = (seg_all / world) / a.steps / (kernel_ms_per_launch * 1e-3)
-        achieved = per_gpu_rays_per_s * FLOP_PER_RAY / 1e12
+        # FLOP_ray = 2*ceil(log2 n)*F_box*1.5 + 2*F_prim + F_rec + F_shade, evaluated there for the four configs
+        flop_per_ray, flop_cfg = (1286.0, "config 4") if a.field > 0 else {1: (692.0, "config 1"), 8: (860.0, "config 3"), 9: (860.0, "config 3")}.get(a.scene, (FLOP_PER_RAY, "config 2"))
+        achieved = per_gpu_rays_per_s * flop_per_ray / 1e12
         traffic = None
         try:    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this config, from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
@@ -354,7 +356,7 @@ def run_mort(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": (f"sphere field G={a.field} ({st2['n_leaves']} leaves, camera {a.fieldcam})" if a.field > 0 else
                                     f"mort scene {a.scene} ({'cornell_box' if a.scene == 6 else 'scene'})") + f" {W}x{H}, {a.spp} spp ({n_spp} effective), max depth {a.depth}",
-                       "scene": a.scene, "width": W, "height": H, "spp": a.spp, "depth": a.depth, "mode": a.mode,
+                       "scene": None if a.field > 0 else a.scene, "width": W, "height": H, "spp": a.spp, "depth": a.depth, "mode": a.mode,
                        "parallelism": f"{a.split}-split x{world} + 1 NCCL int64 SUM reduce of the exact partial frames per frame" if world > 1 else "single GPU",
                        "l2": "192 MiB buffer written between timed iterations (L2 flush)"},
             "mrays_per_s": mrays, "segments_per_sample": seg_all / (samples_per_frame * a.steps),
@@ -366,7 +368,7 @@ def run_mort(a):
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (ncu)", "kernel": "mega_kernel" if a.mode == "mega" else "wavefront kernels",
                          "kernel_ms_per_launch": kernel_ms_per_launch,
-                         "how": f"algorithmic {FLOP_PER_RAY:.0f} FLOP per path segment (SURVEY.md §8d, config 2) x segments per launch / CUDA-event kernel time; "
+                         "how": f"algorithmic {flop_per_ray:.0f} FLOP per path segment (SURVEY.md §8d, {flop_cfg}) x segments per launch / CUDA-event kernel time; "
                                 f"peak = {st['sm_count']} SMs x 128 lanes x 2 x median SM clock under load (the path is neither HBM- nor tensor-bound)",
                          "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
                          # the same kernel against the HBM roofline (the contract's other bound): measured DRAM bytes per launch / kernel time
