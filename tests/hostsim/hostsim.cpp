@@ -131,9 +131,19 @@ int main(int argc, char** argv) {
         std::vector<float> rays((size_t)n * 7); if (fread(rays.data(), 4, rays.size(), fi) != rays.size()) return 3; fclose(fi);
         bool brute = argc > 6 && !strcmp(argv[6], "brute");
         std::vector<mhit_record> out(n);
+        std::vector<mhit_medium_probe> probes((size_t)n * d.n_media);      // like trace_kernel (render.cu): both boundary probes of every kept medium
         for (int i = 0; i < n; i++) {
             const float* q = &rays[7 * (size_t)i];
             Ray r; r.o = mk3(q[0], q[1], q[2]); r.d = mk3(q[3], q[4], q[5]); r.tm = q[6];
+            for (int m = 0; m < d.n_media; m++) {
+                mhit_medium_probe pr; pr.hit1 = pr.hit2 = 0; pr.t1 = pr.t2 = 0.f;
+                float t1, t2;
+                if (boundary_probe(d, d.media[m], r, -INFINITY, INFINITY, t1)) {
+                    pr.hit1 = 1; pr.t1 = t1;
+                    if (boundary_probe(d, d.media[m], r, (float)((double)t1 + 0.0001), INFINITY, t2)) { pr.hit2 = 1; pr.t2 = t2; }
+                }
+                probes[(size_t)i * d.n_media + m] = pr;
+            }
             Hit h; bool any = brute ? closest_hit_brute(d, r, 0.001f, INFINITY, h) : closest_hit<false>(d, nullptr, 0, r, 0.001f, INFINITY, h);
             mhit_record o; memset(&o, 0, sizeof(o)); o.hit = any; o.leaf_type = o.leaf_idx = o.top_type = o.top_idx = -1;
             if (any) {
@@ -148,8 +158,10 @@ int main(int argc, char** argv) {
             }
             out[i] = o;
         }
-        FILE* fo = fopen(argv[5], "wb"); uint32_t oh[4] = {MHIT_MAGIC, (uint32_t)n, 0, (uint32_t)f.stats.n_leaves};
-        fwrite(oh, 4, 4, fo); fwrite(rays.data(), 4, rays.size(), fo); fwrite(out.data(), sizeof(mhit_record), n, fo); fclose(fo);
+        FILE* fo = fopen(argv[5], "wb"); uint32_t oh[4] = {MHIT_MAGIC, (uint32_t)n, (uint32_t)d.n_media, (uint32_t)f.stats.n_leaves};
+        fwrite(oh, 4, 4, fo); fwrite(rays.data(), 4, rays.size(), fo); fwrite(out.data(), sizeof(mhit_record), n, fo);
+        if (!probes.empty()) fwrite(probes.data(), sizeof(mhit_medium_probe), probes.size(), fo);
+        fclose(fo);
     } else if (mode == "render") {
         uint32_t seed = (uint32_t)strtoul(argv[7], 0, 10);
         const CameraParams& cam = f.cam;

@@ -49,8 +49,9 @@ def test_random_scene_closest_hits_match_the_oracle(hostsim, seed, tmp_path):
         assert _refused(p)
         pytest.skip("scene refused: " + p.stderr.strip()[-90:])
     subprocess.run([hostsim, f"text:{txt}", ASSETS, "trace", str(fin), str(fbr), "brute"], check=True, capture_output=True)
-    out, br = F.read_hits(fout)["hits"], F.read_hits(fbr)["hits"]
-    ref, _ = O.OracleScene(str(dump)).trace(rays)
+    res = F.read_hits(fout)
+    out, probes, br = res["hits"], res["probes"], F.read_hits(fbr)["hits"]
+    ref, ref_probes = O.OracleScene(str(dump)).trace(rays)
     b = ref["hit"] == 1
     assert (out["hit"] == ref["hit"]).all()
     assert (bits(out["t"])[b] == bits(ref["t"])[b]).all()
@@ -59,6 +60,15 @@ def test_random_scene_closest_hits_match_the_oracle(hostsim, seed, tmp_path):
     assert (bits(out["p"])[b] == bits(ref["p"])[b]).all() and (bits(out["normal"])[b] == bits(ref["normal"])[b]).all()
     # the tree and the brute-force scan of the same flattened scene agree as well
     assert (out["hit"] == br["hit"]).all() and (bits(out["t"]) == bits(br["t"])).all() and (out["leaf_idx"] == br["leaf_idx"]).all()
+    # boundary probes of the media the product keeps (top-level, not hidden, none once a bvh exists): entry / exit distances
+    sc = F.read_scene(str(dump))
+    vis = [] if len(sc["bvhs"]) else [i for i, m in enumerate(sc["media"]) if int(m["skip"]) == 0]
+    assert probes.shape[1] == len(vis)
+    for j, m in enumerate(vis):
+        mine, want = probes[:, j], ref_probes[:, m]
+        assert (mine["hit1"] == want["hit1"]).all() and (mine["hit2"] == want["hit2"]).all()
+        b1, b2 = want["hit1"] == 1, want["hit2"] == 1
+        assert (bits(mine["t1"])[b1] == bits(want["t1"])[b1]).all() and (bits(mine["t2"])[b2] == bits(want["t2"])[b2]).all()
 
 
 @pytest.mark.parametrize("seed", range(100, 116))

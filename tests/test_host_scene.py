@@ -41,7 +41,14 @@ def test_flatten_bvh_and_traversal_reproduce_reference_hits(hostsim, sc, tmp_pat
         F.write_hits(fin, g[f"{kind}_rays"], g[f"{kind}_hits"])
         run(hostsim, sc, ASSETS, "trace", fin, fout)
         run(hostsim, sc, ASSETS, "trace", fin, fbr, "brute")
-        ref, out, br = g[f"{kind}_hits"], F.read_hits(fout)["hits"], F.read_hits(fbr)["hits"]
+        res = F.read_hits(fout)
+        ref, out, br = g[f"{kind}_hits"], res["hits"], F.read_hits(fbr)["hits"]
+        if f"{kind}_probes" in g.files and g[f"{kind}_probes"].size:          # medium boundary probes recorded from the reference
+            want, got = g[f"{kind}_probes"], res["probes"]
+            assert got.shape == want.shape
+            assert (got["hit1"] == want["hit1"]).all() and (got["hit2"] == want["hit2"]).all()
+            b1, b2 = want["hit1"] == 1, want["hit2"] == 1
+            assert (bits(got["t1"])[b1] == bits(want["t1"])[b1]).all() and (bits(got["t2"])[b2] == bits(want["t2"])[b2]).all()
         b = ref["hit"] == 1
         assert (out["hit"] == ref["hit"]).all() and (bits(out["t"])[b] == bits(ref["t"])[b]).all()
         for k in ("leaf_type", "leaf_idx", "mat_type", "mat_idx", "front_face"):
