@@ -34,5 +34,10 @@ for seed in range(30000, 30000 + int(sys.argv[1])):
 print("runs", ran, "sanitizer reports", bad)
 sys.exit(1 if bad else 0)
 PY
-[ $bad = 0 ] && echo "asan/ubsan: clean"
+# the tree builder runs subtrees on several threads: ThreadSanitizer over a 40 k-sphere field
+g++ -std=c++17 -O1 -g -fsanitize=thread -ffp-contract=off -Imort_b200/csrc -Iinclude \
+    tests/hostsim/hostsim.cpp mort_b200/csrc/scene.cpp mort_b200/csrc/scenes.cpp mort_b200/csrc/scene_text.cpp mort_b200/csrc/flatten.cpp \
+    mort_b200/csrc/bvh_build.cpp -o /tmp/hostsim_tsan
+/tmp/hostsim_tsan field:100 mort_b200/assets checkbvh 2>&1 | grep -E "WARNING: ThreadSanitizer" && bad=1
+[ $bad = 0 ] && echo "asan/ubsan/tsan: clean"
 exit $bad
