@@ -37,8 +37,10 @@ enum mort_status {
 int mort_create(int cuda_device, mort_ctx** out);
 int mort_destroy(mort_ctx* ctx);
 const char* mort_last_error(const mort_ctx* ctx);
-/* launches go to this cudaStream_t (default: the context's own stream).  Lets a host framework time or
- * order the kernels on its current stream. */
+/* launches go to this cudaStream_t.  Default: the context's own stream, a BLOCKING stream — it is ordered after
+ * everything the host queued on the legacy default stream (e.g. a framework's fill of a buffer handed to
+ * mort_render_device) and before what it queues there afterwards.  A host that works on other (non-blocking) streams
+ * passes the stream its buffers are ready on; every device pointer given to a mort_* call must be ready on that stream. */
 int mort_set_stream(mort_ctx* ctx, void* cuda_stream);
 
 /* ---- scenes ------------------------------------------------------------------------------------------- */
@@ -97,12 +99,18 @@ int mort_get_camera_record(mort_ctx* ctx, mscn_camera* out);               /* ev
 int mort_commit(mort_ctx* ctx);
 
 /* ---- render (renderKernel, mort.cu:44-47,99-106; Camera::render, camera.cuh:178-208) ------------------- */
-enum { MORT_MODE_MEGAKERNEL = 0, MORT_MODE_WAVEFRONT = 1 };
+/* Three schedulers over the same per-ray code, Philox stream and estimator:
+ *   MEGAKERNEL  persistent warps, a lane owns a path from camera to termination (render.cu)
+ *   WAVEFRONT   one kernel per stage over SoA queues in HBM (wavefront.cu)
+ *   POOL        block wavefront: one persistent kernel, every thread block alternates trace / shade phases over a pool of
+ *               paths in its shared memory, shading sorted by material class (pool.cu)
+ * MEGAKERNEL and POOL accumulate exactly (integers) and render bit-identical frames. */
+enum { MORT_MODE_MEGAKERNEL = 0, MORT_MODE_WAVEFRONT = 1, MORT_MODE_POOL = 2 };
 typedef struct {
     uint32_t seed, frame;          /* Philox key; the reference's seed is 69420 (mort.cu:707) */
     int32_t mode;                  /* MORT_MODE_* */
     int32_t sample_mod, sample_rem;/* sample-split across GPUs: this call renders strata rows s_j % mod == rem (1,0 = all) */
-    int32_t stage_nodes;           /* BVH nodes staged in shared memory: -1 auto, 0 none, N first N (breadth-first) */
+    int32_t stage_nodes;           /* megakernel: BVH nodes staged in shared memory: <= 0 none (default), N first N (breadth-first) */
     int32_t threads_per_block;     /* 0 = default */
     int32_t blocks_per_sm;         /* 0 = default */
     int32_t wavefront_paths;       /* paths in flight for the wavefront mode, 0 = default */
@@ -111,7 +119,9 @@ typedef struct {
                                       every other pixel of d_accum untouched (0,0 or 1,0 = whole frame) */
     int32_t accumulate;            /* exact_accum only: 1 = ADD this call's sums to the contents of d_accum (progressive rendering:
                                       render frame 0 with 0, frames 1.. with 1, a new `frame` each time), 0 = overwrite */
-    int32_t reserved[3];
+    int32_t pool_paths;            /* MORT_MODE_POOL: paths per thread-block pool (0 = default 1024; 88 B of shared memory each) */
+    int32_t pool_refill;           /* MORT_MODE_POOL: reserved for mid-traversal lane refill (0 = off) */
+    int32_t reserved[1];
 } mort_render_opts;
 void mort_default_render_opts(mort_render_opts* o);
 
@@ -155,6 +165,39 @@ int mort_tonemap_device(mort_ctx* ctx, const void* d_accum, int samples_per_pixe
 /* Host-buffer frame (the reference-facing call): renders, tone-maps and copies back.  rgba8_out: W*H*4 bytes,
  * bottom-up (may be NULL); accum_out: W*H*4 floats (may be NULL). */
 int mort_render(mort_ctx* ctx, const mort_render_opts* opts, uint8_t* rgba8_out, float* accum_out);
+
+/* ---- multi-GPU: shard by samples or tiles, ONE collective per frame -----------------------------
+ * The reference is single-GPU (one renderKernel launch per frame, mort.cu:99-106).  Here every GPU renders its share of
+ * the frame independently into an exact partial frame (opts.exact_accum) and the partial frames are combined once per
+ * frame by one NCCL sum-reduce of 64-bit integers over NVLink; integer sums are associative, so the N-GPU frame equals
+ * the 1-GPU frame bit for bit.  NCCL is bound at run time (dlopen libnccl.so.2); single-GPU use needs no NCCL.
+ *
+ * (a) one PROCESS per GPU: rank 0 obtains a 128-byte id, the launcher hands it to all ranks (a file, MPI, torch.distributed ...),
+ *     every rank attaches its context, renders with sample_mod/sample_rem (or tile_mod/tile_rem) = world/rank and calls
+ *     mort_comm_reduce_exact on the ctx's stream; the root then resolves / tone-maps as usual. */
+int mort_comm_unique_id(void* id128);
+int mort_comm_attach(mort_ctx* ctx, const void* id128, int world, int rank);
+int mort_comm_detach(mort_ctx* ctx);
+int mort_comm_reduce_exact(mort_ctx* ctx, void* d_exact /* W*H x 4 uint64, in place */, int root);
+/* (b) one process drives n GPUs of the box (`mort <scene> --gpus N --split sample|tile`): a context + a host thread per device.
+ *     Build / load / commit the SAME scene on every mort_group_ctx(g, r) with the calls above, then mort_group_render =
+ *     shares rendered concurrently + one grouped ncclReduce to rank 0 + resolve + tone map + copy to the host buffers. */
+typedef struct mort_group mort_group;
+enum { MORT_SPLIT_SAMPLE = 0, MORT_SPLIT_TILE = 1 };
+typedef struct {
+    int32_t n_gpus, split;
+    double kernel_ms_max, kernel_ms_min;   /* render kernels, CUDA events per rank: slowest and fastest rank */
+    double collective_ms;                  /* the ncclReduce on rank 0's stream */
+    uint64_t collective_bytes;             /* partial frame each rank contributes */
+    uint64_t segments, samples;            /* summed over ranks */
+} mort_group_stats;
+int mort_group_create(int n_devices, const int* devices /* NULL: 0..n-1 */, mort_group** out);
+int mort_group_destroy(mort_group* g);
+int mort_group_size(const mort_group* g);
+mort_ctx* mort_group_ctx(mort_group* g, int rank);
+const char* mort_group_last_error(const mort_group* g);
+int mort_group_render(mort_group* g, const mort_render_opts* opts, int split, uint8_t* rgba8_out, float* accum_out);
+int mort_group_get_stats(mort_group* g, mort_group_stats* out);
 
 /* ---- parity hook: closest hit of arbitrary rays (world::hit with the medium loop disabled) -------------- */
 enum { MORT_TRACE_BVH = 0, MORT_TRACE_BRUTE_FORCE = 1 };

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmort_b200.so")
 ASSET_DIR = os.path.join(_HERE, "assets")
 
-MODE_MEGAKERNEL, MODE_WAVEFRONT = 0, 1
+MODE_MEGAKERNEL, MODE_WAVEFRONT, MODE_POOL = 0, 1, 2
 TRACE_BVH, TRACE_BRUTE_FORCE = 0, 1
 
 
@@ -47,7 +47,7 @@ class CameraDesc(C.Structure):
 class RenderOpts(C.Structure):
     _fields_ = [("seed", C.c_uint32), ("frame", C.c_uint32), ("mode", C.c_int32), ("sample_mod", C.c_int32),
                 ("sample_rem", C.c_int32), ("stage_nodes", C.c_int32), ("threads_per_block", C.c_int32),
-                ("blocks_per_sm", C.c_int32), ("wavefront_paths", C.c_int32), ("exact_accum", C.c_int32), ("tile_mod", C.c_int32), ("tile_rem", C.c_int32), ("accumulate", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("blocks_per_sm", C.c_int32), ("wavefront_paths", C.c_int32), ("exact_accum", C.c_int32), ("tile_mod", C.c_int32), ("tile_rem", C.c_int32), ("accumulate", C.c_int32), ("pool_paths", C.c_int32), ("pool_refill", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class Stats(C.Structure):
@@ -64,6 +64,16 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class GroupStats(C.Structure):
+    _fields_ = [("n_gpus", C.c_int32), ("split", C.c_int32), ("kernel_ms_max", C.c_double), ("kernel_ms_min", C.c_double),
+                ("collective_ms", C.c_double), ("collective_bytes", C.c_uint64), ("segments", C.c_uint64), ("samples", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+SPLIT_SAMPLE, SPLIT_TILE = 0, 1
+
 # every symbol include/mort_b200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
     "mort_create", "mort_destroy", "mort_last_error", "mort_set_stream",
@@ -78,6 +88,8 @@ ABI_SYMBOLS = [
     "mort_accumulate_exact_device", "mort_scene_fingerprint", "mort_save_checkpoint", "mort_load_checkpoint",
     "mort_render_progressive", "mort_reset_progressive",
     "mort_trace", "mort_get_stats",
+    "mort_comm_unique_id", "mort_comm_attach", "mort_comm_detach", "mort_comm_reduce_exact",
+    "mort_group_create", "mort_group_destroy", "mort_group_size", "mort_group_ctx", "mort_group_last_error", "mort_group_render", "mort_group_get_stats",
 ]
 
 _lib = None
@@ -117,12 +129,19 @@ def load_library():
         "mort_render_progressive": [P, C.POINTER(RenderOpts), I, C.c_char_p, I, P, P, C.POINTER(C.c_uint32)], "mort_reset_progressive": [P],
         "mort_render": [P, C.POINTER(RenderOpts), P, P], "mort_trace": [P, P, I, P, P, I], "mort_get_stats": [P, C.POINTER(Stats)],
     }
+    sig.update({"mort_comm_unique_id": [P], "mort_comm_attach": [P, P, I, I], "mort_comm_detach": [P], "mort_comm_reduce_exact": [P, P, I],
+                "mort_group_create": [I, C.POINTER(C.c_int), C.POINTER(P)], "mort_group_destroy": [P], "mort_group_size": [P],
+                "mort_group_render": [P, C.POINTER(RenderOpts), I, P, P], "mort_group_get_stats": [P, C.POINTER(GroupStats)]})
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = None if name == "mort_default_render_opts" else C.c_int
     L.mort_last_error.argtypes = [P]
     L.mort_last_error.restype = C.c_char_p
+    L.mort_group_last_error.argtypes = [P]
+    L.mort_group_last_error.restype = C.c_char_p
+    L.mort_group_ctx.argtypes = [P, I]
+    L.mort_group_ctx.restype = P
     _lib = L
     return L
 
@@ -143,8 +162,13 @@ class Frame:
 class Renderer:
     """Owns one mort_ctx on one CUDA device."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed=None):
         self._L = load_library()
+        self._owned = _borrowed is None
+        if _borrowed is not None:                      # a context owned by a Group
+            self._h = C.c_void_p(_borrowed)
+            self.device = device
+            return
         h = C.c_void_p()
         rc = self._L.mort_create(int(device), C.byref(h))
         if rc != 0 or not h:
@@ -159,8 +183,27 @@ class Renderer:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.mort_destroy(self._h)
+            if self._owned:
+                self._L.mort_destroy(self._h)
             self._h = None
+
+    # -- multi-process collective (one process per GPU) --
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        if load_library().mort_comm_unique_id(buf) != 0:
+            raise MortError("mort_comm_unique_id failed (NCCL not loadable?)")
+        return buf.raw
+
+    def comm_attach(self, id128: bytes, world: int, rank: int):
+        self._ck(self._L.mort_comm_attach(self._h, C.c_char_p(id128), int(world), int(rank)))
+
+    def comm_detach(self):
+        self._ck(self._L.mort_comm_detach(self._h))
+
+    def comm_reduce_exact(self, d_exact_ptr: int, root: int = 0):
+        """One NCCL uint64 SUM reduce of the (H, W, 4) exact partial frames to `root`, in place, on the context's stream."""
+        self._ck(self._L.mort_comm_reduce_exact(self._h, C.c_void_p(d_exact_ptr), int(root)))
 
     def __del__(self):
         try:
@@ -344,3 +387,53 @@ class Renderer:
                                     probes.ctypes.data if (nm and want_probes) else None,
                                     TRACE_BRUTE_FORCE if brute_force else TRACE_BVH))
         return out, probes
+
+
+class Group:
+    """One process driving n GPUs of the box (mort_group_*): a Renderer view per rank for scene building, one render call."""
+
+    def __init__(self, n_devices: int, devices=None):
+        self._L = load_library()
+        h = C.c_void_p()
+        arr = (C.c_int * n_devices)(*devices) if devices is not None else None
+        rc = self._L.mort_group_create(int(n_devices), arr, C.byref(h))
+        if rc != 0 or not h:
+            raise MortError(f"mort_group_create({n_devices}) failed with {rc}: needs {n_devices} CUDA devices and NCCL")
+        self._h = h
+        self.n = n_devices
+        self.ranks = [Renderer(devices[i] if devices is not None else i, _borrowed=self._L.mort_group_ctx(h, i)) for i in range(n_devices)]
+
+    def for_each(self, fn):
+        for r in self.ranks:
+            fn(r)
+        return self
+
+    def render(self, split=SPLIT_SAMPLE, want_rgba8=True, want_accum=True, **opts) -> Frame:
+        st = self.ranks[0].stats
+        H, W = st["height"], st["width"]
+        rgba = np.empty((H, W, 4), dtype=np.uint8) if want_rgba8 else None
+        acc = np.empty((H, W, 4), dtype=np.float32) if want_accum else None
+        o = self.ranks[0].opts(**opts)
+        rc = self._L.mort_group_render(self._h, C.byref(o), int(split), rgba.ctypes.data if rgba is not None else None, acc.ctypes.data if acc is not None else None)
+        if rc != 0:
+            raise MortError(f"{self._L.mort_group_last_error(self._h).decode()} (status {rc})")
+        return Frame(acc, rgba, self.stats)
+
+    @property
+    def stats(self) -> dict:
+        s = GroupStats()
+        self._L.mort_group_get_stats(self._h, C.byref(s))
+        return s.asdict()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for r in self.ranks:
+                r.close()
+            self._L.mort_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,66 +20,19 @@
 using namespace mort;
 
 
-namespace {
+#include "ctx.hpp"
 
-struct DeviceArena {                 // every device allocation of one committed scene
-    std::vector<void*> ptrs; size_t bytes = 0;
-    template <class T> cudaError_t upload(const std::vector<T>& v, const T** out) {
-        *out = nullptr;
-        if (v.empty()) return cudaSuccess;
-        void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, v.size() * sizeof(T));
-        if (e != cudaSuccess) return e;
-        ptrs.push_back(p); bytes += v.size() * sizeof(T);
-        e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-        *out = reinterpret_cast<const T*>(p);
-        return e;
-    }
-    void release() { for (void* p : ptrs) cudaFree(p); ptrs.clear(); bytes = 0; }
-};
-
-}  // namespace
-
-struct mort_ctx {
-    int device = 0;
-    cudaDeviceProp prop;
-    Scene scene;
-    HostRng rng;
-    FlatScene flat;
-    bool committed = false;
-    DeviceArena arena;
-    DeviceScene dscene;
-    int32_t* d_mat_offsets = nullptr;
-    unsigned long long* d_counters = nullptr;     // [0] segments [1] samples
-    unsigned int* d_work = nullptr;
-    float4* d_accum = nullptr; size_t accum_pixels = 0;
-    uint8_t* d_rgba = nullptr; size_t rgba_pixels = 0;
-    WavefrontBuffers* wave = nullptr; int wave_paths = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::string err;
-    mort_stats stats;
-    double upload_ms = 0;
-    uint64_t geometry_hash = 0;
-    int stack_fix = 1;
-    unsigned long long* d_prog = nullptr; size_t prog_pixels = 0;   // progressive exact image (mort_render_progressive)
-    uint64_t prog_fingerprint = 0; uint32_t prog_frames = 0, prog_seed = 0;
-};
-
-#define CTX_CHECK(c) do { if (!(c)) return MORT_ERR_ARG; } while (0)
-#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return MORT_ERR_CUDA; } } while (0)
-
-static int fail(mort_ctx* ctx, int code, const std::string& m) { ctx->err = m; return code; }
-static uint64_t fingerprint(const mort_ctx* ctx) {      // committed geometry + current camera (FNV-1a 64)
-    uint64_t h = ctx->geometry_hash;
-    const uint8_t* b = reinterpret_cast<const uint8_t*>(&ctx->flat.cam);
-    for (size_t i = 0; i < sizeof(ctx->flat.cam); i++) { h ^= b[i]; h *= 1099511628211ull; }
-    return h;
-}
 static Handle H(mort_handle h) { return Handle{h.type, h.idx}; }
 static void put(mort_handle* out, Handle h) { if (out) { out->type = h.type; out->idx = h.idx; } }
 static V3 v3(const float* p) { return V3(p[0], p[1], p[2]); }
 static void invalidate(mort_ctx* ctx) { ctx->committed = false; }
+// The tree's boxes are padded for slab-test rounding by 2e-6 * M, M = the largest coordinate in play INCLUDING the camera
+// centre at commit time (flatten.cpp).  A camera moved outside that radius keeps the geometry but needs wider pads: rebuild.
+static bool camera_outgrew_pad(const mort_ctx* ctx) {
+    const Camera& c = ctx->scene.cam;
+    const float m = std::max(std::fabs(c.center.x), std::max(std::fabs(c.center.y), std::fabs(c.center.z)));
+    return m > ctx->flat.stats.scene_extent;
+}
 
 // The reference sets cudaLimitStackSize itself (8192 B, mort.cu:703).  The megakernel's frame is < 1 KB, so the default
 // limit would do — but re-sizing the context's local-memory pool is measurably worth it: inside a process whose CUDA context
@@ -104,10 +58,10 @@ int mort_create(int cuda_device, mort_ctx** out) {
     ctx->device = cuda_device;
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     memset(&ctx->dscene, 0, sizeof(ctx->dscene));
-    if (cudaGetDeviceProperties(&ctx->prop, cuda_device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaGetDeviceProperties(&ctx->prop, cuda_device) != cudaSuccess || cudaStreamCreate(&ctx->own_stream) != cudaSuccess ||     // a BLOCKING stream: ordered after work the host queued on the legacy default stream
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_work, sizeof(unsigned int)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_mat_offsets, 8 * sizeof(int32_t)) != cudaSuccess) {
+        cudaMalloc(&ctx->d_mat_offsets, 8 * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&ctx->d_work64, sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx; return MORT_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
@@ -124,7 +78,7 @@ int mort_destroy(mort_ctx* ctx) {
     cudaDeviceSynchronize();
     ctx->arena.release();
     wavefront_free(ctx->wave);
-    cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_mat_offsets); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgba); cudaFree(ctx->d_prog);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_mat_offsets); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgba); cudaFree(ctx->d_prog); cudaFree(ctx->d_pool_exact); cudaFree(ctx->d_work64);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -219,7 +173,10 @@ int mort_set_camera(mort_ctx* ctx, const mort_camera_desc* d) {
     if (c.light_obj_type != d->light_obj_type || c.light_obj_idx != d->light_obj_idx) invalidate(ctx);
     c.light_obj_type = d->light_obj_type; c.light_obj_idx = d->light_obj_idx;
     c.initialize();
-    if (ctx->committed) camera_params(c, ctx->flat.cam);
+    if (ctx->committed) {
+        if (camera_outgrew_pad(ctx)) return mort_commit(ctx);
+        camera_params(c, ctx->flat.cam);
+    }
     return MORT_OK;
 }
 int mort_override_camera(mort_ctx* ctx, int w, float aspect, int spp, int depth) {
@@ -238,6 +195,7 @@ int mort_get_camera_record(mort_ctx* ctx, mscn_camera* out) { CTX_CHECK(ctx && o
 // ---- commit ---------------------------------------------------------------------------------------------
 int mort_commit(mort_ctx* ctx) {
     CTX_CHECK(ctx);
+    invalidate(ctx);                                      // a failed re-commit must not leave a "committed" context over freed memory
     CU(cudaSetDevice(ctx->device));
     std::string e;
     if (!flatten_scene(ctx->scene, ctx->flat, &e)) return fail(ctx, MORT_ERR_SCENE, e);
@@ -248,7 +206,9 @@ int mort_commit(mort_ctx* ctx) {
         return fail(ctx, MORT_ERR_SCENE, "more than 2^27 primitives of one kind are not addressable by a leaf word");
     auto t0 = std::chrono::steady_clock::now();
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stream != ctx->own_stream) CU(cudaStreamSynchronize(ctx->own_stream));
     ctx->arena.release();
+    memset(&ctx->dscene, 0, sizeof(ctx->dscene));
     DeviceScene d; memset(&d, 0, sizeof(d));
     const FlatScene& f = ctx->flat;
     CU(ctx->arena.upload(f.nodes, &d.nodes)); d.n_nodes = (int)f.nodes.size();
@@ -292,7 +252,7 @@ int mort_commit(mort_ctx* ctx) {
 void mort_default_render_opts(mort_render_opts* o) {
     if (!o) return;
     memset(o, 0, sizeof(*o));
-    o->seed = 69420; o->frame = 0; o->mode = MORT_MODE_MEGAKERNEL; o->sample_mod = 1; o->sample_rem = 0; o->stage_nodes = -1;
+    o->seed = 69420; o->frame = 0; o->mode = MORT_MODE_MEGAKERNEL; o->sample_mod = 1; o->sample_rem = 0; o->stage_nodes = 0;
 }
 
 static int ensure_accum(mort_ctx* ctx, size_t npix) {
@@ -322,7 +282,7 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     p.tile_mod = o.tile_mod > 1 ? o.tile_mod : 1; p.tile_rem = o.tile_mod > 1 ? o.tile_rem : 0;
     if (p.tile_mod > 1) {
         if (o.tile_rem < 0 || o.tile_rem >= o.tile_mod) return fail(ctx, MORT_ERR_ARG, "mort_render: bad tile split");
-        if (o.mode != MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render: tile split is a megakernel feature");
+        if (o.mode == MORT_MODE_WAVEFRONT) return fail(ctx, MORT_ERR_ARG, "mort_render: tile split needs the megakernel or the block wavefront");
         int n = 0;                                           // pixels in this rank's 8-row bands
         for (int b = p.tile_rem; b * 8 < cam.height; b += p.tile_mod) n += std::min(8, cam.height - b * 8) * cam.width;
         p.n_pixels = n;
@@ -336,7 +296,7 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     // guided tail: tasks shrink to >= 256 samples (8 per lane) in the last round of the frame
     p.min_task_px = p.n_subset > 0 ? std::max(1, std::min(PT, (256 + p.n_subset - 1) / p.n_subset)) : PT;
     if (const char* e = getenv("MORT_TAIL")) { if (atoi(e) == 0) p.min_task_px = PT; }                    // experiments only
-    if (o.exact_accum && o.mode != MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render: exact_accum is a megakernel feature");
+    if (o.exact_accum && o.mode == MORT_MODE_WAVEFRONT) return fail(ctx, MORT_ERR_ARG, "mort_render: exact_accum needs the megakernel or the block wavefront");
     if (o.accumulate && !o.exact_accum) return fail(ctx, MORT_ERR_ARG, "mort_render: accumulate needs exact_accum (float sums are not order-independent)");
     p.accumulate = o.accumulate ? 1 : 0;
     p.accum = o.exact_accum ? nullptr : reinterpret_cast<float4*>(d_accum);
@@ -345,12 +305,13 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
 
     const int threads = o.threads_per_block > 0 ? (o.threads_per_block + 31) / 32 * 32 : 128;
     if (threads > 128) return fail(ctx, MORT_ERR_ARG, "mort_render: at most 128 threads per block");
-    // staging: auto = every node if the whole tree fits in 96 KB per block, else none (decided by the ncu
-    // comparison in profiles/)
+    // staging is opt-in (stage_nodes > 0): measured slower than L1-resident LDG.128 nodes (profiles/r01: scene 8 154 vs 276
+    // Msamples/s), so <= 0 means none.  The megakernel keeps 6 KB of static shared memory of its own.
     int n_staged = o.stage_nodes;
-    const int max_stage = (int)((ctx->prop.sharedMemPerBlockOptin > 2048 ? ctx->prop.sharedMemPerBlockOptin - 2048 : 0) / sizeof(Bvh4Node));
-    if (n_staged < 0 || ctx->flat.linear) n_staged = 0;     // nothing to stage for a linear-scan scene
-    n_staged = std::min(n_staged, std::min(max_stage, (int)ctx->flat.nodes.size()));
+    const int max_stage = (int)((ctx->prop.sharedMemPerBlockOptin > 6144 ? ctx->prop.sharedMemPerBlockOptin - 6144 : 0) / sizeof(Bvh4Node));
+    if (n_staged < 0 || ctx->flat.linear || o.mode != MORT_MODE_MEGAKERNEL) n_staged = 0;     // nothing to stage for a linear-scan scene
+    if (n_staged > max_stage) return fail(ctx, MORT_ERR_ARG, "mort_render: stage_nodes exceeds the shared memory of a block (" + std::to_string(max_stage) + " nodes at most)");
+    n_staged = std::min(n_staged, (int)ctx->flat.nodes.size());
     p.n_staged = n_staged;
 
     if (ctx->stack_fix == 2) { raise_stack_limit(); ctx->stack_fix = 0; }
@@ -370,6 +331,35 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         CU(mega_launch(p, sh, min_blocks, ctx->stream));
         launches = 1;
         ctx->stats.threads_per_block = threads; ctx->stats.blocks_per_sm = bps; ctx->stats.regs_per_thread = regs; ctx->stats.staged_nodes = n_staged;
+    } else if (o.mode == MORT_MODE_POOL) {
+        // block wavefront (pool.cu): samples are added into an exact frame with integer reductions; a float4 request
+        // goes through a context-owned exact frame and one resolve pass
+        const size_t npix_full = (size_t)cam.width * cam.height;
+        unsigned long long* target = reinterpret_cast<unsigned long long*>(d_accum);
+        if (!o.exact_accum) {
+            if (ctx->pool_exact_pixels < npix_full) {
+                cudaFree(ctx->d_pool_exact); ctx->d_pool_exact = nullptr; ctx->pool_exact_pixels = 0;
+                CU(cudaMalloc(&ctx->d_pool_exact, npix_full * 4 * sizeof(unsigned long long))); ctx->pool_exact_pixels = npix_full;
+            }
+            target = ctx->d_pool_exact;
+        }
+        p.accum = nullptr; p.accum_exact = target;
+        p.work64 = ctx->d_work64; p.total_samples = (unsigned long long)p.n_pixels * (unsigned long long)p.n_subset;
+        PoolShape ps; ps.threads = o.threads_per_block > 0 ? o.threads_per_block : 512; ps.min_blocks = o.blocks_per_sm > 0 ? o.blocks_per_sm : 2;
+        ps.pool_paths = o.pool_paths > 0 ? o.pool_paths : 1024;
+        if (ps.pool_paths < 32 || ps.pool_paths > 65504) return fail(ctx, MORT_ERR_ARG, "mort_render: pool_paths must be in [32, 65504]");
+        ps.pool_paths = (ps.pool_paths + 31) / 32 * 32;
+        p.pool_paths = ps.pool_paths; p.pool_refill = o.pool_refill;
+        int occ = 0, regs = 0, smem = 0;
+        CU(pool_query(ps, &occ, &regs, &smem));
+        if (occ < 1) return fail(ctx, MORT_ERR_ARG, "mort_render: a pool of " + std::to_string(ps.pool_paths) + " paths (" + std::to_string(smem) + " B) does not fit in a block's shared memory");
+        const int bps = std::min(occ, ps.min_blocks);
+        CU(cudaMemsetAsync(ctx->d_work64, 0, sizeof(unsigned long long), ctx->stream));
+        if (!o.accumulate || !o.exact_accum) CU(zero_exact_launch(target, p.n_pixels, cam.width, p.tile_mod, p.tile_rem, ctx->stream));
+        CU(pool_launch(p, ps, bps * ctx->prop.multiProcessorCount, ctx->stream));
+        launches = 2;
+        if (!o.exact_accum) { CU(resolve_exact_tiles_launch(target, p.n_pixels, cam.width, p.tile_mod, p.tile_rem, reinterpret_cast<float4*>(d_accum), ctx->stream)); launches = 3; }
+        ctx->stats.threads_per_block = ps.threads; ctx->stats.blocks_per_sm = bps; ctx->stats.regs_per_thread = regs; ctx->stats.staged_nodes = 0;
     } else if (o.mode == MORT_MODE_WAVEFRONT) {
         int n_paths = std::max(o.wavefront_paths > 0 ? o.wavefront_paths : 1 << 21, p.n_pixels);   // at least one slot per pixel
         if (!ctx->wave || ctx->wave_paths != n_paths) {
@@ -550,11 +540,17 @@ int mort_render(mort_ctx* ctx, const mort_render_opts* opts, uint8_t* rgba8_out,
     int rc = ensure_accum(ctx, npix);
     if (rc != MORT_OK) return rc;
     mort_render_opts oh; if (opts) oh = *opts; else mort_default_render_opts(&oh);
-    oh.exact_accum = 0;                                  // the host-buffer call returns the float4 image
+    oh.exact_accum = 0; oh.accumulate = 0;               // the host-buffer call returns the float4 image
+    // A host-buffer frame is a whole frame: a tile split would return the other ranks' bands uninitialised (partial frames
+    // are combined on the device: mort_render_device + mort_group_* / the caller's collective).  A sample split is
+    // allowed; its 8-bit frame is the mean over the samples this call rendered.
+    if (oh.tile_mod > 1) return fail(ctx, MORT_ERR_ARG, "mort_render: a tile split has no host-buffer form (use mort_render_device or mort_group_render)");
     rc = mort_render_device(ctx, &oh, ctx->d_accum);
     if (rc != MORT_OK) return rc;
     if (rgba8_out) {
-        rc = mort_tonemap_device(ctx, ctx->d_accum, cam.sqrt_spp * cam.sqrt_spp, ctx->d_rgba);
+        const int sm = oh.sample_mod > 1 ? oh.sample_mod : 1;
+        const int rows = cam.sqrt_spp > oh.sample_rem ? (cam.sqrt_spp - oh.sample_rem + sm - 1) / sm : 0;
+        rc = mort_tonemap_device(ctx, ctx->d_accum, std::max(1, rows * cam.sqrt_spp), ctx->d_rgba);
         if (rc != MORT_OK) return rc;
         CU(cudaMemcpyAsync(rgba8_out, ctx->d_rgba, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -13,15 +13,16 @@
 #include "mort_b200.h"
 
 static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
-                            "            [--mode mega|wave] [--stage N] [--bps blocks/SM] [--tpb threads] [--field G [--fieldcam 0|1]]\n"
+                            "            [--mode mega|wave|pool] [--stage N] [--bps blocks/SM] [--tpb threads] [--pool paths/block] [--field G [--fieldcam 0|1]]\n"
                             "            [--assets DIR] [--out image.ppm] [--hdr image.pfm] [--device K] [--load scene.mscn] [--dump scene.mscn]\n"
                             "            [--scene-file scene.txt] [--dump-text scene.txt]\n"
-                            "            [--accumulate [--checkpoint FILE [--resume]]]\n"); return -1; }
+                            "            [--accumulate [--checkpoint FILE [--resume]]]\n"
+                            "            [--gpus N [--split sample|tile]]   N GPUs of this box, one NCCL reduce of the partial frames per frame\n"); return -1; }
 
 int main(int argc, char** argv) {
     if (argc < 2) return usage();                       // mort.cu:638-641
     int scene = atoi(argv[1]);
-    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = -1, mode = MORT_MODE_MEGAKERNEL, bps = 0, tpb = 0, field = 0, fieldcam = 0;
+    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = 0, mode = MORT_MODE_MEGAKERNEL, bps = 0, tpb = 0, field = 0, fieldcam = 0, pool = 0, refill = 0, gpus = 1, split = MORT_SPLIT_SAMPLE;
     float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr, load, dump, ckpt, text_in, text_out;
     bool accumulate = false, resume = false;
     for (int i = 2; i < argc; i++) {
@@ -37,8 +38,50 @@ int main(int argc, char** argv) {
         else if (a == "--accumulate") accumulate = true; else if (a == "--checkpoint") ckpt = nx(); else if (a == "--resume") resume = true;
         else if (a == "--bps") bps = atoi(nx()); else if (a == "--tpb") tpb = atoi(nx());
         else if (a == "--field") field = atoi(nx()); else if (a == "--fieldcam") fieldcam = atoi(nx());
-        else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : MORT_MODE_MEGAKERNEL; }
+        else if (a == "--gpus") gpus = atoi(nx()); else if (a == "--split") { std::string m = nx(); split = m == "tile" ? MORT_SPLIT_TILE : MORT_SPLIT_SAMPLE; }
+        else if (a == "--pool") pool = atoi(nx()); else if (a == "--refill") refill = atoi(nx());
+        else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : m == "pool" ? MORT_MODE_POOL : MORT_MODE_MEGAKERNEL; }
         else return usage();
+    }
+    if (gpus > 1) {
+        // one process, N GPUs: the same scene is built and committed on every rank's context; each frame is one
+        // mort_group_render = shares rendered concurrently + one NCCL reduce + tone map on rank 0
+        if (accumulate || !dump.empty() || !text_out.empty()) { fprintf(stderr, "mort: --gpus does not combine with --accumulate / --dump / --dump-text\n"); return -1; }
+        mort_group* g = nullptr;
+        if (mort_group_create(gpus, nullptr, &g) != MORT_OK) { fprintf(stderr, "mort: cannot drive %d CUDA devices (NCCL and %d GPUs are required)\n", gpus, gpus); return 2; }
+        for (int r = 0; r < gpus; r++) {
+            mort_ctx* c = mort_group_ctx(g, r);
+            int rc = !text_in.empty() ? mort_load_scene_text(c, text_in.c_str(), assets.c_str()) : !load.empty() ? mort_load_scene(c, load.c_str(), assets.c_str())
+                     : field > 0 ? mort_build_sphere_field(c, field, 69420, fieldcam) : mort_build_scene(c, scene, assets.c_str());
+            if (rc == MORT_OK) rc = mort_override_camera(c, width, aspect, spp, depth);
+            if (rc == MORT_OK) rc = mort_commit(c);
+            if (rc != MORT_OK) { fprintf(stderr, "mort: rank %d: %s\n", r, mort_last_error(c)); mort_group_destroy(g); return 3; }
+        }
+        mort_stats st; mort_get_stats(mort_group_ctx(g, 0), &st);
+        std::vector<uint8_t> img((size_t)st.width * st.height * 4);
+        mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.blocks_per_sm = bps; o.threads_per_block = tpb; o.pool_paths = pool; o.pool_refill = refill;
+        double total = 0, coll = 0, kmin = 0; mort_group_stats gs; memset(&gs, 0, sizeof(gs));
+        for (int f = 0; f < frames; f++) {
+            o.frame = (uint32_t)f;
+            if (mort_group_render(g, &o, split, img.data(), nullptr) != MORT_OK) { fprintf(stderr, "mort: render: %s\n", mort_group_last_error(g)); mort_group_destroy(g); return 3; }
+            mort_group_get_stats(g, &gs);
+            total += gs.kernel_ms_max + gs.collective_ms; coll += gs.collective_ms; kmin += gs.kernel_ms_min;
+            printf("Avg. time per frame: %3.1f ms\n", total / (f + 1));
+        }
+        const double ms = gs.kernel_ms_max + gs.collective_ms;
+        printf("{\"scene\":%d,\"n_gpus\":%d,\"split\":\"%s\",\"width\":%d,\"height\":%d,\"spp_eff\":%d,\"depth\":%d,\"ms\":%.3f,\"kernel_ms_max\":%.3f,\"kernel_ms_min\":%.3f,"
+               "\"collective_ms\":%.3f,\"collective_mb\":%.1f,\"msamples_per_s\":%.3f,\"mrays_per_s\":%.3f}\n",
+               scene, gpus, split == MORT_SPLIT_TILE ? "tile" : "sample", st.width, st.height, st.sqrt_spp * st.sqrt_spp, st.bounce_limit, ms, gs.kernel_ms_max, gs.kernel_ms_min,
+               gs.collective_ms, gs.collective_bytes / 1048576.0, (double)gs.samples / (ms * 1e3), (double)gs.segments / (ms * 1e3));
+        if (!out.empty()) {
+            FILE* f = fopen(out.c_str(), "wb");
+            if (!f) { perror(out.c_str()); mort_group_destroy(g); return 4; }
+            fprintf(f, "P6\n%d %d\n255\n", st.width, st.height);
+            for (int y = st.height - 1; y >= 0; y--) for (int x = 0; x < st.width; x++) fwrite(&img[4 * ((size_t)y * st.width + x)], 1, 3, f);
+            fclose(f);
+        }
+        mort_group_destroy(g);
+        return 0;
     }
     mort_ctx* ctx = nullptr;
     if (mort_create(device, &ctx) != MORT_OK) { fprintf(stderr, "mort: no usable CUDA device %d (this renderer has no CPU path)\n", device); return 2; }
@@ -54,7 +97,7 @@ int main(int argc, char** argv) {
     mort_stats st; mort_get_stats(ctx, &st);
     std::vector<uint8_t> img((size_t)st.width * st.height * 4);
     std::vector<float> acc(hdr.empty() ? 0 : (size_t)st.width * st.height * 4);
-    mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.stage_nodes = stage; o.blocks_per_sm = bps; o.threads_per_block = tpb;
+    mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.stage_nodes = stage; o.blocks_per_sm = bps; o.threads_per_block = tpb; o.pool_paths = pool; o.pool_refill = refill;
     double total = 0;
     uint32_t frames_total = 1;                         // frames averaged into the written image
     if (accumulate) {

@@ -1,0 +1,309 @@
+// pool.cu — the "block wavefront": ONE persistent kernel in which every thread block runs a wavefront over a pool of
+// paths that lives in its shared memory (B200: 227 KB per SM).
+//
+// Why (profiles/r01_scene8_fetch_bound.md, r01_source_level.md): in the warp-task megakernel (render.cu) a lane carries its
+// whole path through traversal AND shading, so (1) the warps of an SM sit in every stage of the integrator at once and
+// the ~100 KB of SASS they walk through thrash the 32 KB instruction cache (scene 8: 10.6 fetch stalls per issued
+// instruction), (2) the traversal registers and the shading registers are live together (64-register cap -> 15.6 GB of
+// spill write-back per launch), and (3) a warp's 32 lanes shade 32 unrelated materials (10 of 32 lanes live in shading).
+// Here the path state (19 words per path: ray, throughput, depth, Philox counters, hit) is an SoA pool in shared memory and
+// the block alternates between two phases separated by __syncthreads():
+//   TRACE   warps pull 32-path chunks of the live list from a shared counter: closest hit + media (rt_core.cuh), the hit
+//           goes back to the pool and the path's slot is appended to its material-class list (ballot / popc aggregation)
+//   SHADE   warps pull 32-slot chunks of ONE class (terminal / diffuse / metal / dielectric): record, texture, ONB, pdf
+//           and light sampling for 32 hits of the same kind; a finished sample is added to the exact frame with
+//           64-bit integer reductions (accum.cuh: order-independent, so the frame equals the megakernel's bit for bit) and the
+//           lane at once claims the next camera sample of the frame from a global counter and regenerates in place
+// so all warps of a block execute the same few KB of code at the same time, each phase only keeps its own state in
+// registers, and shading is coherent by construction.  No state ever goes to HBM: the only global traffic is the scene,
+// the sample counter and the reductions into the frame.
+//
+// Same per-ray code, Philox stream and arithmetic as the megakernel: the two schedulers render bit-identical exact frames
+// (tests/test_gpu_pool.py).
+#include <cuda_runtime.h>
+
+#include "accum.cuh"
+#include "render.hpp"
+#include "rt_core.cuh"
+
+namespace mort {
+
+namespace {
+
+constexpr int kPoolWords = 19;                 // 32-bit words of state per path
+constexpr int kPoolLists = 6;                  // 16-bit slot lists per path: 2 live lists (ping-pong) + 4 class lists
+
+// The pool is addressed as word k of path s = smem[k * np + s] straight off the extern array, so that every access
+// compiles to LDS / STS (pointers kept in a struct decayed to generic LD / ST).
+extern __shared__ __align__(16) unsigned char pool_raw[];
+enum { W_OX = 0, W_OY, W_OZ, W_DX, W_DY, W_DZ, W_TM,        // ray
+       W_TX, W_TY, W_TZ, W_DEPTH,                          // throughput, bounces so far
+       W_PIX, W_SMP, W_BLK, W_STAGE,                       // Philox counter words: pixel, sample, next block, this bounce's stage block
+       W_HT, W_HPRIM, W_HA, W_HB };                        // hit
+static_assert(W_HB + 1 == kPoolWords, "pool layout");
+enum { L_LIVE0 = 0, L_LIVE1 = 1, L_CLS0 = 2 };             // 16-bit slot lists: 2 live lists (ping-pong) + 4 class lists
+struct Pool {
+    int np;
+    __device__ __forceinline__ float& f(int k, unsigned s) const { return reinterpret_cast<float*>(pool_raw)[k * np + (int)s]; }
+    __device__ __forceinline__ uint32_t& u(int k, unsigned s) const { return reinterpret_cast<uint32_t*>(pool_raw)[k * np + (int)s]; }
+    __device__ __forceinline__ uint16_t* list(int l) const { return reinterpret_cast<uint16_t*>(pool_raw) + (2 * kPoolWords + l) * np; }
+};
+
+struct PoolCtl {
+    unsigned t_n[2], t_head[2];                // live list: entries, chunk head
+    unsigned c_n[2][4], c_head[2];             // class lists: entries, chunk head
+};
+
+// warp-aggregated append to a shared-memory list (every lane of the warp must call it)
+__device__ __forceinline__ void list_push(uint16_t* list, unsigned* count, bool pred, unsigned value) {
+    const unsigned full = 0xffffffffu;
+    const unsigned m = __ballot_sync(full, pred);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(full, base, leader);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)value;
+}
+
+// A finished sample goes straight into the exact frame.  Black samples (most of them in the scenes with a black
+// background) add nothing and cost nothing.
+__device__ __forceinline__ void add_sample(const FrameParams& P, uint32_t pixel, f3 col) {
+    unsigned long long* dst = P.accum_exact + (size_t)pixel * 4;
+    if (isnan3(col)) { atomicAdd(dst + 3, 1ull); return; }
+    long long dr = 0, dg = 0, db = 0; unsigned long long fl = 0ull;
+    fx_add(dr, fl, col.x, 20); fx_add(dg, fl, col.y, 34); fx_add(db, fl, col.z, 48);
+    if (dr) atomicAdd(dst, (unsigned long long)dr);
+    if (dg) atomicAdd(dst + 1, (unsigned long long)dg);
+    if (db) atomicAdd(dst + 2, (unsigned long long)db);
+    if (fl) atomicAdd(dst + 3, fl);
+}
+
+struct Lane { Path path; Rng g; };
+
+// Brings a lane to a path whose next segment must be traced: a path that reached the bounce limit or whose ray went NaN is
+// finished here (camera.cuh:161-163; render.cu's path_segment does the same checks before its closest-hit query), and a
+// lane without a path claims the frame's next camera sample.  Warp-convergent (ballots inside).  Returns "lane holds a live path".
+__device__ __forceinline__ bool settle(const FrameParams& P, Lane& L, bool check, bool need_new, unsigned& n_smp) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    bool live = false;
+    for (;;) {
+        if (check) {
+            f3 col;
+            if (path_exhausted(P.cam, L.path, col)) { add_sample(P, L.g.pixel, col); need_new = true; }
+            else if (ray_is_nan(L.path.ray)) { add_sample(P, L.g.pixel, mk3(NAN, NAN, NAN)); need_new = true; }
+            else live = true;
+            check = false;
+        }
+        const unsigned m = __ballot_sync(full, need_new);
+        if (m == 0u) break;
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0ull;
+        if (lane == leader) base = atomicAdd(P.work64, (unsigned long long)__popc(m));
+        base = __shfl_sync(full, base, leader);
+        if (need_new) {
+            need_new = false;
+            const unsigned long long gidx = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+            if (gidx < P.total_samples) {
+                const unsigned long long pl = gidx / (unsigned long long)P.n_subset;
+                const int k = (int)(gidx - pl * (unsigned long long)P.n_subset);
+                const int row = k / P.cam.sqrt_spp;
+                const int pixel = tile_to_global((int)pl, 8 * P.cam.width, P.tile_mod, P.tile_rem);
+                path_start(P.cam, P.seed, P.frame, pixel, k - row * P.cam.sqrt_spp, P.sj_rem + row * P.sj_mod, L.path, L.g);
+                n_smp++;
+                check = true;
+            }
+        }
+    }
+    return live;
+}
+
+__device__ __forceinline__ void store_path(const Pool& S, unsigned s, const Lane& L) {
+    S.f(W_OX, s) = L.path.ray.o.x; S.f(W_OY, s) = L.path.ray.o.y; S.f(W_OZ, s) = L.path.ray.o.z;
+    S.f(W_DX, s) = L.path.ray.d.x; S.f(W_DY, s) = L.path.ray.d.y; S.f(W_DZ, s) = L.path.ray.d.z; S.f(W_TM, s) = L.path.ray.tm;
+    S.f(W_TX, s) = L.path.thr.x; S.f(W_TY, s) = L.path.thr.y; S.f(W_TZ, s) = L.path.thr.z; S.u(W_DEPTH, s) = (uint32_t)L.path.depth;
+    S.u(W_PIX, s) = L.g.pixel; S.u(W_SMP, s) = L.g.sample; S.u(W_BLK, s) = L.g.block;
+}
+__device__ __forceinline__ void load_ray(const Pool& S, unsigned s, Ray& r) {
+    r.o = mk3(S.f(W_OX, s), S.f(W_OY, s), S.f(W_OZ, s)); r.d = mk3(S.f(W_DX, s), S.f(W_DY, s), S.f(W_DZ, s)); r.tm = S.f(W_TM, s);
+}
+
+// one 32-slot chunk of one material class
+template <int kClass>
+__device__ __forceinline__ void shade_chunk(const FrameParams& P, const Pool& S, PoolCtl& ctl, int nxt, bool valid, unsigned slot, unsigned& n_smp) {
+    Lane L;
+    bool done = false;
+    if (valid) {
+        load_ray(S, slot, L.path.ray);
+        L.path.thr = mk3(S.f(W_TX, slot), S.f(W_TY, slot), S.f(W_TZ, slot)); L.path.depth = (int)S.u(W_DEPTH, slot);
+        L.g.k0 = P.seed; L.g.k1 = P.frame; L.g.pixel = S.u(W_PIX, slot); L.g.sample = S.u(W_SMP, slot); L.g.block = S.u(W_BLK, slot);
+        SegHit sh; sh.h.t = S.f(W_HT, slot); sh.h.prim = S.u(W_HPRIM, slot); sh.h.a = S.f(W_HA, slot); sh.h.b = S.f(W_HB, slot);
+        R4 sb = {0.f, 0.f, 0.f, 0.f};
+        if (kClass == CLASS_DIFFUSE || kClass == CLASS_DIELECTRIC) {            // the bounce's stage block, reserved by the trace phase
+            Rng sg = L.g; sg.block = S.u(W_STAGE, slot);
+            sb = rng_block(sg);
+        }
+        f3 color = mk3(0, 0, 0);
+        const int st = segment_shade<kClass>(P.sc, P.cam, sh, L.path, L.g, sb, color);
+        if (st == SEG_DONE) { add_sample(P, L.g.pixel, color); done = true; }
+    } else {
+        L.path.ray.o = L.path.ray.d = L.path.thr = mk3(0, 0, 0); L.path.ray.tm = 0.f; L.path.depth = 0;
+        rng_init(L.g, P.seed, P.frame, 0, 0);
+    }
+    const bool live = settle(P, L, valid && !done, valid && done, n_smp);
+    if (live) store_path(S, slot, L);
+    list_push(S.list(L_LIVE0 + nxt), &ctl.t_n[nxt], live, slot);
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pool_kernel(const __grid_constant__ FrameParams P) {
+    __shared__ PoolCtl ctl;
+    const int NP = P.pool_paths;
+    Pool S; S.np = NP;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned n_seg = 0, n_smp = 0;
+
+    if (threadIdx.x < (int)(sizeof(PoolCtl) / 4)) reinterpret_cast<unsigned*>(&ctl)[threadIdx.x] = 0u;
+    __syncthreads();
+    // initial fill: every slot is free and claims a camera sample
+    for (int s0 = 0; s0 < NP; s0 += NT) {
+        const int s = s0 + (int)threadIdx.x;
+        Lane L;
+        L.path.ray.o = L.path.ray.d = L.path.thr = mk3(0, 0, 0); L.path.ray.tm = 0.f; L.path.depth = 0;
+        rng_init(L.g, P.seed, P.frame, 0, 0);
+        const bool live = settle(P, L, false, s < NP, n_smp);
+        if (live) store_path(S, (unsigned)s, L);
+        list_push(S.list(L_LIVE0), &ctl.t_n[0], live, (unsigned)s);
+    }
+    __syncthreads();
+
+    for (int round = 0;; round++) {
+        const int par = round & 1, nxt = par ^ 1;
+        // the other parity's counters are idle during this trace phase (last read in the previous round, next written
+        // in this round's shade phase / the next round's trace phase): reset them here
+        if (threadIdx.x == 0) {
+            ctl.t_n[nxt] = 0u; ctl.t_head[nxt] = 0u; ctl.c_head[nxt] = 0u;
+            ctl.c_n[nxt][0] = 0u; ctl.c_n[nxt][1] = 0u; ctl.c_n[nxt][2] = 0u; ctl.c_n[nxt][3] = 0u;
+        }
+        const unsigned nt = ctl.t_n[par];
+        if (nt == 0u) break;                                    // block-uniform: no live path and no sample left to claim
+
+        // ---------------- TRACE: closest hit + media for every live path, then the material-class split ----------------
+        for (;;) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&ctl.t_head[par], 32u);
+            base = __shfl_sync(full, base, 0);
+            if (base >= nt) break;
+            const unsigned i = base + (unsigned)lane;
+            const bool valid = i < nt;
+            int cls = -1; unsigned slot = 0;
+            if (valid) {
+                slot = S.list(L_LIVE0 + par)[i];
+                Ray r; load_ray(S, slot, r);
+                Rng g; g.k0 = P.seed; g.k1 = P.frame; g.pixel = S.u(W_PIX, slot); g.sample = S.u(W_SMP, slot); g.block = S.u(W_BLK, slot);
+                const uint32_t stage = g.block; g.block++;        // canonical stream: the stage block precedes the segment's media draws
+                SegHit sh;
+                segment_trace<false>(P.sc, nullptr, 0, r, g, sh);
+                n_seg++;
+                S.u(W_BLK, slot) = g.block; S.u(W_STAGE, slot) = stage;
+                S.f(W_HT, slot) = sh.h.t; S.u(W_HPRIM, slot) = sh.h.prim; S.f(W_HA, slot) = sh.h.a; S.f(W_HB, slot) = sh.h.b;
+                cls = material_class(P.sc, seghit_material(P.sc, sh));
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) list_push(S.list(L_CLS0 + c), &ctl.c_n[par][c], cls == c, slot);
+        }
+        __syncthreads();
+
+        // ---------------- SHADE: one material class per 32-slot chunk; finished lanes regenerate in place ----------------
+        const unsigned cn0 = ctl.c_n[par][0], cn1 = ctl.c_n[par][1], cn2 = ctl.c_n[par][2], cn3 = ctl.c_n[par][3];
+        // heavy classes first so the phase's tail is made of cheap chunks
+        const unsigned k1 = (cn1 + 31u) >> 5, k3 = k1 + ((cn3 + 31u) >> 5), k2 = k3 + ((cn2 + 31u) >> 5), k0 = k2 + ((cn0 + 31u) >> 5);
+        for (;;) {
+            unsigned j = 0;
+            if (lane == 0) j = atomicAdd(&ctl.c_head[par], 1u);
+            j = __shfl_sync(full, j, 0);
+            if (j >= k0) break;
+            if (j < k1) {
+                const unsigned off = j * 32u + (unsigned)lane; const bool v = off < cn1;
+                shade_chunk<CLASS_DIFFUSE>(P, S, ctl, nxt, v, v ? S.list(L_CLS0 + CLASS_DIFFUSE)[off] : 0u, n_smp);
+            } else if (j < k3) {
+                const unsigned off = (j - k1) * 32u + (unsigned)lane; const bool v = off < cn3;
+                shade_chunk<CLASS_DIELECTRIC>(P, S, ctl, nxt, v, v ? S.list(L_CLS0 + CLASS_DIELECTRIC)[off] : 0u, n_smp);
+            } else if (j < k2) {
+                const unsigned off = (j - k3) * 32u + (unsigned)lane; const bool v = off < cn2;
+                shade_chunk<CLASS_METAL>(P, S, ctl, nxt, v, v ? S.list(L_CLS0 + CLASS_METAL)[off] : 0u, n_smp);
+            } else {
+                const unsigned off = (j - k2) * 32u + (unsigned)lane; const bool v = off < cn0;
+                shade_chunk<CLASS_TERMINAL>(P, S, ctl, nxt, v, v ? S.list(L_CLS0 + CLASS_TERMINAL)[off] : 0u, n_smp);
+            }
+        }
+        __syncthreads();
+    }
+    for (int off = 16; off > 0; off >>= 1) { n_seg += __shfl_xor_sync(full, n_seg, off); n_smp += __shfl_xor_sync(full, n_smp, off); }
+    if (lane == 0) { atomicAdd(P.counters, (unsigned long long)n_seg); atomicAdd(P.counters + 1, (unsigned long long)n_smp); }
+}
+
+typedef void (*PoolFn)(const FrameParams);
+PoolFn pool_variant(const PoolShape& s) {
+    if (s.threads >= 1024) return (PoolFn)pool_kernel<1024, 1>;
+    if (s.threads >= 512) return s.min_blocks >= 2 ? (PoolFn)pool_kernel<512, 2> : (PoolFn)pool_kernel<512, 1>;
+    if (s.threads >= 384) return (PoolFn)pool_kernel<384, 2>;
+    return s.min_blocks >= 3 ? (PoolFn)pool_kernel<256, 3> : (PoolFn)pool_kernel<256, 2>;
+}
+int pool_threads(const PoolShape& s) { return s.threads >= 1024 ? 1024 : s.threads >= 512 ? 512 : s.threads >= 384 ? 384 : 256; }
+
+}  // namespace
+
+cudaError_t pool_query(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes) {
+    PoolFn fn = pool_variant(want);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, (const void*)fn);
+    if (e != cudaSuccess) return e;
+    if (regs) *regs = fa.numRegs;
+    const int smem = want.pool_paths * (kPoolWords * 4 + kPoolLists * 2);
+    if (smem_bytes) *smem_bytes = smem;
+    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void*)fn, pool_threads(want), (size_t)smem);
+}
+
+cudaError_t pool_launch(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st) {
+    PoolFn fn = pool_variant(shape);
+    const int smem = shape.pool_paths * (kPoolWords * 4 + kPoolLists * 2);
+    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    void* args[] = {(void*)&p};
+    return cudaLaunchKernel((const void*)fn, dim3(blocks), dim3(pool_threads(shape)), args, (size_t)smem, st);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// zero / resolve the exact frame over the pixels one call renders (all of them, or a rank's 8-row bands)
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) zero_exact_kernel(ulonglong2* __restrict__ ex, int n_local, int band_px, int mod, int rem) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    const size_t g = (size_t)tile_to_global(i, band_px, mod, rem);
+    ex[2 * g] = make_ulonglong2(0ull, 0ull); ex[2 * g + 1] = make_ulonglong2(0ull, 0ull);
+}
+__global__ void __launch_bounds__(256) resolve_exact_tiles_kernel(const ulonglong2* __restrict__ ex, int n_local, int band_px, int mod, int rem, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    const size_t g = (size_t)tile_to_global(i, band_px, mod, rem);
+    const ulonglong2 a = ex[2 * g], b = ex[2 * g + 1];
+    out[g] = fx_resolve((long long)a.x, (long long)a.y, (long long)b.x, b.y);
+}
+cudaError_t zero_exact_launch(unsigned long long* d_exact, int n_local, int width, int tile_mod, int tile_rem, cudaStream_t st) {
+    if (n_local <= 0) return cudaSuccess;
+    if (tile_mod <= 1) return cudaMemsetAsync(d_exact, 0, (size_t)n_local * 32, st);
+    zero_exact_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(reinterpret_cast<ulonglong2*>(d_exact), n_local, 8 * width, tile_mod, tile_rem);
+    return cudaGetLastError();
+}
+cudaError_t resolve_exact_tiles_launch(const unsigned long long* d_exact, int n_local, int width, int tile_mod, int tile_rem, float4* d_accum, cudaStream_t st) {
+    if (n_local <= 0) return cudaSuccess;
+    resolve_exact_tiles_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ulonglong2*>(d_exact), n_local, 8 * width, tile_mod > 1 ? tile_mod : 1, tile_rem, d_accum);
+    return cudaGetLastError();
+}
+
+}  // namespace mort

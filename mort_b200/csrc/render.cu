@@ -11,37 +11,13 @@
 
 #include <cstdlib>
 
+#include "accum.cuh"
 #include "render.hpp"
 #include "rt_core.cuh"
 
 namespace mort {
 
-// ------------------------------------------------------------------------------------------------------
-// Exact, order-independent accumulation.  A finished sample is added as Q39.24 fixed point into 64-bit
-// integers (integer addition is associative: ANY distribution of a pixel's samples over lanes, warps, waves or
-// schedules gives the same bits), with NaN / +inf samples counted on the side so the frame keeps the IEEE
-// semantics of the reference's float sum (camera.cuh:190-198: one NaN sample poisons the pixel).
-//   word 0..2 : sum of r, g, b   (24 fractional bits = the resolution a float sample of magnitude ~1 has anyway; a pixel's sum may
-//               reach 2^39 = 5.5e11 — 4096 samples of radiance 1e8 — before it would wrap; single samples >= 2^38 are counted as +inf)
-//   word 3    : [0,20) NaN samples  [20,34) +inf in r  [34,48) +inf in g  [48,62) +inf in b
-// ------------------------------------------------------------------------------------------------------
 #define MEGA_PMAX 16
-__device__ __forceinline__ void fx_add(long long& acc, unsigned long long& flags, float v, int inf_shift) {
-    if (v != v) return;                                                    // NaN: counted once per sample by the caller
-    if (!(fabsf(v) < 274877906944.0f)) { flags += 1ull << inf_shift; return; }
-    acc += __float2ll_rn(v * 16777216.0f);
-}
-__device__ __forceinline__ float4 fx_resolve(long long r, long long g, long long b, unsigned long long flags) {
-    const float s = 1.0f / 16777216.0f;
-    const unsigned nan_n = (unsigned)(flags & 0xFFFFFu);
-    float4 o;
-    o.x = __ll2float_rn(r) * s; o.y = __ll2float_rn(g) * s; o.z = __ll2float_rn(b) * s; o.w = (float)nan_n;
-    if ((flags >> 20) & 0x3FFFu) o.x = INFINITY;
-    if ((flags >> 34) & 0x3FFFu) o.y = INFINITY;
-    if ((flags >> 48) & 0x3FFFu) o.z = INFINITY;
-    if (nan_n) { o.x = o.y = o.z = __int_as_float(0x7fc00000); }
-    return o;
-}
 
 // 64-bit add into shared memory as two native 32-bit atomics.  atomicAdd(unsigned long long*) on shared memory compiles to a
 // compare-and-swap spin loop (ATOMS.CAST.SPIN.64; 5 % of the stall samples on scene 1).  The low words wrap exactly
@@ -59,13 +35,6 @@ __device__ __forceinline__ void smem_add64(unsigned long long* p, unsigned long 
 
 // kMinBlocks = occupancy target handed to ptxas (register cap 65536 / (128 * kMinBlocks)): 4 -> 128 regs,
 // 6 -> 80, 8 -> 64.  Which one wins is a measurement (profiles/), selectable through mort_render_opts.blocks_per_sm.
-// tile split: the rank's pixels are its 8-row bands packed back to back; local index -> frame index
-__device__ __forceinline__ int tile_to_global(int li, int band_px, int mod, int rem) {
-    if (mod <= 1) return li;
-    const int bl = li / band_px;
-    return (bl * mod + rem) * band_px + (li - bl * band_px);
-}
-
 // kLinear: -1 = the scene's linear flag decides at run time (the shipped configuration), 1 / 0 = specialised builds
 template <bool kStaged, int kMinBlocks, int kLinear>
 __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_constant__ FrameParams P) {

@@ -25,6 +25,11 @@ struct FrameParams {
     unsigned long long* accum_exact;// W*H x 4 (r, g, b fixed point, flags) or null
     unsigned long long* counters;   // [0] segments, [1] samples
     unsigned int* work_counter;     // persistent-warp work queue head
+    // block wavefront (pool.cu)
+    int32_t pool_paths;             // paths per block pool
+    int32_t pool_refill;            // trace phase: lanes refill mid-traversal when at least this many of a warp's lanes are idle (0 = never)
+    unsigned long long* work64;     // head of the call's sample index space [0, total_samples)
+    unsigned long long total_samples;   // n_pixels * n_subset
 };
 
 struct LaunchShape { int threads, blocks, smem_bytes; };
@@ -32,6 +37,14 @@ struct LaunchShape { int threads, blocks, smem_bytes; };
 // megakernel (render.cu)
 cudaError_t mega_query(int threads, int n_staged, int min_blocks, bool linear, int* max_blocks_per_sm, int* regs);
 cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, int min_blocks, cudaStream_t st);
+
+// block wavefront (pool.cu): one persistent kernel, a wavefront per thread block over a pool of paths in shared memory
+struct PoolShape { int threads, min_blocks, pool_paths; };
+cudaError_t pool_query(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes);
+cudaError_t pool_launch(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st);
+// zero / resolve the exact frame over the pixels THIS call renders (all of them, or the rank's 8-row bands)
+cudaError_t zero_exact_launch(unsigned long long* d_exact, int n_pixels_local, int width, int tile_mod, int tile_rem, cudaStream_t st);
+cudaError_t resolve_exact_tiles_launch(const unsigned long long* d_exact, int n_pixels_local, int width, int tile_mod, int tile_rem, float4* d_accum, cudaStream_t st);
 
 // wavefront (wavefront.cu)
 struct WavefrontBuffers;            // opaque SoA queues

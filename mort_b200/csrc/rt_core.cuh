@@ -132,7 +132,7 @@ MORT_HD R4 rng_block(Rng& g) {
 }
 MORT_HD int rnd_int_from(float u, int lo, int hi) {                                             // rng.cuh:30-42
     float r = 1.0f - u;                                  // curand_uniform is (0,1] = 1 - [0,1)
-    r = r * (float)(hi - lo + 0.999999);                 // the reference multiplies in double; same index except exactly on a bin edge
+    r = (float)((double)r * ((double)(hi - lo) + 0.999999));   // `random *= (max - min + 0.999999)`: a double product rounded to float
     r += (float)lo;
     return (int)truncf(r);
 }

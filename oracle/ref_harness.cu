@@ -58,6 +58,118 @@
 #undef main
 #undef private
 
+// ------------------------------------------------------------------------------------------------
+// Harness-built scenes (--scene 101..104).  The reference's ten scene functions never construct an
+// `isotropic` (materials.cuh:169-202, hence never a sphere_pdf, pdf.cuh:28-42), never point the light
+// handle at a single sphere or quad (objects.cuh:110-145, 217-235 are only reached through the Cornell
+// list), never set defocus_angle > 0 (camera.cuh:222-242) and never mix media with a visible top-level
+// list (world.cuh:154-168).  These four scenes are built HERE from the reference's own classes through
+// its own builder calls, so that the reference device code itself produces golden vectors for those
+// paths too (tests/golden/extra_*.{mscn,npz}).  They are test inputs written for this repository, not
+// reference text.
+// ------------------------------------------------------------------------------------------------
+static void extra_room(world& data, int wall_r, int wall_w, int wall_g) {      // five 555-unit walls around the origin corner
+    data.add(quad(point3(555, 0, 0), vec3(0, 555, 0), vec3(0, 0, 555), MAT_LAMBERTIAN, wall_g));
+    data.add(quad(point3(0, 0, 0), vec3(0, 555, 0), vec3(0, 0, 555), MAT_LAMBERTIAN, wall_r));
+    data.add(quad(point3(0, 0, 0), vec3(555, 0, 0), vec3(0, 0, 555), MAT_LAMBERTIAN, wall_w));
+    data.add(quad(point3(555, 555, 555), vec3(-555, 0, 0), vec3(0, 0, -555), MAT_LAMBERTIAN, wall_w));
+    data.add(quad(point3(0, 0, 555), vec3(555, 0, 0), vec3(0, 555, 0), MAT_LAMBERTIAN, wall_w));
+}
+static void extra_room_camera(Camera& cam) {
+    cam.aspect_ratio = 1.0; cam.image_width = 400; cam.samples_per_pixel = 256; cam.bounce_limit = 30;
+    cam.background = color(0, 0, 0); cam.vfov = 40;
+    cam.lookfrom = point3(278, 278, -800); cam.lookat = point3(278, 278, 0); cam.vup = vec3(0, 1, 0); cam.defocus_angle = 0;
+}
+
+// 101: two participating media that scatter with `isotropic` (uniform-sphere pdf) — one bounded by a sphere, one by a
+// rotated + translated box — lit by a quad that is sampled directly (light handle = the quad itself, not a list).
+static void extra_isotropic_media(world& data, Camera& cam) {
+    solid_color c_red(color(.65, .05, .05)), c_white(color(.73, .73, .73)), c_green(color(.12, .45, .15)), c_lamp(color(7, 7, 7));
+    solid_color c_fog(color(.9, .9, .9)), c_ink(color(.15, .2, .55));
+    data.add(c_red); data.add(c_white); data.add(c_green); data.add(c_lamp); data.add(c_fog); data.add(c_ink);
+    lambertian m_red(c_red.getType(), c_red.getIdx()), m_white(c_white.getType(), c_white.getIdx()), m_green(c_green.getType(), c_green.getIdx());
+    diffuse_light m_lamp(c_lamp.getType(), c_lamp.getIdx());
+    isotropic m_fog(c_fog.getType(), c_fog.getIdx()), m_ink(c_ink.getType(), c_ink.getIdx());
+    data.add(m_red); data.add(m_white); data.add(m_green); data.add(m_lamp); data.add(m_fog); data.add(m_ink);
+    extra_room(data, m_red.getIdx(), m_white.getIdx(), m_green.getIdx());
+    quad lamp(point3(113, 554, 127), vec3(330, 0, 0), vec3(0, 0, 305), m_lamp.getType(), m_lamp.getIdx());
+    data.add(lamp);
+    sphere ball(point3(190, 120, 170), 110, m_white.getType(), m_white.getIdx(), true);      // boundary only
+    data.add(ball);
+    constant_medium fog(ball.getType(), ball.getIdx(), 0.02f, m_fog.getType(), m_fog.getIdx(), data.objs);
+    data.add(fog);
+    rotated_smoke_box(point3(165, 330, 165), vec3(300, 0, 280), 20, 0.012f, m_ink.getType(), m_ink.getIdx(), data);
+    extra_room_camera(cam);
+    cam.light_obj_type = lamp.getType(); cam.light_obj_idx = lamp.getIdx();
+}
+
+// 102: a spherical emitter importance-sampled through hittable_pdf -> sphere::pdf_value / sphere::random, under a dim sky.
+static void extra_sphere_light(world& data, Camera& cam) {
+    solid_color c_a(color(.2, .3, .1)), c_b(color(.9, .9, .9)), c_lamp(color(4, 4, 4)), c_matte(color(.7, .3, .3));
+    checker_texture c_ground(0.8, c_a.getType(), c_a.getIdx(), c_b.getType(), c_b.getIdx());
+    data.add(c_a); data.add(c_b); data.add(c_lamp); data.add(c_matte); data.add(c_ground);
+    lambertian m_ground(c_ground.getType(), c_ground.getIdx()), m_matte(c_matte.getType(), c_matte.getIdx());
+    diffuse_light m_lamp(c_lamp.getType(), c_lamp.getIdx());
+    metal m_metal(color(.8, .8, .9), 0.15); dielectric m_glass(1.5);
+    data.add(m_ground); data.add(m_matte); data.add(m_lamp); data.add(m_metal); data.add(m_glass);
+    data.add(sphere(point3(0, -1000, 0), 1000, m_ground.getType(), m_ground.getIdx()));
+    data.add(sphere(point3(0, 2, 0), 2, m_matte.getType(), m_matte.getIdx()));
+    data.add(sphere(point3(-4.5, 1.5, 1.5), 1.5, m_metal.getType(), m_metal.getIdx()));
+    data.add(sphere(point3(3.5, 1, 2.5), 1, m_glass.getType(), m_glass.getIdx()));
+    sphere lamp(point3(1, 7, -1), 1.5, m_lamp.getType(), m_lamp.getIdx());
+    data.add(lamp);
+    cam.aspect_ratio = 16.0 / 9.0; cam.image_width = 400; cam.samples_per_pixel = 256; cam.bounce_limit = 30;
+    cam.background = color(0.02, 0.02, 0.03); cam.vfov = 24;
+    cam.lookfrom = point3(22, 4, 8); cam.lookat = point3(0, 2.2, 0); cam.vup = vec3(0, 1, 0); cam.defocus_angle = 0;
+    cam.light_obj_type = lamp.getType(); cam.light_obj_idx = lamp.getIdx();
+}
+
+// 104: a lambertian-phase medium together with a VISIBLE top-level list (tested after the media, world.cuh:154-168) and a
+// box behind three nested wrappers; no light handle.
+static void extra_media_and_list(world& data, Camera& cam) {
+    solid_color c_ground(color(.5, .5, .5)), c_a(color(.8, .25, .2)), c_b(color(.2, .4, .8)), c_smoke(color(.95, .95, .95)), c_box(color(.3, .7, .3));
+    data.add(c_ground); data.add(c_a); data.add(c_b); data.add(c_smoke); data.add(c_box);
+    lambertian m_ground(c_ground.getType(), c_ground.getIdx()), m_a(c_a.getType(), c_a.getIdx()), m_b(c_b.getType(), c_b.getIdx());
+    lambertian m_smoke(c_smoke.getType(), c_smoke.getIdx()), m_box(c_box.getType(), c_box.getIdx());
+    metal m_mirror(color(.9, .9, .9), 0.0);
+    data.add(m_ground); data.add(m_a); data.add(m_b); data.add(m_smoke); data.add(m_box); data.add(m_mirror);
+    data.add(quad(point3(-30, 0, -30), vec3(60, 0, 0), vec3(0, 0, 60), m_ground.getType(), m_ground.getIdx()));
+    // the visible list: its members are hidden (skip) and only reachable through the list
+    sphere s0(point3(-2.2, 1, 0), 1, m_a.getType(), m_a.getIdx(), true), s1(point3(2.2, 1, 0.5), 1, m_mirror.getType(), m_mirror.getIdx(), true);
+    sphere s2(point3(0, 0.6, 2.4), 0.6, m_b.getType(), m_b.getIdx(), true);
+    quad q0(point3(-4, 0, -3), vec3(8, 0, 0), vec3(0, 3.5, 0), m_b.getType(), m_b.getIdx(), true);
+    data.add(s0); data.add(s1); data.add(s2); data.add(q0);
+    hittable_list shown(false);
+    shown.add(s0.getType(), s0.getIdx(), data.objs); shown.add(s1.getType(), s1.getIdx(), data.objs);
+    shown.add(s2.getType(), s2.getIdx(), data.objs); shown.add(q0.getType(), q0.getIdx(), data.objs);
+    data.add(shown);
+    // a medium that overlaps the list's members front and back
+    sphere hull(point3(0, 1.2, 0.8), 2.6, m_smoke.getType(), m_smoke.getIdx(), true);
+    data.add(hull);
+    constant_medium smoke(hull.getType(), hull.getIdx(), 0.45f, m_smoke.getType(), m_smoke.getIdx(), data.objs);
+    data.add(smoke);
+    // a box behind translate(translate(rotate_y(list)))
+    vec3 dx(1.2, 0, 0), dy(0, 1.6, 0), dz(0, 0, 1.2);
+    quad b0(point3(0, 0, 1.2), dx, dy, m_box.getType(), m_box.getIdx(), true), b1(point3(1.2, 0, 1.2), -dz, dy, m_box.getType(), m_box.getIdx(), true);
+    quad b2(point3(1.2, 0, 0), -dx, dy, m_box.getType(), m_box.getIdx(), true), b3(point3(0, 0, 0), dz, dy, m_box.getType(), m_box.getIdx(), true);
+    quad b4(point3(0, 1.6, 1.2), dx, -dz, m_box.getType(), m_box.getIdx(), true), b5(point3(0, 0, 0), dx, dz, m_box.getType(), m_box.getIdx(), true);
+    data.add(b0); data.add(b1); data.add(b2); data.add(b3); data.add(b4); data.add(b5);
+    hittable_list sides(true);
+    sides.add(b0.getType(), b0.getIdx(), data.objs); sides.add(b1.getType(), b1.getIdx(), data.objs); sides.add(b2.getType(), b2.getIdx(), data.objs);
+    sides.add(b3.getType(), b3.getIdx(), data.objs); sides.add(b4.getType(), b4.getIdx(), data.objs); sides.add(b5.getType(), b5.getIdx(), data.objs);
+    data.add(sides);
+    rotate_y rot(sides.getType(), sides.getIdx(), 32, data.objs, true);
+    data.add(rot);
+    translate t_in(rot.getType(), rot.getIdx(), vec3(3.0, 0, -1.5), data.objs, true);
+    data.add(t_in);
+    translate t_out(t_in.getType(), t_in.getIdx(), vec3(0.8, 0, 3.2), data.objs);
+    data.add(t_out);
+    cam.aspect_ratio = 16.0 / 9.0; cam.image_width = 400; cam.samples_per_pixel = 256; cam.bounce_limit = 30;
+    cam.background = color(0.70, 0.80, 1.00); cam.vfov = 30;
+    cam.lookfrom = point3(4, 5, 14); cam.lookat = point3(0.5, 1, 0.5); cam.vup = vec3(0, 1, 0); cam.defocus_angle = 0;
+    cam.light_obj_type = -1; cam.light_obj_idx = 0;
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
     fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(3); } } while (0)
 
@@ -338,14 +450,15 @@ static void write_img(const char* path, int w, int h, int c, int dtype, const vo
 
 static void usage() {
     fprintf(stderr,
-        "mort_ref --scene N [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
+        "mort_ref --scene N(1-10 | 101-104 harness-built) [--defocus A] [--focus F] [--heap-mb M] [--stack B] [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
         "         [--dump-scene out.mscn] [--dump-image-rgb out.ppm] [--img8 out.mimg] [--hdr out.mimg]\n"
         "         [--trace-grid GW out.mhit] [--trace-random N SEED out.mhit] [--trace-file in.rays out.mhit]\n");
 }
 
 int main(int argc, char** argv) {
     int scene = 0, width = 0, spp = 0, depth = 0, frames = 0, grid_w = 0, rnd_n = 0, host_only = 0, warmup = -1;
-    float aspect = 0; unsigned long seed = 69420; uint64_t rnd_seed = 1;
+    float aspect = 0, defocus = -1.f, focus = -1.f; unsigned long seed = 69420; uint64_t rnd_seed = 1;
+    long heap_mb = 1024, stack_b = 8192;              // harness-side limits (A-Q15, mort.cu:703); overridable to characterise the reference's crashes
     const char *dump = 0, *dump_rgb = 0, *img8 = 0, *hdr = 0, *grid_out = 0, *rnd_out = 0, *file_in = 0, *file_out = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -356,6 +469,8 @@ int main(int argc, char** argv) {
         else if (a == "--frames") frames = atoi(nx()); else if (a == "--warmup") warmup = atoi(nx()); else if (a == "--dump-scene") dump = nx();
         else if (a == "--dump-image-rgb") dump_rgb = nx(); else if (a == "--img8") img8 = nx();
         else if (a == "--hdr") hdr = nx();
+        else if (a == "--defocus") defocus = (float)atof(nx()); else if (a == "--focus") focus = (float)atof(nx());
+        else if (a == "--heap-mb") heap_mb = atol(nx()); else if (a == "--stack") stack_b = atol(nx());
         else if (a == "--host-only") host_only = 1;   // dump the host-side scene and stop before any CUDA call (no GPU needed)
         else if (a == "--trace-grid") { grid_w = atoi(nx()); grid_out = nx(); }
         else if (a == "--trace-random") { rnd_n = atoi(nx()); rnd_seed = strtoull(nx(), 0, 10); rnd_out = nx(); }
@@ -376,12 +491,18 @@ int main(int argc, char** argv) {
         case 8: final_scene(data, cam, 800, 1000, 40); break;
         case 9: final_scene(data, cam, 400, 250, 4); break;
         case 10: out_of_order_spheres(data, cam, 35); break;
+        case 101: extra_isotropic_media(data, cam); break;                    // harness-built (see above)
+        case 102: extra_sphere_light(data, cam); break;
+        case 103: random_spheres(data, cam); cam.defocus_angle = 0.6f; cam.focus_dist = 10.0f; break;   // scene 1 through the lens path
+        case 104: extra_media_and_list(data, cam); break;
         default: break;           // empty world, like the reference
     }
     if (width > 0) cam.image_width = width;
     if (aspect > 0) cam.aspect_ratio = aspect;
     if (spp > 0) cam.samples_per_pixel = spp;
     if (depth > 0) cam.bounce_limit = depth;
+    if (defocus >= 0) cam.defocus_angle = defocus;
+    if (focus > 0) cam.focus_dist = focus;
     cam.initialize();
     if (host_only) { if (dump) dump_scene(dump, data, cam, dump_rgb); return 0; }
     data.toDevice();
@@ -390,8 +511,8 @@ int main(int argc, char** argv) {
 
     const int W = cam.image_width, H = cam.image_height;
     dim3 threads(16, 16), blocks((unsigned)ceil((float)W / 16.0), (unsigned)ceil((float)H / 16.0));
-    CK(cudaDeviceSetLimit(cudaLimitStackSize, 8192));                       // mort.cu:703
-    CK(cudaDeviceSetLimit(cudaLimitMallocHeapSize, (size_t)1 << 30));       // harness-side (A-Q15)
+    CK(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)stack_b));             // mort.cu:703 (8192 unless --stack)
+    CK(cudaDeviceSetLimit(cudaLimitMallocHeapSize, (size_t)heap_mb << 20));  // harness-side (A-Q15); 1 GiB unless --heap-mb
 
     curandState* dev_states;
     size_t n_states = (size_t)blocks.y * 16 * W + 16 * 16 + 16;            // padded (A-Q14)

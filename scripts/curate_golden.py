@@ -24,7 +24,7 @@ DST = "tests/golden"
 os.makedirs(DST, exist_ok=True)
 
 
-def subsample(h, keep=1500):
+def subsample(h, keep=1500):                 # harness-built scenes (101-104) keep the same budget
     n = len(h["hits"])
     ties = np.nonzero((h["hits"]["flags"] & 2) != 0)[0]
     step = max(1, n // keep)
@@ -32,7 +32,7 @@ def subsample(h, keep=1500):
     return idx
 
 
-for sc in range(1, 11):
+for sc in list(range(1, 11)) + [101, 102, 103, 104]:
     p = f"{SRC}/scene_{sc}.mscn"
     if os.path.exists(p):
         if sc == 9:
@@ -70,9 +70,14 @@ for sc in range(1, 11):
         ok = (a[..., 3] == 0) & (b[..., 3] == 0) & np.isfinite(a[..., :3]).all(axis=-1) & np.isfinite(b[..., :3]).all(axis=-1)
         ma, mb = a[..., :3][ok] / spp, b[..., :3][ok] / spp
         rmse_ab = np.sqrt(((ma - mb) ** 2).mean(axis=0)) if ok.any() else np.zeros(3)
+        # firefly-robust floor: the same RMSE without the 0.5 % of pixels with the largest squared difference (in scenes with
+        # media + light sampling a handful of pixels carries most of the squared error of any two renders)
+        d2 = ((ma - mb) ** 2).sum(axis=1)
+        keep = d2 <= np.quantile(d2, 0.995) if len(d2) else np.zeros(0, bool)
+        rmse_trim = np.sqrt(((ma[keep] - mb[keep]) ** 2).mean(axis=0)) if keep.any() else np.zeros(3)
         lum = lambda m: float((0.2126 * m[:, 0] + 0.7152 * m[:, 1] + 0.0722 * m[:, 2]).mean()) if len(m) else 0.0
         np.savez_compressed(f"{DST}/conv_{sc}.npz", mean_a=(a[..., :3] / spp).astype(np.float16), nan_a=a[..., 3].astype(np.uint16),
-                            nan_b=b[..., 3].astype(np.uint16), finite_b=np.isfinite(b[..., :3]).all(axis=-1), spp=np.int32(spp), rmse_ab=rmse_ab.astype(np.float64),
+                            nan_b=b[..., 3].astype(np.uint16), finite_b=np.isfinite(b[..., :3]).all(axis=-1), spp=np.int32(spp), rmse_ab=rmse_ab.astype(np.float64), rmse_ab_trim=rmse_trim.astype(np.float64),
                             lum_a=np.float64(lum(ma)), lum_b=np.float64(lum(mb)),
                             rgba8_a=F.read_mimg(f"{SRC}/conv8_{sc}_a.mimg") if os.path.exists(f"{SRC}/conv8_{sc}_a.mimg") else np.zeros(0, np.uint8))
         print(f"scene {sc}: conv {a.shape} spp {spp} rmse_ab {rmse_ab} lum {lum(ma):.5f} {lum(mb):.5f} nan px {int((a[...,3]>0).sum())}")

@@ -53,3 +53,11 @@ def luminance(rgb):
 
 def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def trimmed_rmse(a, b, trim=0.005):
+    """Per-channel RMSE of two (N, 3) images without the `trim` share of pixels with the largest squared difference
+    (scripts/curate_golden.py computes the fixtures' rmse_ab_trim the same way)."""
+    d2 = ((a - b) ** 2).sum(axis=1)
+    keep = d2 <= np.quantile(d2, 1.0 - trim)
+    return np.sqrt(((a[keep] - b[keep]) ** 2).mean(axis=0))
