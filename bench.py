@@ -3,20 +3,27 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mort|reference]
 
-A "step" is one full frame of the workload BASELINE.json's metric is quoted on:
-  configs[1] = Cornell box (scene 6) at 600x600, 1024 spp (32x32 strata), max depth 50.
-`value` = camera samples (paths) per second over the whole job, frames rendered device-resident;
-`e2e`   = the same metric through the reference-facing host-buffer call (mort_render: kernels + tone map +
-          device->host copy of the RGBA8 frame into pinned memory) with the time of every call included.
-N > 1: one process per GPU (torchrun), the frame is SAMPLE-split across ranks (strong scaling: total work is
-fixed), partial accumulation buffers are combined with one NCCL reduce per frame, rank 0 tone-maps.
+Workload = BASELINE.json configs[2] (config 3): the book-2 final scene (mort scene 8: 2401 quads + 1007 spheres behind a
+4-wide SAH BVH, instanced sub-list, two constant media, earth image texture, Perlin noise, quad light) at 800x800, max
+depth 40.  It is the configuration that exercises EVERYTHING on the hot path — tree traversal, instance transforms, media
+probes, every material and texture, light sampling — where round 1's headline (Cornell, 13 primitives) never entered the
+traversal kernel.  A "step" is one 1024-spp pass (32x32 strata) over the whole frame = a quarter of the 4096-spp frame the
+config names (samples/s does not depend on how the 4096 samples are cut into passes; a 4096-spp step would make the
+default run take minutes).
+`value` = camera samples (paths) per second over the whole job, frames device-resident, CUDA events on the launching stream;
+`e2e`   = the same metric through the reference-facing host-buffer call (mort_render: kernels + tone map + device->host
+          copy of the RGBA8 frame into pinned memory), wall clock around every call;
+`per_config` (N = 1) = short runs of BASELINE configs 1, 2 and 4 for continuity with round 1.
+N > 1: one process per GPU (torchrun), the frame is SAMPLE-split across ranks (strong scaling: total work is fixed), the
+exact partial frames are combined by ONE NCCL uint64 sum-reduce per frame issued through the C ABI
+(mort_comm_reduce_exact; torch.distributed only hands the 128-byte NCCL id around), rank 0 resolves and tone-maps.
 
-`--impl reference` times the UNMODIFIED reference renderer (oracle/_ref/mort_ref = /root/reference/mort.cu
-rebuilt for sm_100a behind the headless harness).  The reference has no CPU renderer (every hit/scatter is
-__device__-only), so per BASELINE.json's north_star its baseline arm is its own CUDA kernel on ONE B200; it
-is timed as the reference times itself (CUDA events around renderKernel, mort.cu:96-114) on a bounded sample
-of the same workload (same scene / resolution / depth at 16 spp — the reference needs ~100 s for one
-1024-spp frame); Msamples/s does not depend on spp once every SM has resident work.
+`--impl reference` times the UNMODIFIED reference renderer (oracle/_ref/mort_ref = /root/reference/mort.cu rebuilt for
+sm_100a behind the headless harness) on the same scene / resolution / depth.  The reference has no CPU renderer (every
+hit/scatter is __device__-only), so per BASELINE.json's north_star its baseline arm is its own CUDA kernel on ONE B200, timed
+as the reference times itself (CUDA events around renderKernel, mort.cu:96-114) on a bounded sample: 1 spp per frame (the
+reference is thread-per-pixel: 640 000 resident threads whatever the spp, so Msamples/s does not depend on spp; one
+1024-spp pass would take it ~1 hour).
 """
 from __future__ import annotations
 
@@ -32,9 +39,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = {"scene": 6, "width": 600, "spp": 1024, "depth": 50}
-FLOP_PER_RAY = 482.0          # algorithmic FLOP per path segment for config 2 (n ~ 20 primitives)
-REF_SPP = 16                  # bounded sample for the reference arm
+WORKLOAD = {"scene": 8, "width": 800, "spp": 1024, "depth": 40}
+SCENE_NAMES = {1: "random_spheres", 6: "cornell_box", 8: "final_scene (book 2)", 9: "final_scene (small)"}
+# algorithmic FLOP per path segment = 2*ceil(log2 n)*F_box*1.5 + 2*F_prim + F_rec + F_shade, evaluated there per config
+FLOP_PER_RAY = {"config 1": 692.0, "config 2": 482.0, "config 3": 860.0, "config 4": 1286.0}
+REF_SPP = 1                   # bounded sample for the reference arm (see the module docstring)
 
 
 def parse():
@@ -43,16 +52,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mort", choices=["mort", "reference"])
-    ap.add_argument("--mode", default="mega", choices=["mega", "wave"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "mega", "wave", "pool"])
     ap.add_argument("--scene", type=int, default=WORKLOAD["scene"])
     ap.add_argument("--width", type=int, default=WORKLOAD["width"])
     ap.add_argument("--spp", type=int, default=WORKLOAD["spp"])
     ap.add_argument("--depth", type=int, default=WORKLOAD["depth"])
     ap.add_argument("--aspect", type=float, default=0.0)
-    ap.add_argument("--stage", type=int, default=-1)
-    ap.add_argument("--bps", type=int, default=0, help="megakernel blocks per SM (selects the register-capped variant)")
+    ap.add_argument("--stage", type=int, default=0)
+    ap.add_argument("--bps", type=int, default=0, help="blocks per SM (selects the register-capped kernel variant)")
+    ap.add_argument("--tpb", type=int, default=0, help="threads per block")
+    ap.add_argument("--pool", type=int, default=0, help="block wavefront: paths per block pool")
+    ap.add_argument("--refill", type=int, default=0, help="block wavefront: lane refill threshold")
     ap.add_argument("--split", default="sample", choices=["sample", "tile"], help="how the frame is sharded over GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true")
     ap.add_argument("--field", type=int, default=0, help="BASELINE config 4: sphere field over cells [-G,G)^2 instead of --scene (G = 500: 1 M spheres)")
     ap.add_argument("--fieldcam", type=int, default=0, choices=[0, 1], help="0 = book view, 1 = aerial")
     return ap.parse_args()
@@ -132,13 +145,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows), "source": self.how}
 
 
+def scene_label(a):
+    return SCENE_NAMES.get(a.scene, "scene")
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     exe = os.path.join(ROOT, "oracle", "_ref", "mort_ref")
-    cfg = {"workload": f"mort scene {a.scene} (cornell_box) {a.width}x{a.width} depth {a.depth}; reference arm at {REF_SPP} spp per frame (bounded sample)",
-           "scene": a.scene, "width": a.width, "spp": REF_SPP, "depth": a.depth, "l2": "working set << L2; reference launches are seconds long"}
+    cfg = {"workload": f"mort scene {a.scene} ({scene_label(a)}) {a.width}x{a.width} depth {a.depth}; reference arm at {REF_SPP} spp per frame (bounded sample: "
+                       "thread-per-pixel kernel, Msamples/s independent of spp)",
+           "scene": a.scene, "width": a.width, "spp": REF_SPP, "depth": a.depth, "l2": "the reference's recursion scratch (depth x W x H x 32 B = 0.8 GB) exceeds L2; launches are seconds long"}
     if not os.path.exists(exe):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/mort_ref not built (needs /root/reference at build time)"}))
         return 0
@@ -146,9 +164,9 @@ def run_reference(a):
            "--frames", str(a.steps), "--warmup", str(a.warmup)]
     if a.aspect > 0:
         cmd += ["--aspect", str(a.aspect)]
-    # The unmodified reference kernel dies now and then with "invalid program counter" (2 of ~12 launches of this very command
-    # on B200; its device-side new/delete, recursion and unchecked indices are SURVEY.md App. A material): a crashed attempt is
-    # repeated, up to 3 times, and the number of attempts is reported.
+    # The unmodified reference kernel dies now and then with "invalid program counter" (profiles/r02_reference_crash.md): it calls a
+    # virtual function through the pointer device-side `new` returned without checking it.  A crashed attempt is repeated, up to 3
+    # times, and the number of attempts is reported.
     line, attempts, failures = None, 0, []
     while line is None and attempts < 3:
         attempts += 1
@@ -188,11 +206,11 @@ def cpu_baseline(a):
     r.build_scene(a.scene)
     r.dump_scene(tmp)
     r.close()
-    import numpy as np
     from mort_b200 import formats as F
     earth = F.read_ppm(os.path.join(ROOT, "mort_b200", "assets", "earthmap.ppm"))
     osc = O.OracleScene(tmp, earth)
-    w, spp = 192, 1024                                         # ~10 s of CPU work on 16 threads
+    # ~10-20 s of CPU work: the oracle scans scene 8's 3408 primitives linearly per segment, like the reference
+    w, spp = (96, 36) if a.scene in (8, 9) else (192, 1024)
     osc.override(width=w, spp=spp, depth=a.depth)
     cores = os.cpu_count() or 1
     t0 = time.time()
@@ -201,6 +219,61 @@ def cpu_baseline(a):
     return {"value": st["samples"] / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
             "sample": f"oracle/mort_oracle.c, scene {a.scene} at {w}x{w}, {spp} spp, depth {a.depth}: {st['samples']} samples in {dt:.1f} s on {cores} threads",
             "mrays_per_s": st["segments"] / dt / 1e6}
+
+
+def pick_mode(a, linear_scan):
+    """auto = the scheduler measured fastest for the scene class (profiles/r02_*): the block wavefront everywhere it was measured."""
+    from mort_b200.api import MODE_MEGAKERNEL, MODE_POOL, MODE_WAVEFRONT
+    if a.mode == "mega":
+        return MODE_MEGAKERNEL, "mega"
+    if a.mode == "wave":
+        return MODE_WAVEFRONT, "wave"
+    return MODE_POOL, "pool"
+
+
+def traffic_for(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel variant bench.py launches for `key`, from this
+    round's ncu --set full capture (profiles/r02_traffic.json; null when that variant was not captured)."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        e = tj.get(key)
+        return (e["dram_bytes_per_launch"], e.get("samples_per_launch")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def short_run(torch, Renderer, dev, stream, setup, spp_label, frames, warmup, mode, kw, flop_key, sm_count, sm_clock_hz):
+    """A few device-resident frames of another BASELINE config (per_config extra); CUDA events on the launching stream."""
+    r = Renderer(dev.index)
+    r.set_stream(stream.cuda_stream)
+    setup(r)
+    r.commit()
+    st = r.stats
+    H, W, n_spp = st["height"], st["width"], st["sqrt_spp"] ** 2
+    accum = torch.zeros(H, W, 4, dtype=torch.float32, device=dev)
+    for i in range(warmup):
+        r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    segs, ker = 0, 0.0
+    e0.record(stream)
+    for i in range(frames):
+        r.render_device(accum.data_ptr(), seed=69420, frame=warmup + i, mode=mode, **kw)
+        s = r.stats
+        segs += s["last_segments"]; ker += s["last_render_ms"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st2 = r.stats
+    r.close()
+    samples = H * W * n_spp * frames
+    achieved = segs / (ker * 1e-3) * FLOP_PER_RAY[flop_key] / 1e12
+    peak = sm_count * 128 * 2 * sm_clock_hz / 1e12
+    return {"workload": f"{spp_label} {W}x{H}, {n_spp} spp effective, depth {st['bounce_limit']}", "value": samples / (ms * 1e3), "unit": "Msamples/s",
+            "mrays_per_s": segs / (ms * 1e3), "ms_per_frame": ms / frames, "kernel_ms_per_frame": ker / frames, "frames": frames,
+            "roofline_frac_fp32": achieved / peak, "flop_per_ray": FLOP_PER_RAY[flop_key],
+            "kernel": {"regs": st2["regs_per_thread"], "threads_per_block": st2["threads_per_block"], "blocks_per_sm": st2["blocks_per_sm"],
+                       "bvh_nodes": st2["n_nodes"], "leaves": st2["n_leaves"]}}
 
 
 def run_mort(a):
@@ -235,37 +308,53 @@ def run_mort(a):
     H, W, n_spp = st["height"], st["width"], st["sqrt_spp"] ** 2
     stream = torch.cuda.current_stream()
     r.set_stream(stream.cuda_stream)
+    mode, mode_name = pick_mode(a, st["n_nodes"] == 1)
+    kw = dict(stage_nodes=a.stage, blocks_per_sm=a.bps, threads_per_block=a.tpb, pool_paths=a.pool, pool_refill=a.refill)
+    if world > 1:
+        # the data-path collective lives behind the C ABI; torch.distributed only carries the 128-byte NCCL id to the ranks
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(Renderer.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, src=0)
+        r.comm_attach(bytes(idt.cpu().numpy().tobytes()), world, rank)
     accum = torch.zeros(H, W, 4, dtype=torch.float32, device=dev)
-    # N > 1: ranks exchange EXACT partial frames (4 x int64 fixed-point words per pixel): integer sums are associative, so the
+    # N > 1: ranks exchange EXACT partial frames (4 x uint64 fixed-point words per pixel): integer sums are associative, so the
     # combined frame is bit-identical to the single-GPU frame whatever the reduction order
     exact = torch.zeros(H, W, 4, dtype=torch.int64, device=dev) if world > 1 else None
     rgba = torch.zeros(H, W, 4, dtype=torch.uint8, device=dev)
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    mode = MODE_MEGAKERNEL if a.mode == "mega" else MODE_WAVEFRONT
     mod, rem = D.sample_split(rank, world)
     split = dict(sample_mod=mod, sample_rem=rem) if a.split == "sample" else dict(tile_mod=world, tile_rem=rank)
     seg_total, ker_ms, launches = 0, 0.0, 0
 
-    def step(i, timed):
-        nonlocal seg_total, ker_ms, launches
-        flush.zero_()                                                       # L2 flush between iterations
-        if world > 1 and mode == MODE_MEGAKERNEL:
+    def frame(i, host_rgba=None):
+        """one step = one frame: every rank renders its share, one collective, rank 0 resolves + tone-maps"""
+        if world > 1 and mode != MODE_WAVEFRONT:
             if a.split == "tile":
                 exact.zero_()                                   # ranks only write their own bands
-            r.render_device(exact.data_ptr(), seed=69420, frame=i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps, exact_accum=1, **split)
+            r.render_device(exact.data_ptr(), seed=69420, frame=i, mode=mode, exact_accum=1, **kw, **split)
             s = r.stats
-            D.combine(exact, how="reduce")
+            r.comm_reduce_exact(exact.data_ptr(), 0)
             if rank == 0:
                 r.resolve_exact_device(exact.data_ptr(), accum.data_ptr())
         else:
-            r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps, **split)
+            r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, **kw, **split)
             s = r.stats
             if world > 1:
                 D.combine(accum, how="reduce")
         if rank == 0:
             r.tonemap_device(accum.data_ptr(), n_spp, rgba.data_ptr())
+            if host_rgba is not None:
+                host_rgba.copy_(rgba, non_blocking=False)
+        return s
+
+    def step(i, timed):
+        nonlocal seg_total, ker_ms, launches
+        flush.zero_()                                                       # L2 flush between iterations
+        s = frame(i)
         if timed:
-            seg_total += s["last_segments"]; ker_ms += s["last_render_ms"]; launches += s["last_kernel_launches"] + (1 if rank == 0 else 0)
+            seg_total += s["last_segments"]; ker_ms += s["last_render_ms"]
+            launches += s["last_kernel_launches"] + (1 if rank == 0 else 0) + (2 if world > 1 and rank == 0 else (1 if world > 1 else 0))
 
     for i in range(a.warmup):
         step(i, False)
@@ -293,41 +382,27 @@ def run_mort(a):
     value = samples_per_frame * a.steps / (ms * 1e3)                         # Msamples/s, whole job
     mrays = seg_all / (ms * 1e3)
 
-    # ---- end-to-end through the reference-facing host-buffer call (N = 1 semantics on every rank's share) ----
+    # ---- end-to-end through the reference-facing host-buffer call ----
     host_rgba = torch.empty(H, W, 4, dtype=torch.uint8).pin_memory()
-    e2e_ms = None
     if world == 1:
-        r.render_into(host_rgba.data_ptr(), 0, seed=69420, frame=0, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps)      # warm
+        r.render_into(host_rgba.data_ptr(), 0, seed=69420, frame=0, mode=mode, **kw)      # warm
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(a.steps):
-            r.render_into(host_rgba.data_ptr(), 0, seed=69420, frame=a.warmup + i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps)
+            r.render_into(host_rgba.data_ptr(), 0, seed=69420, frame=a.warmup + i, mode=mode, **kw)
             _ = int(host_rgba[0, 0, 3])                                        # touch the result on the host
         e2e_ms = (time.perf_counter() - t0) * 1e3
     else:
-        # N > 1: same call per rank on its sample share + the one collective + tone map + D2H on rank 0
-        part = torch.empty(H, W, 4, dtype=torch.float32).pin_memory()
+        # N > 1: the same frame function + the RGBA8 frame copied to pinned host memory on rank 0
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(a.steps):
-            if mode == MODE_MEGAKERNEL:
-                if a.split == "tile":
-                    exact.zero_()
-                r.render_device(exact.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps, exact_accum=1, **split)
-                D.combine(exact, how="reduce")
-                if rank == 0:
-                    r.resolve_exact_device(exact.data_ptr(), accum.data_ptr())
-            else:
-                r.render_device(accum.data_ptr(), seed=69420, frame=a.warmup + i, mode=mode, stage_nodes=a.stage, blocks_per_sm=a.bps, **split)
-                D.combine(accum, how="reduce")
+            frame(a.warmup + i, host_rgba if rank == 0 else None)
             if rank == 0:
-                r.tonemap_device(accum.data_ptr(), n_spp, rgba.data_ptr())
-                host_rgba.copy_(rgba, non_blocking=False)
                 _ = int(host_rgba[0, 0, 3])
         dist.barrier(); torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev); dist.all_reduce(tt, op=dist.ReduceOp.MAX); e2e_ms = float(tt[0])
-        del part
 
     if rank == 0:
         st2 = r.stats
@@ -341,23 +416,23 @@ def run_mort(a):
         fp32_peak = st["sm_count"] * 128 * 2 * sm_clock / 1e12                    # TFLOP/s at the clock actually sustained
         kernel_ms_per_launch = ker_ms_max / a.steps
         per_gpu_rays_per_s = (seg_all / world) / a.steps / (kernel_ms_per_launch * 1e-3)
-        # FLOP_ray = 2*ceil(log2 n)*F_box*1.5 + 2*F_prim + F_rec + F_shade, evaluated there for the four configs
-        flop_per_ray, flop_cfg = (1286.0, "config 4") if a.field > 0 else {1: (692.0, "config 1"), 8: (860.0, "config 3"), 9: (860.0, "config 3")}.get(a.scene, (FLOP_PER_RAY, "config 2"))
+        flop_cfg = "config 4" if a.field > 0 else {1: "config 1", 6: "config 2"}.get(a.scene, "config 3")
+        flop_per_ray = FLOP_PER_RAY[flop_cfg]
         achieved = per_gpu_rays_per_s * flop_per_ray / 1e12
-        traffic = None
-        try:    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this config, from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if (a.scene, a.width, a.spp, a.depth, a.mode, a.field) == (6, 600, 1024, 50, "mega", 0) and world == 1:
-                traffic = tj["dram_bytes_per_launch"]
-        except Exception:
-            pass
+        tkey = f"field{a.field}:{mode_name}" if a.field > 0 else f"scene{a.scene}:{mode_name}"
+        traffic, traffic_samples = traffic_for(tkey) if world == 1 else (None, None)
+        if traffic and traffic_samples:                                         # the capture ran a shorter launch of the same kernel: scale to this launch
+            traffic = traffic * (samples_per_frame / traffic_samples)
+        kname = {"mega": "mega_kernel", "pool": "pool_kernel", "wave": "wavefront kernels"}[mode_name]
+        workload = (f"sphere field G={a.field} ({st2['n_leaves']} leaves, camera {a.fieldcam})" if a.field > 0 else
+                    f"BASELINE config 3 scene: mort scene {a.scene} ({scene_label(a)})" if a.scene == 8 else f"mort scene {a.scene} ({scene_label(a)})")
         res = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"sphere field G={a.field} ({st2['n_leaves']} leaves, camera {a.fieldcam})" if a.field > 0 else
-                                    f"mort scene {a.scene} ({'cornell_box' if a.scene == 6 else 'scene'})") + f" {W}x{H}, {a.spp} spp ({n_spp} effective), max depth {a.depth}",
-                       "scene": None if a.field > 0 else a.scene, "width": W, "height": H, "spp": a.spp, "depth": a.depth, "mode": a.mode,
-                       "parallelism": f"{a.split}-split x{world} + 1 NCCL int64 SUM reduce of the exact partial frames per frame" if world > 1 else "single GPU",
+            "config": {"workload": workload + f" {W}x{H}, max depth {a.depth}; one step = one {a.spp}-spp pass ({n_spp} effective)"
+                                   + (" = 1/4 of the 4096-spp frame the config names" if (a.scene, a.spp) == (8, 1024) else ""),
+                       "scene": None if a.field > 0 else a.scene, "width": W, "height": H, "spp": a.spp, "depth": a.depth, "mode": mode_name,
+                       "parallelism": f"{a.split}-split x{world} + 1 NCCL uint64 SUM reduce of the exact partial frames per frame (C ABI: mort_comm_reduce_exact)" if world > 1 else "single GPU",
                        "l2": "192 MiB buffer written between timed iterations (L2 flush)"},
             "mrays_per_s": mrays, "segments_per_sample": seg_all / (samples_per_frame * a.steps),
             "clocks": clocks,
@@ -366,10 +441,11 @@ def run_mort(a):
                     "note": "per step: kernel-parameter block up (the scene is resident, as in the reference's frame loop), RGBA8 frame down to pinned host memory"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (ncu)", "kernel": "mega_kernel" if a.mode == "mega" else "wavefront kernels",
+                         "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel variant, this round)", "kernel": kname,
                          "kernel_ms_per_launch": kernel_ms_per_launch,
                          "how": f"algorithmic {flop_per_ray:.0f} FLOP per path segment (SURVEY.md §8d, {flop_cfg}) x segments per launch / CUDA-event kernel time; "
                                 f"peak = {st['sm_count']} SMs x 128 lanes x 2 x median SM clock under load (the path is neither HBM- nor tensor-bound)",
+                         "algorithmic_bytes_per_launch": H * W * 16,
                          "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
                          # the same kernel against the HBM roofline (the contract's other bound): measured DRAM bytes per launch / kernel time
                          "hbm": ({"achieved_gbs": traffic / (kernel_ms_per_launch * 1e6), "peak_gbs": peaks.get("hbm_gbs"),
@@ -378,6 +454,18 @@ def run_mort(a):
             "kernel": {"regs": st2["regs_per_thread"], "threads_per_block": st2["threads_per_block"], "blocks_per_sm": st2["blocks_per_sm"],
                        "staged_nodes": st2["staged_nodes"], "bvh_nodes": st2["n_nodes"], "leaves": st2["n_leaves"], "linear_scan": st2["n_nodes"] == 1},
         }
+        r.close()
+        if world == 1 and not a.no_per_config and a.field == 0 and (a.scene, a.width, a.depth) == (WORKLOAD["scene"], WORKLOAD["width"], WORKLOAD["depth"]):
+            # continuity with round 1 (whose headline was config 2): short device-resident runs of the other single-GPU configs
+            pc = {}
+            try:
+                args = (torch, Renderer, dev, stream)
+                pc["config 1"] = short_run(*args, lambda q: q.build_scene(1).override_camera(width=400, aspect=16 / 9, spp=32, depth=50), "mort scene 1 (random_spheres)", 20, 3, mode, kw, "config 1", st["sm_count"], sm_clock)
+                pc["config 2"] = short_run(*args, lambda q: q.build_scene(6).override_camera(width=600, spp=1024, depth=50), "mort scene 6 (cornell_box)", 3, 1, mode, kw, "config 2", st["sm_count"], sm_clock)
+                pc["config 4"] = short_run(*args, lambda q: q.build_sphere_field(500, 69420, 0).override_camera(width=1920, aspect=16 / 9, spp=256, depth=50), "1 M-sphere field, book view", 2, 1, mode, kw, "config 4", st["sm_count"], sm_clock)
+            except Exception as ex:  # an extra, never a gate
+                pc["error"] = str(ex)
+            res["per_config"] = pc
         if world == 1 and not a.no_cpu_baseline and a.field == 0:
             try:
                 res["cpu_baseline"] = cpu_baseline(a)
@@ -388,7 +476,8 @@ def run_mort(a):
             os.write(json_fd, (json.dumps(res) + "\n").encode())
         else:
             print(json.dumps(res))
-    r.close()
+    else:
+        r.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

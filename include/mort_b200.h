@@ -120,8 +120,9 @@ typedef struct {
     int32_t accumulate;            /* exact_accum only: 1 = ADD this call's sums to the contents of d_accum (progressive rendering:
                                       render frame 0 with 0, frames 1.. with 1, a new `frame` each time), 0 = overwrite */
     int32_t pool_paths;            /* MORT_MODE_POOL: paths per thread-block pool (0 = default 1024; 88 B of shared memory each) */
-    int32_t pool_refill;           /* MORT_MODE_POOL: reserved for mid-traversal lane refill (0 = off) */
-    int32_t reserved[1];
+    int32_t pool_refill;           /* MORT_MODE_POOL, tree scenes: lanes whose ray left the tree take a new one as soon as this many lanes of
+                                      their warp are idle (1..31; 0 = default, -1 = off: fixed 32-ray chunks) */
+    int32_t pool_sync;             /* MORT_MODE_POOL: 1 = the phased form (trace | __syncthreads | shade | __syncthreads), 0 = barrier-free queues (default) */
 } mort_render_opts;
 void mort_default_render_opts(mort_render_opts* o);
 

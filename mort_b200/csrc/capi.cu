@@ -60,7 +60,7 @@ int mort_create(int cuda_device, mort_ctx** out) {
     memset(&ctx->dscene, 0, sizeof(ctx->dscene));
     if (cudaGetDeviceProperties(&ctx->prop, cuda_device) != cudaSuccess || cudaStreamCreate(&ctx->own_stream) != cudaSuccess ||     // a BLOCKING stream: ordered after work the host queued on the legacy default stream
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_work, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_work, sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&ctx->d_mat_offsets, 8 * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&ctx->d_work64, sizeof(unsigned long long)) != cudaSuccess) {
         delete ctx; return MORT_ERR_CUDA;
     }
@@ -76,6 +76,7 @@ int mort_destroy(mort_ctx* ctx) {
     CTX_CHECK(ctx);
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->comm) mort_comm_detach(ctx);
     ctx->arena.release();
     wavefront_free(ctx->wave);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_mat_offsets); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgba); cudaFree(ctx->d_prog); cudaFree(ctx->d_pool_exact); cudaFree(ctx->d_work64);
@@ -304,7 +305,7 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     p.counters = ctx->d_counters; p.work_counter = ctx->d_work;
 
     const int threads = o.threads_per_block > 0 ? (o.threads_per_block + 31) / 32 * 32 : 128;
-    if (threads > 128) return fail(ctx, MORT_ERR_ARG, "mort_render: at most 128 threads per block");
+    if (threads > 128 && o.mode == MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render: the megakernel takes at most 128 threads per block");
     // staging is opt-in (stage_nodes > 0): measured slower than L1-resident LDG.128 nodes (profiles/r01: scene 8 154 vs 276
     // Msamples/s), so <= 0 means none.  The megakernel keeps 6 KB of static shared memory of its own.
     int n_staged = o.stage_nodes;
@@ -315,7 +316,7 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     p.n_staged = n_staged;
 
     if (ctx->stack_fix == 2) { raise_stack_limit(); ctx->stack_fix = 0; }
-    CU(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
     uint64_t launches = 0;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -346,10 +347,10 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         p.accum = nullptr; p.accum_exact = target;
         p.work64 = ctx->d_work64; p.total_samples = (unsigned long long)p.n_pixels * (unsigned long long)p.n_subset;
         PoolShape ps; ps.threads = o.threads_per_block > 0 ? o.threads_per_block : 512; ps.min_blocks = o.blocks_per_sm > 0 ? o.blocks_per_sm : 2;
-        ps.pool_paths = o.pool_paths > 0 ? o.pool_paths : 1024;
-        if (ps.pool_paths < 32 || ps.pool_paths > 65504) return fail(ctx, MORT_ERR_ARG, "mort_render: pool_paths must be in [32, 65504]");
+        ps.pool_paths = o.pool_paths > 0 ? o.pool_paths : 1024; ps.async = o.pool_sync ? 0 : 1;
+        if (ps.pool_paths < 32 || ps.pool_paths > 32736) return fail(ctx, MORT_ERR_ARG, "mort_render: pool_paths must be in [32, 32736]");
         ps.pool_paths = (ps.pool_paths + 31) / 32 * 32;
-        p.pool_paths = ps.pool_paths; p.pool_refill = o.pool_refill;
+        p.pool_patience = (ps.async && o.pool_refill > 0) ? o.pool_refill : 16;   /* experiments: --refill doubles as the patience of the barrier-free form */ p.pool_paths = ps.pool_paths; p.pool_refill = o.pool_refill < 0 ? 0 : (o.pool_refill == 0 ? 0 : std::min(31, o.pool_refill));   // default: off until measured
         int occ = 0, regs = 0, smem = 0;
         CU(pool_query(ps, &occ, &regs, &smem));
         if (occ < 1) return fail(ctx, MORT_ERR_ARG, "mort_render: a pool of " + std::to_string(ps.pool_paths) + " paths (" + std::to_string(smem) + " B) does not fit in a block's shared memory");
@@ -370,9 +371,10 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         ctx->stats.threads_per_block = 128; ctx->stats.blocks_per_sm = 8; ctx->stats.staged_nodes = 0; ctx->stats.regs_per_thread = 0;
     } else return fail(ctx, MORT_ERR_ARG, "mort_render: unknown mode");
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    unsigned long long cnt[2] = {0, 0};
+    unsigned long long cnt[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (cnt[2] != 0) return fail(ctx, MORT_ERR_CUDA, "mort_render: the block wavefront's scheduler watchdog tripped (a warp waited for work for seconds): frame incomplete");
     float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.reserved0 = (int32_t)sizeof(FrameParams);      // bytes of kernel parameters that go host->device per frame
     ctx->stats.last_render_ms = ms; ctx->stats.last_segments = cnt[0]; ctx->stats.last_samples = cnt[1]; ctx->stats.last_kernel_launches = launches;

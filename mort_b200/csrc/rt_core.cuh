@@ -327,8 +327,90 @@ MORT_HD float safe_rcp_dir(float d) {
     return 1.0f / a;
 }
 
+// Traversal of the 4-wide BVH as a resumable state machine: per-ray constants + current node + stack depth.  closest_hit()
+// below runs it to completion for one ray; the block wavefront's trace phase (pool.cu) runs it in bursts and hands lanes
+// whose ray has finished a new ray while their neighbours are still traversing.
+struct Trav {
+    float idx, idy, idz, oix, oiy, oiz;                 // 1 / d and o / d per axis: a slab plane is one FMA
+    int nxo, nyo, nzo;                                   // float offsets of the ray's near-plane rows inside a Bvh4Node (far = 12/20/28 - near)
+    uint32_t cur;                                        // node index | leaf word | MORT_CHILD_EMPTY = finished
+    int sp;
+};
+MORT_HD void trav_begin(Trav& T, const Ray& r) {
+    T.idx = safe_rcp_dir(r.d.x); T.idy = safe_rcp_dir(r.d.y); T.idz = safe_rcp_dir(r.d.z);
+    T.oix = r.o.x * T.idx; T.oiy = r.o.y * T.idy; T.oiz = r.o.z * T.idz;
+    // per-ray octant: which of the node's lo/hi planes is the entry ("near") plane on each axis.  Picking the
+    // rows by address replaces 12 of the 18 min/max per child (float offsets into Bvh4Node: lo rows at 0/4/8, hi at 12/16/20).
+    T.nxo = T.idx < 0.f ? 12 : 0; T.nyo = T.idy < 0.f ? 16 : 4; T.nzo = T.idz < 0.f ? 20 : 8;
+    T.cur = 0; T.sp = 0;                                 // root
+}
+// entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit
+MORT_HD uint32_t trav_pop(Trav& T, const StackEntry* stack, float best_t) {
+    uint32_t next = MORT_CHILD_EMPTY;
+    while (T.sp > 0 && next == MORT_CHILD_EMPTY) { T.sp--; const StackEntry e = stack[T.sp]; if (e.t <= best_t) next = e.child; }
+    return next;
+}
+// one internal node: slab-test its 4 children, continue with the nearest hit child, push the others
 // kStaged: the first n_staged nodes (breadth-first prefix = top levels) are read from a shared-memory copy,
 // the rest from global memory, through generic 128-bit loads; otherwise every node is a read-only LDG.128.
+template <bool kStaged>
+MORT_HD void trav_node(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, Trav& T, StackEntry* stack, float tmin, float best_t) {
+    MORT_COUNT(node_steps, 1);
+    const uint32_t cur = T.cur;
+    const int nxo = T.nxo, nyo = T.nyo, nzo = T.nzo, fxo = 12 - nxo, fyo = 20 - nyo, fzo = 28 - nzo;
+    const float idx = T.idx, idy = T.idy, idz = T.idz, oix = T.oix, oiy = T.oiy, oiz = T.oiz;
+    F4 nx, ny, nz, fx, fy, fz, chf;
+#if defined(__CUDA_ARCH__)
+    if (kStaged) {
+        // generic 128-bit loads: the pointer may be shared or global
+        const float* n = reinterpret_cast<const float*>(((int)cur < n_staged ? staged : sc.nodes) + cur);
+        float4 a0 = *reinterpret_cast<const float4*>(n + nxo), a1 = *reinterpret_cast<const float4*>(n + nyo), a2 = *reinterpret_cast<const float4*>(n + nzo);
+        float4 a3 = *reinterpret_cast<const float4*>(n + fxo), a4 = *reinterpret_cast<const float4*>(n + fyo), a5 = *reinterpret_cast<const float4*>(n + fzo);
+        float4 a6 = *reinterpret_cast<const float4*>(n + 24);
+        nx = F4{a0.x, a0.y, a0.z, a0.w}; ny = F4{a1.x, a1.y, a1.z, a1.w}; nz = F4{a2.x, a2.y, a2.z, a2.w};
+        fx = F4{a3.x, a3.y, a3.z, a3.w}; fy = F4{a4.x, a4.y, a4.z, a4.w}; fz = F4{a5.x, a5.y, a5.z, a5.w}; chf = F4{a6.x, a6.y, a6.z, a6.w};
+    } else
+#endif
+    {
+        const float* n = reinterpret_cast<const float*>(sc.nodes + cur);
+        nx = ld4(n + nxo); ny = ld4(n + nyo); nz = ld4(n + nzo); fx = ld4(n + fxo); fy = ld4(n + fyo); fz = ld4(n + fzo); chf = ld4(n + 24);
+    }
+    (void)staged; (void)n_staged;
+    float tn[4]; uint32_t cw[4] = {(uint32_t)f2i_bits(chf.x), (uint32_t)f2i_bits(chf.y), (uint32_t)f2i_bits(chf.z), (uint32_t)f2i_bits(chf.w)};
+    const float nxa[4] = {nx.x, nx.y, nx.z, nx.w}, nya[4] = {ny.x, ny.y, ny.z, ny.w}, nza[4] = {nz.x, nz.y, nz.z, nz.w};
+    const float fxa[4] = {fx.x, fx.y, fx.z, fx.w}, fya[4] = {fy.x, fy.y, fy.z, fy.w}, fza[4] = {fz.x, fz.y, fz.z, fz.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float tnear = fmaxf(fmaxf(fmaf(nxa[k], idx, -oix), fmaf(nya[k], idy, -oiy)), fmaxf(fmaf(nza[k], idz, -oiz), tmin));
+        float tfar = fminf(fminf(fmaf(fxa[k], idx, -oix), fmaf(fya[k], idy, -oiy)), fminf(fmaf(fza[k], idz, -oiz), best_t));
+        bool h = tnear <= tfar;                         // empty slots carry an inverted box (lo = +inf, hi = -inf): never hit
+        tn[k] = h ? tnear : INFINITY;
+        cw[k] = h ? cw[k] : MORT_CHILD_EMPTY;
+    }
+#define MORT_CSWAP(i, j) { bool sw = tn[j] < tn[i]; float ta = sw ? tn[j] : tn[i], tb = sw ? tn[i] : tn[j]; uint32_t ca = sw ? cw[j] : cw[i], cb = sw ? cw[i] : cw[j]; tn[i] = ta; tn[j] = tb; cw[i] = ca; cw[j] = cb; }
+    // Only the nearest hit is brought to slot 0 (3 comparators); the other hits are pushed in slot order and
+    // culled by their entry distance when popped.  Measured against the full 5-comparator sort
+    // (profiles/r01_ab_variants2.jsonl): scene 1 +3.6 %, 1 M-sphere field +4.5 %, scene 8 +1 % — most node
+    // visits hit at most two children, where the two orders coincide.
+    MORT_CSWAP(0, 1) MORT_CSWAP(2, 3) MORT_CSWAP(0, 2)
+#undef MORT_CSWAP
+    // push far-to-near, continue with the nearest; nothing hit -> pop
+    int sp = T.sp;
+#pragma unroll
+    for (int k = 3; k >= 1; k--)
+        if (cw[k] != MORT_CHILD_EMPTY) { MORT_COUNT(pushes, 1); MORT_COUNT(push_at[sp], 1); StackEntry e; e.child = cw[k]; e.t = tn[k]; stack[sp] = e; sp++; }   // depth * 3 <= MORT_STACK is checked at commit
+    T.sp = sp;
+    uint32_t next = cw[0];
+    if (next == MORT_CHILD_EMPTY) next = trav_pop(T, stack, best_t);
+    T.cur = next;
+}
+// one leaf: exact primitive tests, then the next stack entry
+MORT_HD void trav_leaf(const DeviceScene& sc, Trav& T, const StackEntry* stack, const Ray& r, float tmin, Hit& best, int order_lo, int order_hi) {
+    MORT_COUNT(leaf_visits, 1); MORT_COUNT(prim_tests, ((T.cur >> 27) & 7u) + 1);
+    leaf_intersect(sc, T.cur, r, tmin, best, order_lo, order_hi);
+    T.cur = trav_pop(T, stack, best.t);
+}
+
 // kLinear: -1 = sc.linear decides at run time, 1 / 0 = the caller's kernel is specialised for linear-scan / tree scenes
 // (the other traversal is not even compiled into it).
 template <bool kStaged, int kLinear = -1>
@@ -337,76 +419,16 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
     best.t = tmax; best.prim = MORT_PRIM_NONE; best.a = best.b = 0.f;
     if (sc.empty) return false;
     if (kLinear == 1 || (kLinear < 0 && sc.linear)) { closest_hit_linear(sc, r, tmin, best, order_lo, order_hi); return best.prim != MORT_PRIM_NONE; }
-    const float idx = safe_rcp_dir(r.d.x), idy = safe_rcp_dir(r.d.y), idz = safe_rcp_dir(r.d.z);
-    const float oix = r.o.x * idx, oiy = r.o.y * idy, oiz = r.o.z * idz;
-    // per-ray octant: which of the node's lo/hi planes is the entry ("near") plane on each axis.  Picking the
-    // rows by address replaces 12 of the 18 min/max per child (float offsets into Bvh4Node: lo rows at 0/4/8, hi at 12/16/20).
-    const int nxo = idx < 0.f ? 12 : 0, nyo = idy < 0.f ? 16 : 4, nzo = idz < 0.f ? 20 : 8;
-    const int fxo = 12 - nxo, fyo = 20 - nyo, fzo = 28 - nzo;
+    Trav T; trav_begin(T, r);
     StackEntry stack[MORT_STACK];                        // one 64-bit local store / load per push / pop
-    int sp = 0;
-    uint32_t cur = 0;                                   // root; MORT_CHILD_EMPTY (leaf bit set) = traversal finished
     // "while-while" (Aila & Laine): an inner loop that only descends internal nodes, then one leaf step.  The
     // loops are structured (no continue / break across them) so the compiler's convergence barriers sit at
     // the loop exits: the warp's lanes test nodes together and intersect leaves together instead of drifting
     // apart for the whole traversal (lane utilisation 6.6/32 with the former single loop).
     MORT_COUNT(queries, 1);
-    while (cur != MORT_CHILD_EMPTY) {
-        while (!(cur & MORT_LEAF_BIT)) {
-            MORT_COUNT(node_steps, 1);
-            F4 nx, ny, nz, fx, fy, fz, chf;
-#if defined(__CUDA_ARCH__)
-            if (kStaged) {
-                // generic 128-bit loads: the pointer may be shared or global
-                const float* n = reinterpret_cast<const float*>(((int)cur < n_staged ? staged : sc.nodes) + cur);
-                float4 a0 = *reinterpret_cast<const float4*>(n + nxo), a1 = *reinterpret_cast<const float4*>(n + nyo), a2 = *reinterpret_cast<const float4*>(n + nzo);
-                float4 a3 = *reinterpret_cast<const float4*>(n + fxo), a4 = *reinterpret_cast<const float4*>(n + fyo), a5 = *reinterpret_cast<const float4*>(n + fzo);
-                float4 a6 = *reinterpret_cast<const float4*>(n + 24);
-                nx = F4{a0.x, a0.y, a0.z, a0.w}; ny = F4{a1.x, a1.y, a1.z, a1.w}; nz = F4{a2.x, a2.y, a2.z, a2.w};
-                fx = F4{a3.x, a3.y, a3.z, a3.w}; fy = F4{a4.x, a4.y, a4.z, a4.w}; fz = F4{a5.x, a5.y, a5.z, a5.w}; chf = F4{a6.x, a6.y, a6.z, a6.w};
-            } else
-#endif
-            {
-                const float* n = reinterpret_cast<const float*>(sc.nodes + cur);
-                nx = ld4(n + nxo); ny = ld4(n + nyo); nz = ld4(n + nzo); fx = ld4(n + fxo); fy = ld4(n + fyo); fz = ld4(n + fzo); chf = ld4(n + 24);
-            }
-            (void)staged; (void)n_staged;
-            float tn[4]; uint32_t cw[4] = {(uint32_t)f2i_bits(chf.x), (uint32_t)f2i_bits(chf.y), (uint32_t)f2i_bits(chf.z), (uint32_t)f2i_bits(chf.w)};
-            const float nxa[4] = {nx.x, nx.y, nx.z, nx.w}, nya[4] = {ny.x, ny.y, ny.z, ny.w}, nza[4] = {nz.x, nz.y, nz.z, nz.w};
-            const float fxa[4] = {fx.x, fx.y, fx.z, fx.w}, fya[4] = {fy.x, fy.y, fy.z, fy.w}, fza[4] = {fz.x, fz.y, fz.z, fz.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                float tnear = fmaxf(fmaxf(fmaf(nxa[k], idx, -oix), fmaf(nya[k], idy, -oiy)), fmaxf(fmaf(nza[k], idz, -oiz), tmin));
-                float tfar = fminf(fminf(fmaf(fxa[k], idx, -oix), fmaf(fya[k], idy, -oiy)), fminf(fmaf(fza[k], idz, -oiz), best.t));
-                bool h = tnear <= tfar;                         // empty slots carry an inverted box (lo = +inf, hi = -inf): never hit
-                tn[k] = h ? tnear : INFINITY;
-                cw[k] = h ? cw[k] : MORT_CHILD_EMPTY;
-            }
-#define MORT_CSWAP(i, j) { bool sw = tn[j] < tn[i]; float ta = sw ? tn[j] : tn[i], tb = sw ? tn[i] : tn[j]; uint32_t ca = sw ? cw[j] : cw[i], cb = sw ? cw[i] : cw[j]; tn[i] = ta; tn[j] = tb; cw[i] = ca; cw[j] = cb; }
-            // Only the nearest hit is brought to slot 0 (3 comparators); the other hits are pushed in slot order and
-            // culled by their entry distance when popped.  Measured against the full 5-comparator sort
-            // (profiles/r01_ab_variants2.jsonl): scene 1 +3.6 %, 1 M-sphere field +4.5 %, scene 8 +1 % — most node
-            // visits hit at most two children, where the two orders coincide.
-            MORT_CSWAP(0, 1) MORT_CSWAP(2, 3) MORT_CSWAP(0, 2)
-#undef MORT_CSWAP
-            // push far-to-near, continue with the nearest; nothing hit -> pop
-#pragma unroll
-            for (int k = 3; k >= 1; k--)
-                if (cw[k] != MORT_CHILD_EMPTY) { MORT_COUNT(pushes, 1); MORT_COUNT(push_at[sp], 1); StackEntry e; e.child = cw[k]; e.t = tn[k]; stack[sp] = e; sp++; }   // depth * 3 <= MORT_STACK is checked at commit
-            uint32_t next = cw[0];
-            if (next == MORT_CHILD_EMPTY) {
-                // entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit
-                while (sp > 0 && next == MORT_CHILD_EMPTY) { sp--; const StackEntry e = stack[sp]; if (e.t <= best.t) next = e.child; }
-            }
-            cur = next;
-        }
-        if (cur != MORT_CHILD_EMPTY) {
-            MORT_COUNT(leaf_visits, 1); MORT_COUNT(prim_tests, ((cur >> 27) & 7u) + 1);
-            leaf_intersect(sc, cur, r, tmin, best, order_lo, order_hi);
-            uint32_t next = MORT_CHILD_EMPTY;
-            while (sp > 0 && next == MORT_CHILD_EMPTY) { sp--; const StackEntry e = stack[sp]; if (e.t <= best.t) next = e.child; }
-            cur = next;
-        }
+    while (T.cur != MORT_CHILD_EMPTY) {
+        while (!(T.cur & MORT_LEAF_BIT)) trav_node<kStaged>(sc, staged, n_staged, T, stack, tmin, best.t);
+        if (T.cur != MORT_CHILD_EMPTY) trav_leaf(sc, T, stack, r, tmin, best, order_lo, order_hi);
     }
     return best.prim != MORT_PRIM_NONE;
 }
@@ -535,13 +557,9 @@ MORT_HD_NOINLINE MediaOut media_scan(const DeviceScene& sc, Ray r, float tmin, f
 #define MORT_PRIM_MEDIUM 0xFFFFFFFEu
 struct SegHit { Hit h; };                         // h.prim == MORT_PRIM_NONE: miss; == MORT_PRIM_MEDIUM: medium event, h.a = medium index bits
 
-template <bool kStaged, int kLinear = -1>
-MORT_HD void segment_trace(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, const Ray& r, Rng& g, SegHit& out) {
+// everything of world::hit after the surfaces: media clipped to the closest surface, then (rare) the post-media leaves
+MORT_HD void segment_finish(const DeviceScene& sc, const Ray& r, Rng& g, bool any, Hit h, SegHit& out) {
     const float tmin = 0.001f;
-    Hit h;
-    // one traversal; only when media and top-level lists coexist (no shipped scene) is the visit-order window
-    // narrower than everything and a second, out-of-line pass needed
-    bool any = closest_hit<kStaged, kLinear>(sc, staged, n_staged, r, tmin, INFINITY, h, 0, sc.two_pass ? sc.post_media_order : 0x7FFFFFFF);
     float closest = any ? h.t : INFINITY;
     int med = -1; float tmed = 0.f;
     if (sc.n_media > 0) {                                   // cold for most scenes: kept out of line
@@ -556,6 +574,14 @@ MORT_HD void segment_trace(const DeviceScene& sc, const Bvh4Node* staged, int n_
     if (med >= 0) { h.t = tmed; h.prim = MORT_PRIM_MEDIUM; h.a = i2f_bits(med); h.b = 0.f; }
     else if (!any) { h.prim = MORT_PRIM_NONE; }
     out.h = h;
+}
+template <bool kStaged, int kLinear = -1>
+MORT_HD void segment_trace(const DeviceScene& sc, const Bvh4Node* staged, int n_staged, const Ray& r, Rng& g, SegHit& out) {
+    Hit h;
+    // one traversal; only when media and top-level lists coexist (no shipped scene) is the visit-order window
+    // narrower than everything and a second, out-of-line pass needed
+    const bool any = closest_hit<kStaged, kLinear>(sc, staged, n_staged, r, 0.001f, INFINITY, h, 0, sc.two_pass ? sc.post_media_order : 0x7FFFFFFF);
+    segment_finish(sc, r, g, any, h, out);
 }
 MORT_HD int seghit_material(const DeviceScene& sc, const SegHit& sh) {     // material gid of the winner (-1: none)
     if (sh.h.prim == MORT_PRIM_NONE) return -1;

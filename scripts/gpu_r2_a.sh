@@ -4,7 +4,7 @@
 set -u
 ROOT=$(pwd); OUT=$ROOT/gpurun_out/r2a; mkdir -p $OUT
 export PYTHONUNBUFFERED=1
-echo "== pytest pool"; timeout 900 python -m pytest tests/test_gpu_pool.py -q -x --timeout 300 2>&1 | tail -15 | tee $OUT/pytest_pool.txt
+echo "== diag"; timeout 300 python scripts/diag_pool_vs_mega.py 2>&1 | tail -12
 M=mort_b200/mort
 run() { tag=$1; shift; echo -n "$tag: "; timeout 120 $M "$@" 2>&1 | tail -1 | tee -a $OUT/ab.jsonl | cut -c1-200; echo "  # $tag :: $*" >> $OUT/ab.jsonl; }
 for cfg in "8 --width 800 --spp 256 --depth 40" "6 --width 600 --spp 256 --depth 50" "1" "1 --field 500 --width 1920 --aspect 1.7777778 --spp 64 --depth 50"; do
@@ -18,4 +18,6 @@ for cfg in "8 --width 800 --spp 256 --depth 40" "6 --width 600 --spp 256 --depth
   run pool_256x3_768 $cfg --frames 2 --mode pool --tpb 256 --bps 3 --pool 768
   run pool_256x2_1024 $cfg --frames 2 --mode pool --tpb 256 --bps 2 --pool 1024
   run pool_512x1_2048 $cfg --frames 2 --mode pool --tpb 512 --bps 1 --pool 2048
+  for rf in 4 8 16 24; do run pool_512x2_1024_refill$rf $cfg --frames 2 --mode pool --tpb 512 --bps 2 --pool 1024 --refill $rf; done
+  run pool_256x2_1024_refill8 $cfg --frames 2 --mode pool --tpb 256 --bps 2 --pool 1024 --refill 8
 done

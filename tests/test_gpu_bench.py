@@ -24,11 +24,14 @@ def _run(*args):
 
 def test_own_arm_json_line():
     d = _run("--steps", "2", "--warmup", "3", "--spp", "64")
-    assert BASE_KEYS | {"roofline"} <= set(d)
+    assert BASE_KEYS | {"roofline", "per_config"} <= set(d)
+    assert d["config"]["scene"] == 8 and d["config"]["width"] == 800 and d["kernel"]["bvh_nodes"] > 1, "the headline must run the BVH traversal (BASELINE config 3)"
+    assert {"config 1", "config 2", "config 4"} <= set(d["per_config"]), d["per_config"]
+    assert all(d["per_config"][k]["value"] > 0 for k in ("config 1", "config 2", "config 4"))
     assert d["metric"] == "Msamples/s" and d["unit"] == "Msamples/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3
     assert d["higher_is_better"] is True and d["dtype"] == "f32" and d["vs_baseline"] is None and "workload" in d["config"]
     assert d["value"] > 0 and d["gpu_launches"] >= 2 * 2
-    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["d2h_bytes_per_step"] == 600 * 600 * 4
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["d2h_bytes_per_step"] == 800 * 800 * 4
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"]) and 0 < d["roofline"]["frac"] < 1.2
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
