@@ -102,8 +102,8 @@ int mort_commit(mort_ctx* ctx);
 /* Three schedulers over the same per-ray code, Philox stream and estimator:
  *   MEGAKERNEL  persistent warps, a lane owns a path from camera to termination (render.cu)
  *   WAVEFRONT   one kernel per stage over SoA queues in HBM (wavefront.cu)
- *   POOL        block wavefront: one persistent kernel, every thread block alternates trace / shade phases over a pool of
- *               paths in its shared memory, shading sorted by material class (pool.cu)
+ *   POOL        block wavefront: one persistent kernel, every thread block alternates trace / (classify /) shade phases over a
+ *               pool of paths in its shared memory, shading sorted by material class (pool.cu)
  * MEGAKERNEL and POOL accumulate exactly (integers) and render bit-identical frames. */
 enum { MORT_MODE_MEGAKERNEL = 0, MORT_MODE_WAVEFRONT = 1, MORT_MODE_POOL = 2 };
 typedef struct {
@@ -122,7 +122,7 @@ typedef struct {
     int32_t pool_paths;            /* MORT_MODE_POOL: paths per thread-block pool (0 = default 1024; 88 B of shared memory each) */
     int32_t pool_refill;           /* MORT_MODE_POOL, tree scenes: lanes whose ray left the tree take a new one as soon as this many lanes of
                                       their warp are idle (1..31; 0 = default, -1 = off: fixed 32-ray chunks) */
-    int32_t pool_sync;             /* MORT_MODE_POOL: 1 = the phased form (trace | __syncthreads | shade | __syncthreads), 0 = barrier-free queues (default) */
+    int32_t pool_flags;            /* MORT_MODE_POOL experiments: bit 0 = barrier between trace and classify, bit 1 = force the overlapped form (0 = by scene class) */
 } mort_render_opts;
 void mort_default_render_opts(mort_render_opts* o);
 

@@ -215,6 +215,7 @@ int mort_commit(mort_ctx* ctx) {
     CU(ctx->arena.upload(f.nodes, &d.nodes)); d.n_nodes = (int)f.nodes.size();
     CU(ctx->arena.upload(f.spheres, &d.spheres)); CU(ctx->arena.upload(f.sphere_info, &d.sphere_info)); d.n_spheres = (int)f.spheres.size();
     CU(ctx->arena.upload(f.quads, &d.quads)); d.n_quads = (int)f.quads.size();
+    CU(ctx->arena.upload(f.sphere_cls, &d.sphere_cls)); CU(ctx->arena.upload(f.quad_cls, &d.quad_cls));
     CU(ctx->arena.upload(f.instances, &d.instances)); d.n_instances = (int)f.instances.size();
     CU(ctx->arena.upload(f.materials, &d.materials)); d.n_materials = (int)f.materials.size();
     CU(ctx->arena.upload(f.textures, &d.textures)); d.n_textures = (int)f.textures.size();
@@ -346,11 +347,21 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         }
         p.accum = nullptr; p.accum_exact = target;
         p.work64 = ctx->d_work64; p.total_samples = (unsigned long long)p.n_pixels * (unsigned long long)p.n_subset;
-        PoolShape ps; ps.threads = o.threads_per_block > 0 ? o.threads_per_block : 512; ps.min_blocks = o.blocks_per_sm > 0 ? o.blocks_per_sm : 2;
-        ps.pool_paths = o.pool_paths > 0 ? o.pool_paths : 1024; ps.async = o.pool_sync ? 0 : 1;
+        // Block shape, pool size and trace-phase form per scene class, from same-box A/B runs (profiles/r02_pool_ab.md):
+        //   linear-scan scenes (<= 40 leaves)        2 blocks x 512 threads, 1024 paths each, generic kernel
+        //   tree scenes without media                2 blocks x 512 threads, 1024 paths each, fixed 32-ray trace chunks
+        //   tree scenes with media                   1 block x 640 threads (96 registers), 2048 paths, lane refill + classify pass
+        //                                            that starts while the slowest rays are still in the tree
+        const bool tree = !ctx->flat.linear, media = !ctx->flat.media.empty();
+        PoolShape ps; ps.tree = tree ? 1 : 0;
+        ps.threads = o.threads_per_block > 0 ? o.threads_per_block : (tree && media ? 640 : 512);
+        ps.min_blocks = o.blocks_per_sm > 0 ? o.blocks_per_sm : (ps.threads >= 640 ? 1 : 2);
+        ps.pool_paths = o.pool_paths > 0 ? o.pool_paths : (ps.min_blocks >= 2 ? 1024 : 2048);
         if (ps.pool_paths < 32 || ps.pool_paths > 32736) return fail(ctx, MORT_ERR_ARG, "mort_render: pool_paths must be in [32, 32736]");
         ps.pool_paths = (ps.pool_paths + 31) / 32 * 32;
-        p.pool_patience = (ps.async && o.pool_refill > 0) ? o.pool_refill : 16;   /* experiments: --refill doubles as the patience of the barrier-free form */ p.pool_paths = ps.pool_paths; p.pool_refill = o.pool_refill < 0 ? 0 : (o.pool_refill == 0 ? 0 : std::min(31, o.pool_refill));   // default: off until measured
+        p.pool_paths = ps.pool_paths;
+        p.pool_refill = o.pool_refill < 0 ? 0 : (o.pool_refill == 0 ? (tree && media ? 16 : 0) : std::min(31, o.pool_refill));
+        p.pool_overlap = (o.pool_flags & 1) ? 0 : ((o.pool_flags & 2) ? 1 : (media && ps.min_blocks == 1 ? 1 : 0));
         int occ = 0, regs = 0, smem = 0;
         CU(pool_query(ps, &occ, &regs, &smem));
         if (occ < 1) return fail(ctx, MORT_ERR_ARG, "mort_render: a pool of " + std::to_string(ps.pool_paths) + " paths (" + std::to_string(smem) + " B) does not fit in a block's shared memory");

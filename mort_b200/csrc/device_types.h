@@ -39,6 +39,9 @@ struct alignas(32) QuadRec {
 };
 
 enum { INST_OP_TRANSLATE = 1, INST_OP_ROTATE_Y = 2 };
+// Shading queues of the block wavefront (pool.cu).  COLD = a diffuse material whose texture tree contains a noise or image
+// texture (Perlin turbulence in double precision / texel fetches): kept apart so those warps run converged instead of 4 lanes at a time.
+enum { SHADE_TERMINAL = 0, SHADE_DIFFUSE = 1, SHADE_METAL = 2, SHADE_DIELECTRIC = 3, SHADE_DIFFUSE_COLD = 4, SHADE_CLASSES = 5 };
 #define MORT_INSTANCE_OPS 7                 // 16 + 7 * 16 = 128 B; only the first nops rows are ever read
 struct alignas(32) Instance {
     int32_t nops; int32_t pad[3];           // up to MORT_INSTANCE_OPS nested wrappers, outermost first
@@ -72,7 +75,7 @@ struct alignas(32) LightPrim {
 struct alignas(32) Medium {
     double neg_inv_density;
     int32_t mat_gid; int32_t first, count;  // range in boundary[]
-    int32_t obj_idx; int32_t pad[2];
+    int32_t obj_idx; int32_t cls; int32_t pad;   // cls: shade class of the phase material
 };
 struct alignas(32) BoundaryPrim {           // same geometry as SphereGeom / QuadRec, one union-sized record
     int32_t type; int32_t inst; int32_t pad[2];
@@ -89,6 +92,7 @@ struct DeviceScene {
     const Bvh4Node* nodes; int32_t n_nodes;
     const SphereGeom* spheres; const PrimInfo* sphere_info; int32_t n_spheres;
     const QuadRec* quads; int32_t n_quads;
+    const uint8_t* sphere_cls; const uint8_t* quad_cls;   // shade class (SHADE_*) of each record's material: one byte decides a hit's shading queue
     const Instance* instances; int32_t n_instances;
     const Material* materials; int32_t n_materials;
     const Texture* textures; int32_t n_textures;

@@ -352,6 +352,29 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
             uint32_t first = w & 0x07FFFFFFu;
             n.child[k] = (w & ~0x07FFFFFFu) | (uint32_t)rec_index[first];
         }
+    // ---- shade class per record (and per medium): the block wavefront's queue for a hit, decided by one byte ----
+    auto tex_cold = [&](int gid) {
+        for (int guard = 0, stack_n = 1, stack[64] = {gid}; stack_n > 0 && guard < 64; guard++) {
+            const int t = stack[--stack_n];
+            if (t < 0 || t >= (int)out.textures.size()) continue;
+            const Texture& T = out.textures[t];
+            if (T.type == MORT_TEX_IMAGE || T.type == MORT_TEX_NOISE) return true;
+            if (T.type == MORT_TEX_CHECKER && stack_n + 2 <= 64) { stack[stack_n++] = T.even_gid; stack[stack_n++] = T.odd_gid; }
+        }
+        return false;
+    };
+    auto shade_class = [&](int gid) -> uint8_t {
+        if (gid < 0 || gid >= (int)out.materials.size()) return SHADE_TERMINAL;
+        const Material& M = out.materials[gid];
+        if (M.type == MORT_MAT_LAMBERTIAN || M.type == MORT_MAT_ISOTROPIC) return tex_cold(M.tex_gid) ? SHADE_DIFFUSE_COLD : SHADE_DIFFUSE;
+        if (M.type == MORT_MAT_METAL) return SHADE_METAL;
+        if (M.type == MORT_MAT_DIELECTRIC) return SHADE_DIELECTRIC;
+        return SHADE_TERMINAL;                                   // diffuse_light, unknown tags
+    };
+    out.sphere_cls.resize(out.sphere_info.size()); out.quad_cls.resize(out.quads.size());
+    for (size_t i = 0; i < out.sphere_info.size(); i++) out.sphere_cls[i] = shade_class(out.sphere_info[i].mat_gid);
+    for (size_t i = 0; i < out.quads.size(); i++) out.quad_cls[i] = shade_class(out.quads[i].mat_gid);
+    for (Medium& M : out.media) M.cls = shade_class(M.mat_gid);
     camera_params(s.cam, out.cam);
     return true;
 }

@@ -25,6 +25,7 @@ struct FlatScene {
     std::vector<Bvh4Node> nodes;
     std::vector<SphereGeom> spheres; std::vector<PrimInfo> sphere_info;
     std::vector<QuadRec> quads;
+    std::vector<uint8_t> sphere_cls, quad_cls;   // SHADE_* per record
     std::vector<Instance> instances;
     std::vector<Material> materials;
     std::vector<Texture> textures;

@@ -22,7 +22,7 @@ static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [
 int main(int argc, char** argv) {
     if (argc < 2) return usage();                       // mort.cu:638-641
     int scene = atoi(argv[1]);
-    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = 0, mode = MORT_MODE_MEGAKERNEL, bps = 0, tpb = 0, field = 0, fieldcam = 0, pool = 0, refill = 0, gpus = 1, split = MORT_SPLIT_SAMPLE, pool_sync = 0;
+    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = 0, mode = MORT_MODE_MEGAKERNEL, bps = 0, tpb = 0, field = 0, fieldcam = 0, pool = 0, refill = 0, gpus = 1, split = MORT_SPLIT_SAMPLE, xflags = 0;
     float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr, load, dump, ckpt, text_in, text_out;
     bool accumulate = false, resume = false;
     for (int i = 2; i < argc; i++) {
@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
         else if (a == "--bps") bps = atoi(nx()); else if (a == "--tpb") tpb = atoi(nx());
         else if (a == "--field") field = atoi(nx()); else if (a == "--fieldcam") fieldcam = atoi(nx());
         else if (a == "--gpus") gpus = atoi(nx()); else if (a == "--split") { std::string m = nx(); split = m == "tile" ? MORT_SPLIT_TILE : MORT_SPLIT_SAMPLE; }
-        else if (a == "--pool") pool = atoi(nx()); else if (a == "--pool-sync") pool_sync = 1; else if (a == "--refill") refill = atoi(nx());
+        else if (a == "--pool") pool = atoi(nx()); else if (a == "--xflags") xflags = atoi(nx()); else if (a == "--refill") refill = atoi(nx());
         else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : m == "pool" ? MORT_MODE_POOL : MORT_MODE_MEGAKERNEL; }
         else return usage();
     }
@@ -59,7 +59,7 @@ int main(int argc, char** argv) {
         }
         mort_stats st; mort_get_stats(mort_group_ctx(g, 0), &st);
         std::vector<uint8_t> img((size_t)st.width * st.height * 4);
-        mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.blocks_per_sm = bps; o.threads_per_block = tpb; o.pool_paths = pool; o.pool_refill = refill; o.pool_sync = pool_sync;
+        mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.blocks_per_sm = bps; o.threads_per_block = tpb; o.pool_paths = pool; o.pool_refill = refill; o.pool_flags = xflags;
         double total = 0, coll = 0, kmin = 0; mort_group_stats gs; memset(&gs, 0, sizeof(gs));
         for (int f = 0; f < frames; f++) {
             o.frame = (uint32_t)f;
@@ -97,7 +97,7 @@ int main(int argc, char** argv) {
     mort_stats st; mort_get_stats(ctx, &st);
     std::vector<uint8_t> img((size_t)st.width * st.height * 4);
     std::vector<float> acc(hdr.empty() ? 0 : (size_t)st.width * st.height * 4);
-    mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.stage_nodes = stage; o.blocks_per_sm = bps; o.threads_per_block = tpb; o.pool_paths = pool; o.pool_refill = refill; o.pool_sync = pool_sync;
+    mort_render_opts o; mort_default_render_opts(&o); o.seed = seed; o.mode = mode; o.stage_nodes = stage; o.blocks_per_sm = bps; o.threads_per_block = tpb; o.pool_paths = pool; o.pool_refill = refill; o.pool_flags = xflags;
     double total = 0;
     uint32_t frames_total = 1;                         // frames averaged into the written image
     if (accumulate) {

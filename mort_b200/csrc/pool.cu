@@ -31,7 +31,7 @@ namespace mort {
 namespace {
 
 constexpr int kPoolWords = 19;                 // 32-bit words of state per path
-constexpr int kPoolLists = 6;                  // 16-bit slot lists per path: 2 live lists (ping-pong) + 4 class lists
+constexpr int kPoolLists = 3 + SHADE_CLASSES;  // 16-bit slot lists per path: 2 live lists (ping-pong), one list per shade class, the traced list
 
 // The pool is addressed as word k of path s = smem[k * np + s] straight off the extern array, so that every access
 // compiles to LDS / STS (pointers kept in a struct decayed to generic LD / ST).
@@ -41,7 +41,7 @@ enum { W_OX = 0, W_OY, W_OZ, W_DX, W_DY, W_DZ, W_TM,        // ray
        W_PIX, W_SMP, W_BLK, W_STAGE,                       // Philox counter words: pixel, sample, next block, this bounce's stage block
        W_HT, W_HPRIM, W_HA, W_HB };                        // hit
 static_assert(W_HB + 1 == kPoolWords, "pool layout");
-enum { L_LIVE0 = 0, L_LIVE1 = 1, L_CLS0 = 2 };             // 16-bit slot lists: 2 live lists (ping-pong) + 4 class lists
+enum { L_LIVE0 = 0, L_LIVE1 = 1, L_CLS0 = 2, L_DONE = 2 + SHADE_CLASSES };   // 16-bit slot lists: 2 live lists (ping-pong), the class lists, paths whose traversal is finished
 struct Pool {
     int np;
     __device__ __forceinline__ float& f(int k, unsigned s) const { return reinterpret_cast<float*>(pool_raw)[k * np + (int)s]; }
@@ -51,8 +51,9 @@ struct Pool {
 
 struct PoolCtl {
     unsigned t_n[2], t_head[2];                // live list: entries, chunk head
-    unsigned c_n[2][4], c_head[2];             // class lists: entries, chunk head
+    unsigned c_n[2][SHADE_CLASSES], c_head[2];             // class lists: entries, chunk head
     unsigned k_head[2];                        // classify pass: chunk head
+    unsigned d_n[2];                           // traced list: entries reserved
 };
 
 // warp-aggregated append to a shared-memory list (every lane of the warp must call it)
@@ -85,6 +86,7 @@ struct Lane { Path path; Rng g; };
 // Brings a lane to a path whose next segment must be traced: a path that reached the bounce limit or whose ray went NaN is
 // finished here (camera.cuh:161-163; render.cu's path_segment does the same checks before its closest-hit query), and a
 // lane without a path claims the frame's next camera sample.  Warp-convergent (ballots inside).  Returns "lane holds a live path".
+// (force-inlined on purpose: one out-of-line copy was measured 6-15 % slower on every scene, profiles/r02_pool_ab.md)
 __device__ __forceinline__ bool settle(const FrameParams& P, Lane& L, bool check, bool need_new, unsigned& n_smp) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -141,7 +143,7 @@ __device__ __forceinline__ bool shade_chunk(const FrameParams& P, const Pool& S,
         L.g.k0 = P.seed; L.g.k1 = P.frame; L.g.pixel = S.u(W_PIX, slot); L.g.sample = S.u(W_SMP, slot); L.g.block = S.u(W_BLK, slot);
         SegHit sh; sh.h.t = S.f(W_HT, slot); sh.h.prim = S.u(W_HPRIM, slot); sh.h.a = S.f(W_HA, slot); sh.h.b = S.f(W_HB, slot);
         R4 sb = {0.f, 0.f, 0.f, 0.f};
-        if (kClass == CLASS_DIFFUSE || kClass == CLASS_DIELECTRIC) {            // the bounce's stage block, reserved by the trace phase
+        if (kClass == CLASS_DIFFUSE || kClass == CLASS_DIFFUSE_COLD || kClass == CLASS_DIELECTRIC) {            // the bounce's stage block, reserved by the trace phase
             Rng sg = L.g; sg.block = S.u(W_STAGE, slot);
             sb = rng_block(sg);
         }
@@ -158,16 +160,17 @@ __device__ __forceinline__ bool shade_chunk(const FrameParams& P, const Pool& S,
 }
 
 // closest hit + media of one lane's path; returns its material class
+template <int kLinear>
 __device__ __forceinline__ int trace_lane(const FrameParams& P, const Pool& S, unsigned slot, unsigned& n_seg) {
     Ray r; load_ray(S, slot, r);
     Rng g; g.k0 = P.seed; g.k1 = P.frame; g.pixel = S.u(W_PIX, slot); g.sample = S.u(W_SMP, slot); g.block = S.u(W_BLK, slot);
     const uint32_t stage = g.block; g.block++;        // canonical stream: the stage block precedes the segment's media draws
     SegHit sh;
-    segment_trace<false>(P.sc, nullptr, 0, r, g, sh);
+    segment_trace<false, kLinear>(P.sc, nullptr, 0, r, g, sh);
     n_seg++;
     S.u(W_BLK, slot) = g.block; S.u(W_STAGE, slot) = stage;
     S.f(W_HT, slot) = sh.h.t; S.u(W_HPRIM, slot) = sh.h.prim; S.f(W_HA, slot) = sh.h.a; S.f(W_HB, slot) = sh.h.b;
-    return material_class(P.sc, seghit_material(P.sc, sh));
+    return seghit_class(P.sc, sh);
 }
 
 // TRACE phase for tree scenes with lane refill (Aila & Laine's persistent while-while, inside one block).  With fixed
@@ -180,7 +183,7 @@ __device__ __forceinline__ int trace_lane(const FrameParams& P, const Pool& S, u
 //                  only the idle lanes active, so every instruction in it is paid at low utilisation.
 //   classify       everything else of the segment (media, the rare second pass, Philox block bookkeeping, material-class
 //                  split) for 32 paths at a time after a barrier: uniform work, all lanes busy.
-__device__ __forceinline__ void trace_refill(const FrameParams& P, const Pool& S, PoolCtl& ctl, int par, unsigned nt, int want) {
+__device__ __forceinline__ void trace_refill(const FrameParams& P, const Pool& S, PoolCtl& ctl, int par, unsigned nt, int want, bool overlap) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -196,9 +199,18 @@ __device__ __forceinline__ void trace_refill(const FrameParams& P, const Pool& S
         const bool fin = have && T.cur == MORT_CHILD_EMPTY;
         const unsigned busy = __ballot_sync(full, have && !fin);
         if (busy == 0u || (!exhausted && 32 - __popc(busy) >= want)) {
-            if (fin) {
-                S.f(W_HT, slot) = best.t; S.u(W_HPRIM, slot) = best.prim; S.f(W_HA, slot) = best.a; S.f(W_HB, slot) = best.b;
-                have = false;
+            const unsigned fm = __ballot_sync(full, fin);
+            if (!overlap) {
+                if (fin) { S.f(W_HT, slot) = best.t; S.u(W_HPRIM, slot) = best.prim; S.f(W_HA, slot) = best.a; S.f(W_HB, slot) = best.b; have = false; }
+            } else if (fm != 0u) {
+                // hits go to the pool, the slots to the traced list: the classify pass starts on them while other warps still trace
+                if (fin) { S.f(W_HT, slot) = best.t; S.u(W_HPRIM, slot) = best.prim; S.f(W_HA, slot) = best.a; S.f(W_HB, slot) = best.b; }
+                __threadfence_block();
+                const int fl = __ffs(fm) - 1;
+                unsigned db = 0;
+                if (lane == fl) db = atomicAdd(&ctl.d_n[par], (unsigned)__popc(fm));
+                db = __shfl_sync(full, db, fl);
+                if (fin) { reinterpret_cast<volatile uint16_t*>(S.list(L_DONE))[db + (unsigned)__popc(fm & lt)] = (uint16_t)slot; have = false; }
             }
             if (!exhausted) {
                 const unsigned need = ~busy;                            // every lane that is not traversing
@@ -239,10 +251,13 @@ __device__ __forceinline__ int classify_lane(const FrameParams& P, const Pool& S
     } else sh.h = h;
     n_seg++;
     S.u(W_BLK, slot) = g.block; S.u(W_STAGE, slot) = stage;
-    return material_class(P.sc, seghit_material(P.sc, sh));
+    return seghit_class(P.sc, sh);
 }
 
-template <int NT, int MINB>
+// kTree: built for tree scenes only (no lockstep linear scan in it: scene 1 +6 %, 1 M-sphere field +7 % over the generic kernel);
+// !kTree: the GENERIC kernel (run-time flag, both closest-hit codes compiled in), used for linear-scan scenes — a kernel with the
+// linear scan alone is allocated worse by ptxas and loses 10 % on Cornell (profiles/r02_pool_ab.md; round 1 saw the same).
+template <int NT, int MINB, bool kTree>
 __global__ void __launch_bounds__(NT, MINB) pool_kernel(const __grid_constant__ FrameParams P) {
     __shared__ PoolCtl ctl;
     const int NP = P.pool_paths;
@@ -252,6 +267,7 @@ __global__ void __launch_bounds__(NT, MINB) pool_kernel(const __grid_constant__ 
     unsigned n_seg = 0, n_smp = 0;
 
     if (threadIdx.x < (int)(sizeof(PoolCtl) / 4)) reinterpret_cast<unsigned*>(&ctl)[threadIdx.x] = 0u;
+    for (int i = threadIdx.x; i < NP; i += NT) S.list(L_DONE)[i] = (uint16_t)0xFFFFu;
     __syncthreads();
     // initial fill: every slot is free and claims a camera sample
     for (int s0 = 0; s0 < NP; s0 += NT) {
@@ -270,26 +286,39 @@ __global__ void __launch_bounds__(NT, MINB) pool_kernel(const __grid_constant__ 
         // the other parity's counters are idle during this trace phase (last read in the previous round, next written
         // in this round's shade phase / the next round's trace phase): reset them here
         if (threadIdx.x == 0) {
-            ctl.t_n[nxt] = 0u; ctl.t_head[nxt] = 0u; ctl.c_head[nxt] = 0u; ctl.k_head[nxt] = 0u;
-            ctl.c_n[nxt][0] = 0u; ctl.c_n[nxt][1] = 0u; ctl.c_n[nxt][2] = 0u; ctl.c_n[nxt][3] = 0u;
+            ctl.t_n[nxt] = 0u; ctl.t_head[nxt] = 0u; ctl.c_head[nxt] = 0u; ctl.k_head[nxt] = 0u; ctl.d_n[nxt] = 0u;
+            for (int c = 0; c < SHADE_CLASSES; c++) ctl.c_n[nxt][c] = 0u;
         }
         const unsigned nt = ctl.t_n[par];
         if (nt == 0u) break;                                    // block-uniform: no live path and no sample left to claim
 
         // ---------------- TRACE: closest hit + media for every live path, then the material-class split ----------------
-        if (P.pool_refill > 0 && !P.sc.linear && !P.sc.two_pass && !P.sc.empty) {
-            trace_refill(P, S, ctl, par, nt, P.pool_refill);
-            __syncthreads();
-            for (;;) {                                              // classify: media + class split, 32 paths per warp
+        if (P.pool_refill > 0 && (kTree || !P.sc.linear) && !P.sc.two_pass && !P.sc.empty) {
+            const bool overlap = P.pool_overlap != 0;
+            trace_refill(P, S, ctl, par, nt, P.pool_refill, overlap);
+            if (!overlap) __syncthreads();
+            // classify: media + class split, 32 traced paths per warp.  No barrier: a warp that has run out of rays starts on the
+            // paths already traced (in completion order) while the slowest rays of the phase are still in the tree; an entry that
+            // has not been published yet is waited for (every one of the nt live paths ends up in the list).
+            for (;;) {
                 unsigned base = 0;
                 if (lane == 0) base = atomicAdd(&ctl.k_head[par], 32u);
                 base = __shfl_sync(full, base, 0);
                 if (base >= nt) break;
                 const unsigned i = base + (unsigned)lane;
                 int cls = -1; unsigned slot = 0;
-                if (i < nt) { slot = S.list(L_LIVE0 + par)[i]; cls = classify_lane(P, S, slot, n_seg); }
+                if (i < nt) {
+                    if (overlap) {
+                        volatile uint16_t* e = reinterpret_cast<volatile uint16_t*>(S.list(L_DONE)) + i;
+                        unsigned v;
+                        while ((v = *e) == 0xFFFFu) __nanosleep(20);
+                        slot = v;
+                    } else slot = S.list(L_LIVE0 + par)[i];
+                }
+                if (overlap) __threadfence_block();
+                if (i < nt) cls = classify_lane(P, S, slot, n_seg);
 #pragma unroll
-                for (int c = 0; c < 4; c++) list_push(S.list(L_CLS0 + c), &ctl.c_n[par][c], cls == c, slot);
+                for (int c = 0; c < SHADE_CLASSES; c++) list_push(S.list(L_CLS0 + c), &ctl.c_n[par][c], cls == c, slot);
             }
         } else
         for (;;) {
@@ -300,38 +329,39 @@ __global__ void __launch_bounds__(NT, MINB) pool_kernel(const __grid_constant__ 
             const unsigned i = base + (unsigned)lane;
             const bool valid = i < nt;
             int cls = -1; unsigned slot = 0;
-            if (valid) { slot = S.list(L_LIVE0 + par)[i]; cls = trace_lane(P, S, slot, n_seg); }
+            if (valid) { slot = S.list(L_LIVE0 + par)[i]; cls = trace_lane<kTree ? 0 : -1>(P, S, slot, n_seg); }
 #pragma unroll
-            for (int c = 0; c < 4; c++) list_push(S.list(L_CLS0 + c), &ctl.c_n[par][c], cls == c, slot);
+            for (int c = 0; c < SHADE_CLASSES; c++) list_push(S.list(L_CLS0 + c), &ctl.c_n[par][c], cls == c, slot);
         }
         __syncthreads();
 
         // ---------------- SHADE: one material class per 32-slot chunk; finished lanes regenerate in place ----------------
-        const unsigned cn0 = ctl.c_n[par][0], cn1 = ctl.c_n[par][1], cn2 = ctl.c_n[par][2], cn3 = ctl.c_n[par][3];
-        // heavy classes first so the phase's tail is made of cheap chunks
-        const unsigned k1 = (cn1 + 31u) >> 5, k3 = k1 + ((cn3 + 31u) >> 5), k2 = k3 + ((cn2 + 31u) >> 5), k0 = k2 + ((cn0 + 31u) >> 5);
+        if (P.pool_overlap != 0 && P.pool_refill > 0 && !P.sc.linear && !P.sc.two_pass && !P.sc.empty)
+            for (int i = threadIdx.x; i < NP; i += NT) S.list(L_DONE)[i] = (uint16_t)0xFFFFu;      // consumed by classify; unpublished again for the next round
+        // chunk j of the phase -> (class, offset); heavy classes first so the phase's tail is made of cheap chunks
+        const int order[SHADE_CLASSES] = {CLASS_DIFFUSE_COLD, CLASS_DIFFUSE, CLASS_DIELECTRIC, CLASS_METAL, CLASS_TERMINAL};
+        unsigned cnt[SHADE_CLASSES], first[SHADE_CLASSES + 1];
+        first[0] = 0u;
+#pragma unroll
+        for (int k = 0; k < SHADE_CLASSES; k++) { cnt[k] = ctl.c_n[par][order[k]]; first[k + 1] = first[k] + ((cnt[k] + 31u) >> 5); }
         for (;;) {
             unsigned j = 0;
             if (lane == 0) j = atomicAdd(&ctl.c_head[par], 1u);
             j = __shfl_sync(full, j, 0);
-            if (j >= k0) break;
-            if (j < k1) {
-                const unsigned off = j * 32u + (unsigned)lane; const bool v = off < cn1;
-                const unsigned sl = v ? S.list(L_CLS0 + CLASS_DIFFUSE)[off] : 0u;
-                list_push(S.list(L_LIVE0 + nxt), &ctl.t_n[nxt], shade_chunk<CLASS_DIFFUSE>(P, S, v, sl, n_smp), sl);
-            } else if (j < k3) {
-                const unsigned off = (j - k1) * 32u + (unsigned)lane; const bool v = off < cn3;
-                const unsigned sl = v ? S.list(L_CLS0 + CLASS_DIELECTRIC)[off] : 0u;
-                list_push(S.list(L_LIVE0 + nxt), &ctl.t_n[nxt], shade_chunk<CLASS_DIELECTRIC>(P, S, v, sl, n_smp), sl);
-            } else if (j < k2) {
-                const unsigned off = (j - k3) * 32u + (unsigned)lane; const bool v = off < cn2;
-                const unsigned sl = v ? S.list(L_CLS0 + CLASS_METAL)[off] : 0u;
-                list_push(S.list(L_LIVE0 + nxt), &ctl.t_n[nxt], shade_chunk<CLASS_METAL>(P, S, v, sl, n_smp), sl);
-            } else {
-                const unsigned off = (j - k2) * 32u + (unsigned)lane; const bool v = off < cn0;
-                const unsigned sl = v ? S.list(L_CLS0 + CLASS_TERMINAL)[off] : 0u;
-                list_push(S.list(L_LIVE0 + nxt), &ctl.t_n[nxt], shade_chunk<CLASS_TERMINAL>(P, S, v, sl, n_smp), sl);
-            }
+            if (j >= first[SHADE_CLASSES]) break;
+            int k = 0; unsigned fk = 0u, ck = cnt[0]; int ok = order[0];
+#pragma unroll
+            for (int q = 1; q < SHADE_CLASSES; q++) if (j >= first[q]) { k = q; fk = first[q]; ck = cnt[q]; ok = order[q]; }      // constant indices: registers
+            const unsigned off = (j - fk) * 32u + (unsigned)lane;
+            const bool v = off < ck;
+            const unsigned sl = v ? S.list(L_CLS0 + ok)[off] : 0u;
+            bool live;
+            if (k == 0) live = shade_chunk<CLASS_DIFFUSE_COLD>(P, S, v, sl, n_smp);
+            else if (k == 1) live = shade_chunk<CLASS_DIFFUSE>(P, S, v, sl, n_smp);
+            else if (k == 2) live = shade_chunk<CLASS_DIELECTRIC>(P, S, v, sl, n_smp);
+            else if (k == 3) live = shade_chunk<CLASS_METAL>(P, S, v, sl, n_smp);
+            else live = shade_chunk<CLASS_TERMINAL>(P, S, v, sl, n_smp);
+            list_push(S.list(L_LIVE0 + nxt), &ctl.t_n[nxt], live, sl);
         }
         __syncthreads();
     }
@@ -340,181 +370,19 @@ __global__ void __launch_bounds__(NT, MINB) pool_kernel(const __grid_constant__ 
 }
 
 
-// ------------------------------------------------------------------------------------------------------
-// The barrier-free form.  ncu of the phased kernel above (profiles/r02_pool_phased.md): 24.5 % of all warp time on scene 8
-// (14 % on Cornell) is spent at the two __syncthreads() of a round — a phase ends when its slowest 32-ray chunk does, and
-// a chunk's closest-hit time is the maximum over 32 unrelated rays.  Here the two lists of a round become five ring
-// queues in shared memory (rays to trace + one queue per material class) and every warp, on its own, keeps taking
-// whatever full 32-entry chunk is available: a class chunk to shade (its survivors and the regenerated camera paths go
-// to the ray queue) or a ray chunk to trace (its hits go to the class queues).  Nothing waits for a slowest warp; partial
-// chunks are only taken when nothing full has shown up for a while (the end of the frame, or a class that is rare in
-// the scene).  Same per-path code and the same exact accumulation: the frame does not depend on the schedule.
-// ------------------------------------------------------------------------------------------------------
-enum { Q_RAY = 0, Q_CLS0 = 1, Q_N = 5, JOB_WAIT = -1, JOB_EXIT = -2 };
-struct AsyncCtl {
-    unsigned head[Q_N], tail[Q_N];
-    unsigned mode;                             // what the block's warps currently prefer: 0 = trace, 1 = shade (phases without barriers)
-    unsigned live;                             // paths alive in the block (queued or held by a warp); 0 = the block is done
-};
-
-struct Queues {
-    int np, qcap;                              // qcap: power of two >= np (a path is in at most one queue at a time)
-    __device__ __forceinline__ volatile uint16_t* ent(int q) const { return reinterpret_cast<volatile uint16_t*>(pool_raw) + 2 * kPoolWords * np + q * qcap; }
-};
-// Entry = slot | lap bit, lap = (index / qcap) & 1: a consumer that reserved index i waits until the entry carries i's lap
-// bit, so producers publish by the store itself (no commit counter, no clearing).  An entry cannot be overwritten before it is
-// read: that would take more than qcap >= np paths queued at once.
-__device__ __forceinline__ void q_push(const Queues& Q, AsyncCtl& ctl, int q, bool pred, unsigned slot) {
-    const unsigned full = 0xffffffffu;
-    const unsigned m = __ballot_sync(full, pred);
-    if (m == 0u) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(&ctl.tail[q], (unsigned)__popc(m));
-    base = __shfl_sync(full, base, leader);
-    if (pred) {
-        const unsigned idx = base + (unsigned)__popc(m & ((1u << lane) - 1u));
-        Q.ent(q)[idx & (unsigned)(Q.qcap - 1)] = (uint16_t)(slot | (((idx / (unsigned)Q.qcap) & 1u) << 15));
-    }
-}
-// up to 32 entries of queue q (at least min_n, else 0); lane l < n receives its slot
-__device__ __forceinline__ int q_pop(const Queues& Q, AsyncCtl& ctl, int q, int min_n, unsigned& slot) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    unsigned h = 0; int n = 0;
-    if (lane == 0) {
-        for (;;) {
-            h = *reinterpret_cast<volatile unsigned*>(&ctl.head[q]);
-            const unsigned t = *reinterpret_cast<volatile unsigned*>(&ctl.tail[q]);
-            const int avail = (int)(t - h);
-            if (avail < min_n || avail <= 0) { n = 0; break; }
-            n = avail < 32 ? avail : 32;
-            if (atomicCAS(&ctl.head[q], h, h + (unsigned)n) == h) break;
-        }
-    }
-    h = __shfl_sync(full, h, 0); n = __shfl_sync(full, n, 0);
-    if (lane < n) {
-        const unsigned idx = h + (unsigned)lane;
-        volatile uint16_t* e = Q.ent(q) + (idx & (unsigned)(Q.qcap - 1));
-        const unsigned want = ((idx / (unsigned)Q.qcap) & 1u) << 15;
-        unsigned v;
-        do { v = *e; } while ((v & 0x8000u) != want);           // reserved by a producer a few instructions ago at worst
-        slot = v & 0x7FFFu;
-    }
-    __threadfence_block();                                      // the path's state was written before its queue entry
-    return n;
-}
-
-template <int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) pool_async_kernel(const __grid_constant__ FrameParams P) {
-    __shared__ AsyncCtl ctl;
-    const int NP = P.pool_paths;
-    Pool S; S.np = NP;
-    Queues Q; Q.np = NP; Q.qcap = 1; while (Q.qcap < NP) Q.qcap <<= 1;
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    unsigned n_seg = 0, n_smp = 0;
-
-    if (threadIdx.x < (int)(sizeof(AsyncCtl) / 4)) reinterpret_cast<unsigned*>(&ctl)[threadIdx.x] = 0u;
-    for (int i = threadIdx.x; i < Q_N * Q.qcap; i += NT) Q.ent(0)[i] = (uint16_t)0x8000u;      // lap 1: nothing published for lap 0 yet
-    __syncthreads();
-    // initial fill: every slot is free and claims a camera sample
-    for (int s0 = 0; s0 < NP; s0 += NT) {
-        const int s = s0 + (int)threadIdx.x;
-        Lane L;
-        L.path.ray.o = L.path.ray.d = L.path.thr = mk3(0, 0, 0); L.path.ray.tm = 0.f; L.path.depth = 0;
-        rng_init(L.g, P.seed, P.frame, 0, 0);
-        const bool live = settle(P, L, false, s < NP, n_smp);
-        if (live) store_path(S, (unsigned)s, L);
-        __threadfence_block();
-        q_push(Q, ctl, Q_RAY, live, (unsigned)s);
-        const unsigned born = __ballot_sync(full, live);
-        if (born != 0u && lane == 0) atomicAdd(&ctl.live, (unsigned)__popc(born));
-    }
-    __syncthreads();
-
-    // Scheduling: the block keeps a preferred job kind (ctl.mode).  A warp takes a full chunk of the preferred kind; when there
-    // is none it flips the preference if the other kind has a full chunk.  So the warps of a block trace together until the ray
-    // queue runs dry, then shade together — two phases whose code fits the instruction cache — but a warp that finishes a
-    // long chunk late simply joins the next phase instead of holding everybody at a barrier.  Partial chunks are taken only
-    // after `pool_patience` polls without any full chunk (end of the frame, or a class that is rare in the scene).
-    unsigned patience = 0;
-    for (;;) {
-        int job = JOB_WAIT;
-        if (lane == 0) {
-            volatile unsigned* vh = ctl.head; volatile unsigned* vt = ctl.tail;
-            const unsigned mode = *reinterpret_cast<volatile unsigned*>(&ctl.mode);
-            int a_ray, a[4], bc = 0;
-            { const unsigned h = vh[Q_RAY]; a_ray = (int)(vt[Q_RAY] - h); }
-            if (mode == 0u && a_ray >= 32) job = Q_RAY;
-            else {
-#pragma unroll
-                for (int c = 0; c < 4; c++) { const unsigned h = vh[Q_CLS0 + c]; a[c] = (int)(vt[Q_CLS0 + c] - h); }
-#pragma unroll
-                for (int c = 1; c < 4; c++) if (a[c] > a[bc]) bc = c;
-                if (a[bc] >= 32) { job = Q_CLS0 + bc; if (mode == 0u) ctl.mode = 1u; }
-                else if (a_ray >= 32) { job = Q_RAY; if (mode != 0u) ctl.mode = 0u; }
-                else if (a_ray + a[0] + a[1] + a[2] + a[3] > 0) { if (patience > (unsigned)P.pool_patience) job = (a_ray > 0 && a_ray >= a[bc]) ? Q_RAY : Q_CLS0 + bc; }
-                else if (*reinterpret_cast<volatile unsigned*>(&ctl.live) == 0u) job = JOB_EXIT;
-            }
-        }
-        job = __shfl_sync(full, job, 0);
-        if (job == JOB_EXIT) break;
-        if (job == JOB_WAIT) {
-            if (++patience > 40000000u) { if (lane == 0) atomicAdd(P.counters + 2, 1ull); break; }      // watchdog (~ seconds): reported as an error by the host
-            __nanosleep(32);
-            continue;
-        }
-        unsigned slot = 0;
-        const int n = q_pop(Q, ctl, job, 1, slot);
-        if (n == 0) continue;                                   // another warp was faster
-        patience = 0;
-        const bool valid = lane < n;
-        if (job == Q_RAY) {
-            int cls = -1;
-            if (valid) cls = trace_lane(P, S, slot, n_seg);
-            __threadfence_block();
-#pragma unroll
-            for (int c = 0; c < 4; c++) q_push(Q, ctl, Q_CLS0 + c, cls == c, slot);
-        } else {
-            bool live;
-            if (job == Q_CLS0 + CLASS_DIFFUSE) live = shade_chunk<CLASS_DIFFUSE>(P, S, valid, slot, n_smp);
-            else if (job == Q_CLS0 + CLASS_DIELECTRIC) live = shade_chunk<CLASS_DIELECTRIC>(P, S, valid, slot, n_smp);
-            else if (job == Q_CLS0 + CLASS_METAL) live = shade_chunk<CLASS_METAL>(P, S, valid, slot, n_smp);
-            else live = shade_chunk<CLASS_TERMINAL>(P, S, valid, slot, n_smp);
-            __threadfence_block();
-            q_push(Q, ctl, Q_RAY, live, slot);
-            const unsigned died = __ballot_sync(full, valid && !live);          // only once the frame's samples are exhausted
-            if (died != 0u && lane == 0) atomicSub(&ctl.live, (unsigned)__popc(died));
-        }
-    }
-    for (int off = 16; off > 0; off >>= 1) { n_seg += __shfl_xor_sync(full, n_seg, off); n_smp += __shfl_xor_sync(full, n_smp, off); }
-    if (lane == 0) { atomicAdd(P.counters, (unsigned long long)n_seg); atomicAdd(P.counters + 1, (unsigned long long)n_smp); }
-}
-
 typedef void (*PoolFn)(const FrameParams);
-PoolFn pool_variant(const PoolShape& s) {
-    if (s.async) {
-        if (s.threads >= 1024) return (PoolFn)pool_async_kernel<1024, 1>;
-        if (s.threads >= 768) return (PoolFn)pool_async_kernel<768, 1>;
-        if (s.threads >= 640) return (PoolFn)pool_async_kernel<640, 1>;
-        if (s.threads >= 512) return s.min_blocks >= 2 ? (PoolFn)pool_async_kernel<512, 2> : (PoolFn)pool_async_kernel<512, 1>;
-        if (s.threads >= 384) return (PoolFn)pool_async_kernel<384, 2>;
-        return s.min_blocks >= 3 ? (PoolFn)pool_async_kernel<256, 3> : (PoolFn)pool_async_kernel<256, 2>;
-    }
-    if (s.threads >= 1024) return (PoolFn)pool_kernel<1024, 1>;
-    if (s.threads >= 768) return (PoolFn)pool_kernel<768, 1>;
-    if (s.threads >= 640) return (PoolFn)pool_kernel<640, 1>;
-    if (s.threads >= 512) return s.min_blocks >= 2 ? (PoolFn)pool_kernel<512, 2> : (PoolFn)pool_kernel<512, 1>;
-    if (s.threads >= 384) return (PoolFn)pool_kernel<384, 2>;
-    return s.min_blocks >= 3 ? (PoolFn)pool_kernel<256, 3> : (PoolFn)pool_kernel<256, 2>;
+template <bool kTree>
+PoolFn pool_variant_of(const PoolShape& s) {
+    if (s.threads >= 1024) return (PoolFn)pool_kernel<1024, 1, kTree>;
+    if (s.threads >= 768) return (PoolFn)pool_kernel<768, 1, kTree>;
+    if (s.threads >= 640) return (PoolFn)pool_kernel<640, 1, kTree>;
+    if (s.threads >= 512) return s.min_blocks >= 2 ? (PoolFn)pool_kernel<512, 2, kTree> : (PoolFn)pool_kernel<512, 1, kTree>;
+    if (s.threads >= 384) return s.min_blocks >= 2 ? (PoolFn)pool_kernel<384, 2, kTree> : (PoolFn)pool_kernel<384, 1, kTree>;
+    return s.min_blocks >= 3 ? (PoolFn)pool_kernel<256, 3, kTree> : (PoolFn)pool_kernel<256, 2, kTree>;
 }
-int pool_smem(const PoolShape& s) {
-    if (!s.async) return s.pool_paths * (kPoolWords * 4 + kPoolLists * 2);
-    int qcap = 1; while (qcap < s.pool_paths) qcap <<= 1;
-    return s.pool_paths * kPoolWords * 4 + Q_N * qcap * 2;
-}
+PoolFn pool_variant(const PoolShape& s) { return s.tree ? pool_variant_of<true>(s) : pool_variant_of<false>(s); }
 int pool_threads(const PoolShape& s) { return s.threads >= 1024 ? 1024 : s.threads >= 768 ? 768 : s.threads >= 640 ? 640 : s.threads >= 512 ? 512 : s.threads >= 384 ? 384 : 256; }
+int pool_smem(const PoolShape& s) { return s.pool_paths * (kPoolWords * 4 + kPoolLists * 2); }
 
 }  // namespace
 

@@ -27,7 +27,7 @@ struct FrameParams {
     unsigned int* work_counter;     // persistent-warp work queue head
     // block wavefront (pool.cu)
     int32_t pool_paths;             // paths per block pool
-    int32_t pool_patience;          // barrier-free form: polls (~64 ns each) without a full chunk before a warp takes a partial one
+    int32_t pool_overlap;           // tree scenes: classify starts on traced paths while other warps still trace (no barrier between the two)
     int32_t pool_refill;            // trace phase: lanes refill mid-traversal when at least this many of a warp's lanes are idle (0 = never)
     unsigned long long* work64;     // head of the call's sample index space [0, total_samples)
     unsigned long long total_samples;   // n_pixels * n_subset
@@ -40,7 +40,7 @@ cudaError_t mega_query(int threads, int n_staged, int min_blocks, bool linear, i
 cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, int min_blocks, cudaStream_t st);
 
 // block wavefront (pool.cu): one persistent kernel, a wavefront per thread block over a pool of paths in shared memory
-struct PoolShape { int threads, min_blocks, pool_paths, async; };
+struct PoolShape { int threads, min_blocks, pool_paths, tree; };
 cudaError_t pool_query(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes);
 cudaError_t pool_launch(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st);
 // zero / resolve the exact frame over the pixels THIS call renders (all of them, or the rank's 8-row bands)

@@ -65,9 +65,13 @@ MORT_HD f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); 
 MORT_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
 MORT_HD f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
 MORT_HD f3 operator*(float t, f3 a) { return mk3(t * a.x, t * a.y, t * a.z); }
-MORT_HD float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// Device code is compiled with -fmad=false (no implicit contraction: the arithmetic of a path must not depend on the kernel its
+// code was inlined into), so the fused forms that matter for speed in SHADING are written out here.  fmaf is exact-by-definition on
+// both the device and the host build, whatever the surrounding code.
+MORT_HD float dot3(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+MORT_HD f3 madd3(float t, f3 a, f3 b) { return mk3(fmaf(t, a.x, b.x), fmaf(t, a.y, b.y), fmaf(t, a.z, b.z)); }      // t * a + b
 MORT_HD float len2(f3 a) { return dot3(a, a); }
-MORT_HD f3 cross3(f3 u, f3 v) { return mk3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x); }
+MORT_HD f3 cross3(f3 u, f3 v) { return mk3(fmaf(u.y, v.z, -(u.z * v.y)), fmaf(u.z, v.x, -(u.x * v.z)), fmaf(u.x, v.y, -(u.y * v.x))); }
 MORT_HD f3 unit3(f3 a);                                                           // vec3.cuh:133-136, defined after rsqrt_fast
 MORT_HD bool isnan3(f3 a) { return a.x != a.x || a.y != a.y || a.z != a.z; }
 // exact forms (reference contraction: e2*f2 fused last, first product fused onto the plain middle one)
@@ -330,11 +334,17 @@ MORT_HD float safe_rcp_dir(float d) {
 // Traversal of the 4-wide BVH as a resumable state machine: per-ray constants + current node + stack depth.  closest_hit()
 // below runs it to completion for one ray; the block wavefront's trace phase (pool.cu) runs it in bursts and hands lanes
 // whose ray has finished a new ray while their neighbours are still traversing.
+#if defined(MORT_STACK_TOP)
+#define MORT_SET_TOP(T, e) ((T).top = (e))
+#else
+#define MORT_SET_TOP(T, e) ((void)0)
+#endif
 struct Trav {
     float idx, idy, idz, oix, oiy, oiz;                 // 1 / d and o / d per axis: a slab plane is one FMA
     int nxo, nyo, nzo;                                   // float offsets of the ray's near-plane rows inside a Bvh4Node (far = 12/20/28 - near)
     uint32_t cur;                                        // node index | leaf word | MORT_CHILD_EMPTY = finished
     int sp;
+    StackEntry top;                                      // copy of stack[sp - 1]: a pop hands it out at once and starts loading the entry below
 };
 MORT_HD void trav_begin(Trav& T, const Ray& r) {
     T.idx = safe_rcp_dir(r.d.x); T.idy = safe_rcp_dir(r.d.y); T.idz = safe_rcp_dir(r.d.z);
@@ -342,12 +352,24 @@ MORT_HD void trav_begin(Trav& T, const Ray& r) {
     // per-ray octant: which of the node's lo/hi planes is the entry ("near") plane on each axis.  Picking the
     // rows by address replaces 12 of the 18 min/max per child (float offsets into Bvh4Node: lo rows at 0/4/8, hi at 12/16/20).
     T.nxo = T.idx < 0.f ? 12 : 0; T.nyo = T.idy < 0.f ? 16 : 4; T.nzo = T.idz < 0.f ? 20 : 8;
-    T.cur = 0; T.sp = 0;                                 // root
+    T.cur = 0; T.sp = 0; T.top.child = MORT_CHILD_EMPTY; T.top.t = 0.f;       // root
 }
 // entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit
 MORT_HD uint32_t trav_pop(Trav& T, const StackEntry* stack, float best_t) {
+    // The top entry lives in registers (stack[] in local memory is its backing store), so the usual pop does not wait for
+    // a local-memory load: the load it issues (the new top) is only needed by the NEXT pop (ncu, scene 8: the pop loop was
+    // 3.8 % of the instructions but 9.1 % of the stall samples).
     uint32_t next = MORT_CHILD_EMPTY;
+#if defined(MORT_STACK_TOP)
+    while (T.sp > 0 && next == MORT_CHILD_EMPTY) {
+        const StackEntry e = T.top;
+        T.sp--;
+        if (T.sp > 0) T.top = stack[T.sp - 1];
+        if (e.t <= best_t) next = e.child;
+    }
+#else
     while (T.sp > 0 && next == MORT_CHILD_EMPTY) { T.sp--; const StackEntry e = stack[T.sp]; if (e.t <= best_t) next = e.child; }
+#endif
     return next;
 }
 // one internal node: slab-test its 4 children, continue with the nearest hit child, push the others
@@ -398,7 +420,7 @@ MORT_HD void trav_node(const DeviceScene& sc, const Bvh4Node* staged, int n_stag
     int sp = T.sp;
 #pragma unroll
     for (int k = 3; k >= 1; k--)
-        if (cw[k] != MORT_CHILD_EMPTY) { MORT_COUNT(pushes, 1); MORT_COUNT(push_at[sp], 1); StackEntry e; e.child = cw[k]; e.t = tn[k]; stack[sp] = e; sp++; }   // depth * 3 <= MORT_STACK is checked at commit
+        if (cw[k] != MORT_CHILD_EMPTY) { MORT_COUNT(pushes, 1); MORT_COUNT(push_at[sp], 1); StackEntry e; e.child = cw[k]; e.t = tn[k]; stack[sp] = e; MORT_SET_TOP(T, e); sp++; }   // depth * 3 <= MORT_STACK is checked at commit
     T.sp = sp;
     uint32_t next = cw[0];
     if (next == MORT_CHILD_EMPTY) next = trav_pop(T, stack, best_t);
@@ -695,7 +717,7 @@ MORT_HD void onb_from_w(Onb& b, f3 w) {
     f3 v = unit3(cross3(uw, a));
     b.u = cross3(uw, v); b.v = v; b.w = uw;
 }
-MORT_HD f3 onb_local(const Onb& b, f3 a) { return a.x * b.u + a.y * b.v + a.z * b.w; }
+MORT_HD f3 onb_local(const Onb& b, f3 a) { return madd3(a.z, b.w, madd3(a.y, b.v, a.x * b.u)); }
 MORT_HD f3 random_unit_vector(Rng& g) {
     for (;;) {
         R4 b = rng_block(g);                               // one aligned block per rejection attempt
@@ -721,12 +743,11 @@ MORT_HD f3 random_cosine_direction(float r1, float r2) {
     sincos_fast(phi, sn, cs);
     return mk3(cs * sr, sn * sr, sqrtf(1 - r2));
 }
-MORT_HD f3 reflect3(f3 v, f3 n) { return v - (2 * dot3(v, n)) * n; }
+MORT_HD f3 reflect3(f3 v, f3 n) { return madd3(-(2 * dot3(v, n)), n, v); }
 MORT_HD f3 refract3(f3 uv, f3 n, float eta) {
     float cos_theta = fminf(dot3(-uv, n), 1.0f);
-    f3 perp = eta * (uv + cos_theta * n);
-    f3 par = (-sqrtf(fabsf(1.0f - len2(perp)))) * n;
-    return perp + par;
+    f3 perp = eta * madd3(cos_theta, n, uv);
+    return madd3(-sqrtf(fabsf(1.0f - len2(perp))), n, perp);
 }
 MORT_HD float reflectance(float cosine, float ref_idx) {
     float r0 = div_fast(1 - ref_idx, 1 + ref_idx); r0 = r0 * r0;
@@ -772,7 +793,7 @@ MORT_HD f3 light_prim_random(const LightPrim* L, f3 origin, float r1, float r2) 
     }
     if (kind == LIGHT_QUAD) {                                                         // objects.cuh:231-235
         F4 Q = ld4(&L->a[1][0]), U = ld4(&L->a[2][0]), Vv = ld4(&L->a[3][0]);
-        f3 p = mk3(Q.x, Q.y, Q.z) + r1 * mk3(U.x, U.y, U.z) + r2 * mk3(Vv.x, Vv.y, Vv.z);
+        f3 p = madd3(r2, mk3(Vv.x, Vv.y, Vv.z), madd3(r1, mk3(U.x, U.y, U.z), mk3(Q.x, Q.y, Q.z)));
         return p - origin;
     }
     return mk3(1, 0, 0);
@@ -825,7 +846,15 @@ struct Path { Ray ray; f3 thr; int depth; };
 enum { SEG_CONTINUE = 0, SEG_DONE = 1 };
 
 // Material classes = the wavefront's shade queues.
-enum { CLASS_TERMINAL = 0, CLASS_DIFFUSE = 1, CLASS_METAL = 2, CLASS_DIELECTRIC = 3, CLASS_ANY = 4 };
+enum { CLASS_TERMINAL = SHADE_TERMINAL, CLASS_DIFFUSE = SHADE_DIFFUSE, CLASS_METAL = SHADE_METAL, CLASS_DIELECTRIC = SHADE_DIELECTRIC,
+       CLASS_DIFFUSE_COLD = SHADE_DIFFUSE_COLD, CLASS_ANY = SHADE_CLASSES };
+// the shading queue of a segment's winner, from the byte tables built at commit (flatten.cpp): one dependent load
+MORT_HD int seghit_class(const DeviceScene& sc, const SegHit& sh) {
+    if (sh.h.prim == MORT_PRIM_NONE) return CLASS_TERMINAL;
+    if (sh.h.prim == MORT_PRIM_MEDIUM) return sc.media[f2i_bits(sh.h.a)].cls;
+    const uint32_t i = sh.h.prim & 0x07FFFFFFu;
+    return (int)ldu8(((sh.h.prim & MORT_LEAF_QUAD_BIT) ? sc.quad_cls : sc.sphere_cls) + i);
+}
 MORT_HD int material_class(const DeviceScene& sc, int mat_gid) {
     if (mat_gid < 0) return CLASS_TERMINAL;
     int type = f2i_bits(ld4(sc.materials + mat_gid).x);
@@ -857,7 +886,7 @@ MORT_HD int segment_shade(const DeviceScene& sc, const CameraParams& cam, const 
     if ((kClass == CLASS_ANY || kClass == CLASS_METAL) && type == MORT_MAT_METAL) {      // materials.cuh:73-84
         f3 refl = reflect3(P.ray.d, rec.normal);
         float fuzz = m1.y;
-        refl = unit3(refl) + fuzz * random_unit_vector(g);
+        refl = madd3(fuzz, random_unit_vector(g), unit3(refl));
         P.thr = P.thr * mk3(m0.z, m0.w, m1.x);
         P.ray.o = rec.p; P.ray.d = refl; P.depth++;
         return SEG_CONTINUE;
@@ -874,7 +903,7 @@ MORT_HD int segment_shade(const DeviceScene& sc, const CameraParams& cam, const 
         P.ray.o = rec.p; P.ray.d = dir; P.depth++;       // attenuation (1,1,1)
         return SEG_CONTINUE;
     }
-    if (!(kClass == CLASS_ANY || kClass == CLASS_DIFFUSE) || (type != MORT_MAT_LAMBERTIAN && type != MORT_MAT_ISOTROPIC)) {
+    if (!(kClass == CLASS_ANY || kClass == CLASS_DIFFUSE || kClass == CLASS_DIFFUSE_COLD) || (type != MORT_MAT_LAMBERTIAN && type != MORT_MAT_ISOTROPIC)) {
         color = P.thr * mk3(0, 0, 0); return SEG_DONE;
     }
 

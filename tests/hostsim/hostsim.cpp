@@ -20,6 +20,7 @@ static DeviceScene make_device_scene(const Scene& s, const FlatScene& f, std::ve
     d.nodes = f.nodes.data(); d.n_nodes = (int)f.nodes.size();
     d.spheres = f.spheres.data(); d.sphere_info = f.sphere_info.data(); d.n_spheres = (int)f.spheres.size();
     d.quads = f.quads.data(); d.n_quads = (int)f.quads.size();
+    d.sphere_cls = f.sphere_cls.data(); d.quad_cls = f.quad_cls.data();
     d.instances = f.instances.data(); d.n_instances = (int)f.instances.size();
     d.materials = f.materials.data(); d.n_materials = (int)f.materials.size();
     d.textures = f.textures.data(); d.n_textures = (int)f.textures.size();

@@ -39,8 +39,8 @@ def test_pool_frame_is_bit_identical_to_the_megakernel(renderer, sc):
     H, W = st["height"], st["width"]
     mega, sm = _exact(renderer, H, W, seed=99, frame=2, mode=MODE_MEGAKERNEL)
     pool, sp = _exact(renderer, H, W, seed=99, frame=2, mode=MODE_POOL)
-    sync, _ = _exact(renderer, H, W, seed=99, frame=2, mode=MODE_POOL, pool_sync=1, pool_refill=8)
-    assert torch.equal(sync, pool), "phased form (with lane refill) vs barrier-free form"
+    other, _ = _exact(renderer, H, W, seed=99, frame=2, mode=MODE_POOL, pool_refill=-1 if st["n_nodes"] > 1 else 8)
+    assert torch.equal(other, pool), "fixed 32-ray chunks vs lane refill + classify pass"
     assert sp["last_samples"] == sm["last_samples"] == H * W * st["sqrt_spp"] ** 2
     assert sp["last_segments"] == sm["last_segments"]
     assert torch.equal(pool, mega), f"scene {sc}: {(pool != mega).any(-1).float().mean().item():.4f} of pixels differ"
@@ -53,10 +53,10 @@ def test_pool_frame_is_bit_identical_to_the_megakernel(renderer, sc):
     assert torch.equal(torch.nan_to_num(facc, nan=-1.0), torch.nan_to_num(ref, nan=-1.0))
 
 
-@pytest.mark.parametrize("sync", [0, 1])
+@pytest.mark.parametrize("refill", [-1, 6, 20])
 @pytest.mark.parametrize("shape", [(256, 2, 256), (256, 3, 544), (384, 2, 1024), (512, 1, 2048), (512, 2, 96), (640, 1, 2048), (768, 1, 1536), (1024, 1, 2304)])
-def test_pool_shape_does_not_change_the_frame(renderer, shape, sync):
-    """any block shape, any pool size, phased (pool_sync=1) or barrier-free (0): the same exact frame"""
+def test_pool_shape_does_not_change_the_frame(renderer, shape, refill):
+    """any block shape, any pool size, fixed 32-ray trace chunks (-1) or lane refill at any threshold: the same exact frame"""
     import torch
     from mort_b200.api import MODE_MEGAKERNEL, MODE_POOL
     threads, bps, paths = shape
@@ -64,7 +64,7 @@ def test_pool_shape_does_not_change_the_frame(renderer, shape, sync):
     st = renderer.stats
     H, W = st["height"], st["width"]
     mega, _ = _exact(renderer, H, W, seed=5, mode=MODE_MEGAKERNEL)
-    pool, sp = _exact(renderer, H, W, seed=5, mode=MODE_POOL, threads_per_block=threads, blocks_per_sm=bps, pool_paths=paths, pool_sync=sync)
+    pool, sp = _exact(renderer, H, W, seed=5, mode=MODE_POOL, threads_per_block=threads, blocks_per_sm=bps, pool_paths=paths, pool_refill=refill)
     assert torch.equal(pool, mega)
     assert sp["threads_per_block"] == threads
 
