@@ -108,7 +108,7 @@ int mort_commit(mort_ctx* ctx);
 enum { MORT_MODE_MEGAKERNEL = 0, MORT_MODE_WAVEFRONT = 1, MORT_MODE_POOL = 2 };
 typedef struct {
     uint32_t seed, frame;          /* Philox key; the reference's seed is 69420 (mort.cu:707) */
-    int32_t mode;                  /* MORT_MODE_* */
+    int32_t mode;                  /* MORT_MODE_* (default: MORT_MODE_POOL) */
     int32_t sample_mod, sample_rem;/* sample-split across GPUs: this call renders strata rows s_j % mod == rem (1,0 = all) */
     int32_t stage_nodes;           /* megakernel: BVH nodes staged in shared memory: <= 0 none (default), N first N (breadth-first) */
     int32_t threads_per_block;     /* 0 = default */

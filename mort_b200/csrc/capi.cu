@@ -254,7 +254,7 @@ int mort_commit(mort_ctx* ctx) {
 void mort_default_render_opts(mort_render_opts* o) {
     if (!o) return;
     memset(o, 0, sizeof(*o));
-    o->seed = 69420; o->frame = 0; o->mode = MORT_MODE_MEGAKERNEL; o->sample_mod = 1; o->sample_rem = 0; o->stage_nodes = 0;
+    o->seed = 69420; o->frame = 0; o->mode = MORT_MODE_POOL; o->sample_mod = 1; o->sample_rem = 0; o->stage_nodes = 0;
 }
 
 static int ensure_accum(mort_ctx* ctx, size_t npix) {
@@ -312,8 +312,8 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     int n_staged = o.stage_nodes;
     const int max_stage = (int)((ctx->prop.sharedMemPerBlockOptin > 6144 ? ctx->prop.sharedMemPerBlockOptin - 6144 : 0) / sizeof(Bvh4Node));
     if (n_staged < 0 || ctx->flat.linear || o.mode != MORT_MODE_MEGAKERNEL) n_staged = 0;     // nothing to stage for a linear-scan scene
+    n_staged = std::min(n_staged, (int)ctx->flat.nodes.size());          // "more than the tree has" = the whole tree
     if (n_staged > max_stage) return fail(ctx, MORT_ERR_ARG, "mort_render: stage_nodes exceeds the shared memory of a block (" + std::to_string(max_stage) + " nodes at most)");
-    n_staged = std::min(n_staged, (int)ctx->flat.nodes.size());
     p.n_staged = n_staged;
 
     if (ctx->stack_fix == 2) { raise_stack_limit(); ctx->stack_fix = 0; }
@@ -484,7 +484,7 @@ int mort_render_progressive(mort_ctx* ctx, const mort_render_opts* opts, int n_f
     int rc = ensure_accum(ctx, npix);
     if (rc != MORT_OK) return rc;
     mort_render_opts o; if (opts) o = *opts; else mort_default_render_opts(&o);
-    if (o.mode != MORT_MODE_MEGAKERNEL) return fail(ctx, MORT_ERR_ARG, "mort_render_progressive: megakernel only (exact sums)");
+    if (o.mode == MORT_MODE_WAVEFRONT) return fail(ctx, MORT_ERR_ARG, "mort_render_progressive: needs exact sums (megakernel or block wavefront)");
     // the running image restarts when the scene, the camera, the frame size or the seed changed
     const uint64_t fp = fingerprint(ctx);
     if (ctx->prog_pixels != npix || ctx->prog_fingerprint != fp || ctx->prog_seed != o.seed || !ctx->d_prog) {

@@ -22,7 +22,7 @@ static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [
 int main(int argc, char** argv) {
     if (argc < 2) return usage();                       // mort.cu:638-641
     int scene = atoi(argv[1]);
-    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = 0, mode = MORT_MODE_MEGAKERNEL, bps = 0, tpb = 0, field = 0, fieldcam = 0, pool = 0, refill = 0, gpus = 1, split = MORT_SPLIT_SAMPLE, xflags = 0;
+    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = 0, mode = MORT_MODE_POOL, bps = 0, tpb = 0, field = 0, fieldcam = 0, pool = 0, refill = 0, gpus = 1, split = MORT_SPLIT_SAMPLE, xflags = 0;
     float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr, load, dump, ckpt, text_in, text_out;
     bool accumulate = false, resume = false;
     for (int i = 2; i < argc; i++) {
@@ -40,7 +40,7 @@ int main(int argc, char** argv) {
         else if (a == "--field") field = atoi(nx()); else if (a == "--fieldcam") fieldcam = atoi(nx());
         else if (a == "--gpus") gpus = atoi(nx()); else if (a == "--split") { std::string m = nx(); split = m == "tile" ? MORT_SPLIT_TILE : MORT_SPLIT_SAMPLE; }
         else if (a == "--pool") pool = atoi(nx()); else if (a == "--xflags") xflags = atoi(nx()); else if (a == "--refill") refill = atoi(nx());
-        else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : m == "pool" ? MORT_MODE_POOL : MORT_MODE_MEGAKERNEL; }
+        else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : m == "mega" ? MORT_MODE_MEGAKERNEL : MORT_MODE_POOL; }
         else return usage();
     }
     if (gpus > 1) {

@@ -51,7 +51,7 @@ def test_no_cpu_fallback():
     assert L.mort_create(0, ctypes.byref(h)) == -2 and not h          # MORT_ERR_CUDA
     o = api.RenderOpts()
     L.mort_default_render_opts(ctypes.byref(o))
-    assert (o.seed, o.sample_mod, o.sample_rem, o.stage_nodes, o.pool_paths) == (69420, 1, 0, 0, 0)
+    assert (o.seed, o.mode, o.sample_mod, o.sample_rem, o.stage_nodes, o.pool_paths) == (69420, api.MODE_POOL, 1, 0, 0, 0)
 
 
 def test_product_sources_never_touch_the_oracle():

@@ -167,8 +167,10 @@ def test_tile_split_assembles_the_same_frame(renderer):
 
 def test_staging_and_launch_shapes_do_not_change_the_image(renderer):
     renderer.build_scene(1).override_camera(width=96, spp=25, depth=50).commit()
+    from mort_b200.api import MODE_MEGAKERNEL, MODE_POOL
     base = renderer.render(seed=9).accum
-    for kw in ({"stage_nodes": 64}, {"stage_nodes": 100000}, {"blocks_per_sm": 1}, {"threads_per_block": 64}):
+    for kw in ({"stage_nodes": 64, "mode": MODE_MEGAKERNEL}, {"stage_nodes": 100000, "mode": MODE_MEGAKERNEL}, {"blocks_per_sm": 1, "mode": MODE_MEGAKERNEL},
+               {"threads_per_block": 64, "mode": MODE_MEGAKERNEL}, {"mode": MODE_MEGAKERNEL}, {"mode": MODE_POOL, "threads_per_block": 256, "blocks_per_sm": 3, "pool_paths": 512}):
         other = renderer.render(seed=9, **kw).accum
         assert np.array_equal(base, other, equal_nan=True), f"{kw} changed the frame"
 
