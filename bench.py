@@ -242,38 +242,49 @@ def traffic_for(key):
         return None, None
 
 
-def short_run(torch, Renderer, dev, stream, setup, spp_label, frames, warmup, mode, kw, flop_key, sm_count, sm_clock_hz):
-    """A few device-resident frames of another BASELINE config (per_config extra); CUDA events on the launching stream."""
+def short_run(torch, Renderer, dev, stream, setup, spp_label, frames, warmup, mode, kw, flop_key, sm_count, sm_clock_hz, batch=False):
+    """A few device-resident frames of another BASELINE config (per_config extra); CUDA events on the launching stream.
+    batch=True: the frames are ALSO rendered as one launch (opts.n_frames: the reference's frame loop without a kernel tail per frame)."""
     r = Renderer(dev.index)
     r.set_stream(stream.cuda_stream)
     setup(r)
     r.commit()
     st = r.stats
     H, W, n_spp = st["height"], st["width"], st["sqrt_spp"] ** 2
-    accum = torch.zeros(H, W, 4, dtype=torch.float32, device=dev)
-    for i in range(warmup):
-        r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, **kw)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    segs, ker = 0, 0.0
-    e0.record(stream)
-    for i in range(frames):
-        r.render_device(accum.data_ptr(), seed=69420, frame=warmup + i, mode=mode, **kw)
-        s = r.stats
-        segs += s["last_segments"]; ker += s["last_render_ms"]
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    accum = torch.zeros(frames if batch else 1, H, W, 4, dtype=torch.float32, device=dev)
+
+    def timed(fn, reps):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        segs, ker = 0, 0.0
+        e0.record(stream)
+        for i in range(reps):
+            fn(warmup + i)
+            s = r.stats
+            segs += s["last_segments"]; ker += s["last_render_ms"]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), segs, ker
+
+    ms, segs, ker = timed(lambda i: r.render_device(accum.data_ptr(), seed=69420, frame=i, mode=mode, **kw), frames)
+    samples = H * W * n_spp * frames
+    one_per_launch = samples / (ms * 1e3)
+    if batch:
+        bms, bsegs, bker = timed(lambda i: r.render_device(accum.data_ptr(), seed=69420, frame=i * frames, mode=mode, n_frames=frames, **kw), 3)
+        ms, segs, ker, samples = bms, bsegs, bker, 3 * samples
     st2 = r.stats
     r.close()
-    samples = H * W * n_spp * frames
     achieved = segs / (ker * 1e-3) * FLOP_PER_RAY[flop_key] / 1e12
     peak = sm_count * 128 * 2 * sm_clock_hz / 1e12
-    return {"workload": f"{spp_label} {W}x{H}, {n_spp} spp effective, depth {st['bounce_limit']}", "value": samples / (ms * 1e3), "unit": "Msamples/s",
-            "mrays_per_s": segs / (ms * 1e3), "ms_per_frame": ms / frames, "kernel_ms_per_frame": ker / frames, "frames": frames,
-            "roofline_frac_fp32": achieved / peak, "flop_per_ray": FLOP_PER_RAY[flop_key],
-            "kernel": {"regs": st2["regs_per_thread"], "threads_per_block": st2["threads_per_block"], "blocks_per_sm": st2["blocks_per_sm"],
-                       "bvh_nodes": st2["n_nodes"], "leaves": st2["n_leaves"]}}
+    res = {"workload": f"{spp_label} {W}x{H}, {n_spp} spp effective, depth {st['bounce_limit']}" + (f", {frames} frames per launch" if batch else ""),
+           "value": samples / (ms * 1e3), "unit": "Msamples/s",
+           "mrays_per_s": segs / (ms * 1e3), "ms_per_frame": ms / (frames * (3 if batch else 1)), "frames": frames,
+           "roofline_frac_fp32": achieved / peak, "flop_per_ray": FLOP_PER_RAY[flop_key], "value_one_launch_per_frame": one_per_launch,
+           "kernel": {"regs": st2["regs_per_thread"], "threads_per_block": st2["threads_per_block"], "blocks_per_sm": st2["blocks_per_sm"],
+                      "bvh_nodes": st2["n_nodes"], "leaves": st2["n_leaves"]}}
+    return res
 
 
 def run_mort(a):
@@ -460,7 +471,7 @@ def run_mort(a):
             pc = {}
             try:
                 args = (torch, Renderer, dev, stream)
-                pc["config 1"] = short_run(*args, lambda q: q.build_scene(1).override_camera(width=400, aspect=16 / 9, spp=32, depth=50), "mort scene 1 (random_spheres)", 20, 3, mode, kw, "config 1", st["sm_count"], sm_clock)
+                pc["config 1"] = short_run(*args, lambda q: q.build_scene(1).override_camera(width=400, aspect=16 / 9, spp=32, depth=50), "mort scene 1 (random_spheres)", 20, 3, mode, kw, "config 1", st["sm_count"], sm_clock, batch=(mode_name == "pool"))
                 pc["config 2"] = short_run(*args, lambda q: q.build_scene(6).override_camera(width=600, spp=1024, depth=50), "mort scene 6 (cornell_box)", 3, 1, mode, kw, "config 2", st["sm_count"], sm_clock)
                 pc["config 4"] = short_run(*args, lambda q: q.build_sphere_field(500, 69420, 0).override_camera(width=1920, aspect=16 / 9, spp=256, depth=50), "1 M-sphere field, book view", 2, 1, mode, kw, "config 4", st["sm_count"], sm_clock)
             except Exception as ex:  # an extra, never a gate

@@ -122,6 +122,9 @@ typedef struct {
     int32_t pool_paths;            /* MORT_MODE_POOL: paths per thread-block pool (0 = default 1024; 88 B of shared memory each) */
     int32_t pool_refill;           /* MORT_MODE_POOL, tree scenes: lanes whose ray left the tree take a new one as soon as this many lanes of
                                       their warp are idle (1..31; 0 = default, -1 = off: fixed 32-ray chunks) */
+    int32_t n_frames;              /* MORT_MODE_POOL, mort_render_device: > 1 = a batch: frame keys frame .. frame + n - 1 in ONE launch into n consecutive
+                                      frames of d_accum (the reference's frame loop, mort.cu:93-120, without a kernel tail per frame); <= 256 */
+    int32_t tile_rows;             /* tile split: rows per band, 0 = 8.  Thin bands balance the ranks better (sky vs geometry): mort_group_render uses 2 */
     int32_t pool_flags;            /* MORT_MODE_POOL experiments: bit 0 = barrier between trace and classify, bit 1 = force the overlapped form (0 = by scene class) */
 } mort_render_opts;
 void mort_default_render_opts(mort_render_opts* o);

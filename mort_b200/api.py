@@ -47,7 +47,7 @@ class CameraDesc(C.Structure):
 class RenderOpts(C.Structure):
     _fields_ = [("seed", C.c_uint32), ("frame", C.c_uint32), ("mode", C.c_int32), ("sample_mod", C.c_int32),
                 ("sample_rem", C.c_int32), ("stage_nodes", C.c_int32), ("threads_per_block", C.c_int32),
-                ("blocks_per_sm", C.c_int32), ("wavefront_paths", C.c_int32), ("exact_accum", C.c_int32), ("tile_mod", C.c_int32), ("tile_rem", C.c_int32), ("accumulate", C.c_int32), ("pool_paths", C.c_int32), ("pool_refill", C.c_int32), ("pool_flags", C.c_int32)]
+                ("blocks_per_sm", C.c_int32), ("wavefront_paths", C.c_int32), ("exact_accum", C.c_int32), ("tile_mod", C.c_int32), ("tile_rem", C.c_int32), ("accumulate", C.c_int32), ("pool_paths", C.c_int32), ("pool_refill", C.c_int32), ("n_frames", C.c_int32), ("tile_rows", C.c_int32), ("pool_flags", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -282,11 +282,13 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     p.n_subset = p.n_rows * cam.sqrt_spp;
     p.n_pixels = cam.width * cam.height;
     p.tile_mod = o.tile_mod > 1 ? o.tile_mod : 1; p.tile_rem = o.tile_mod > 1 ? o.tile_rem : 0;
+    const int rows = o.tile_rows > 0 ? o.tile_rows : 8;      // band height of the tile split
+    p.band_px = rows * cam.width;
     if (p.tile_mod > 1) {
         if (o.tile_rem < 0 || o.tile_rem >= o.tile_mod) return fail(ctx, MORT_ERR_ARG, "mort_render: bad tile split");
         if (o.mode == MORT_MODE_WAVEFRONT) return fail(ctx, MORT_ERR_ARG, "mort_render: tile split needs the megakernel or the block wavefront");
-        int n = 0;                                           // pixels in this rank's 8-row bands
-        for (int b = p.tile_rem; b * 8 < cam.height; b += p.tile_mod) n += std::min(8, cam.height - b * 8) * cam.width;
+        int n = 0;                                           // pixels in this rank's bands
+        for (int b = p.tile_rem; b * rows < cam.height; b += p.tile_mod) n += std::min(rows, cam.height - b * rows) * cam.width;
         p.n_pixels = n;
     }
     // pixels per warp task: enough samples per task (~2048) to amortise the end-of-task tail, at most 16 pixels
@@ -321,6 +323,7 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
     uint64_t launches = 0;
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (o.n_frames > 1 && o.mode != MORT_MODE_POOL) return fail(ctx, MORT_ERR_ARG, "mort_render: n_frames > 1 is a block-wavefront feature");
     if (o.mode == MORT_MODE_MEGAKERNEL) {
         int occ = 0, regs = 0;
         // measured (profiles/r01_v4_variants.jsonl): 6 blocks/SM (80 regs) wins for the lockstep linear scan, 8 (64 regs) for the
@@ -337,16 +340,24 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         // block wavefront (pool.cu): samples are added into an exact frame with integer reductions; a float4 request
         // goes through a context-owned exact frame and one resolve pass
         const size_t npix_full = (size_t)cam.width * cam.height;
+        // a batch of frames (opts.n_frames > 1): frame keys frame .. frame + n - 1 rendered by ONE launch into n consecutive frames of
+        // d_accum — the reference's frame loop (mort.cu:93-120) without a kernel tail and a launch gap per frame
+        const int n_frames = o.n_frames > 1 ? o.n_frames : 1;
+        if (n_frames > 1 && (n_frames > 256 || npix_full > (1u << 24) || p.tile_mod > 1 || o.accumulate))
+            return fail(ctx, MORT_ERR_ARG, "mort_render: a batch takes at most 256 frames of at most 2^24 pixels, whole frames, no accumulate");
         unsigned long long* target = reinterpret_cast<unsigned long long*>(d_accum);
         if (!o.exact_accum) {
-            if (ctx->pool_exact_pixels < npix_full) {
+            if (ctx->pool_exact_pixels < npix_full * n_frames) {
                 cudaFree(ctx->d_pool_exact); ctx->d_pool_exact = nullptr; ctx->pool_exact_pixels = 0;
-                CU(cudaMalloc(&ctx->d_pool_exact, npix_full * 4 * sizeof(unsigned long long))); ctx->pool_exact_pixels = npix_full;
+                CU(cudaMalloc(&ctx->d_pool_exact, npix_full * n_frames * 4 * sizeof(unsigned long long))); ctx->pool_exact_pixels = npix_full * n_frames;
             }
             target = ctx->d_pool_exact;
         }
         p.accum = nullptr; p.accum_exact = target;
-        p.work64 = ctx->d_work64; p.total_samples = (unsigned long long)p.n_pixels * (unsigned long long)p.n_subset;
+        p.frame_samples = (unsigned long long)p.n_pixels * (unsigned long long)p.n_subset;
+        p.total_samples = p.frame_samples * (unsigned long long)n_frames; p.frame_words = (unsigned long long)npix_full * 4ull;
+        p.pix_mask = n_frames > 1 ? 0x00FFFFFFu : 0xFFFFFFFFu; p.frame_shift = n_frames > 1 ? 24 : 0;
+        p.work64 = ctx->d_work64;
         // Block shape, pool size and trace-phase form per scene class, from same-box A/B runs (profiles/r02_pool_ab.md):
         //   linear-scan scenes (<= 40 leaves)        2 blocks x 512 threads, 1024 paths each, generic kernel
         //   tree scenes without media                2 blocks x 512 threads, 1024 paths each, fixed 32-ray trace chunks
@@ -367,10 +378,10 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         if (occ < 1) return fail(ctx, MORT_ERR_ARG, "mort_render: a pool of " + std::to_string(ps.pool_paths) + " paths (" + std::to_string(smem) + " B) does not fit in a block's shared memory");
         const int bps = std::min(occ, ps.min_blocks);
         CU(cudaMemsetAsync(ctx->d_work64, 0, sizeof(unsigned long long), ctx->stream));
-        if (!o.accumulate || !o.exact_accum) CU(zero_exact_launch(target, p.n_pixels, cam.width, p.tile_mod, p.tile_rem, ctx->stream));
+        if (!o.accumulate || !o.exact_accum) CU(zero_exact_launch(target, p.n_pixels * n_frames, p.band_px, p.tile_mod, p.tile_rem, ctx->stream));
         CU(pool_launch(p, ps, bps * ctx->prop.multiProcessorCount, ctx->stream));
         launches = 2;
-        if (!o.exact_accum) { CU(resolve_exact_tiles_launch(target, p.n_pixels, cam.width, p.tile_mod, p.tile_rem, reinterpret_cast<float4*>(d_accum), ctx->stream)); launches = 3; }
+        if (!o.exact_accum) { CU(resolve_exact_tiles_launch(target, p.n_pixels * n_frames, p.band_px, p.tile_mod, p.tile_rem, reinterpret_cast<float4*>(d_accum), ctx->stream)); launches = 3; }
         ctx->stats.threads_per_block = ps.threads; ctx->stats.blocks_per_sm = bps; ctx->stats.regs_per_thread = regs; ctx->stats.staged_nodes = 0;
     } else if (o.mode == MORT_MODE_WAVEFRONT) {
         int n_paths = std::max(o.wavefront_paths > 0 ? o.wavefront_paths : 1 << 21, p.n_pixels);   // at least one slot per pixel
@@ -507,7 +518,7 @@ int mort_render_progressive(mort_ctx* ctx, const mort_render_opts* opts, int n_f
     }
     double ms = 0; uint64_t segs = 0, smps = 0, launches = 0;
     for (int f = 0; f < n_frames; f++) {
-        o.exact_accum = 1; o.accumulate = ctx->prog_frames > 0 ? 1 : 0; o.frame = ctx->prog_frames;
+        o.exact_accum = 1; o.accumulate = ctx->prog_frames > 0 ? 1 : 0; o.frame = ctx->prog_frames; o.n_frames = 0;
         rc = mort_render_device(ctx, &o, ctx->d_prog);
         if (rc != MORT_OK) return rc;
         ctx->prog_frames++;
@@ -553,7 +564,7 @@ int mort_render(mort_ctx* ctx, const mort_render_opts* opts, uint8_t* rgba8_out,
     int rc = ensure_accum(ctx, npix);
     if (rc != MORT_OK) return rc;
     mort_render_opts oh; if (opts) oh = *opts; else mort_default_render_opts(&oh);
-    oh.exact_accum = 0; oh.accumulate = 0;               // the host-buffer call returns the float4 image
+    oh.exact_accum = 0; oh.accumulate = 0; oh.n_frames = 0;   // the host-buffer call returns ONE float4 image
     // A host-buffer frame is a whole frame: a tile split would return the other ranks' bands uninitialised (partial frames
     // are combined on the device: mort_render_device + mort_group_* / the caller's collective).  A sample split is
     // allowed; its 8-bit frame is the mean over the samples this call rendered.

@@ -178,9 +178,9 @@ int mort_group_render(mort_group* g, const mort_render_opts* opts_in, int split,
             g->exact_pixels[i] = npix;
         }
         mort_render_opts o = base;
-        o.exact_accum = 1; o.accumulate = 0;
+        o.exact_accum = 1; o.accumulate = 0; o.n_frames = 0;
         if (split == MORT_SPLIT_SAMPLE) { o.sample_mod = n; o.sample_rem = i; o.tile_mod = 0; o.tile_rem = 0; }
-        else { o.sample_mod = 1; o.sample_rem = 0; o.tile_mod = n; o.tile_rem = i; }
+        else { o.sample_mod = 1; o.sample_rem = 0; o.tile_mod = n; o.tile_rem = i; if (o.tile_rows <= 0) o.tile_rows = 2; }   // thin bands: every rank sees every part of the frame
         // a tile split leaves the other ranks' bands untouched: they must be zero for the sum
         if (split == MORT_SPLIT_TILE && n > 1 && cudaMemsetAsync(g->d_exact[i], 0, npix * 32, ctx->stream) != cudaSuccess) { rc[i] = MORT_ERR_CUDA; return; }
         rc[i] = mort_render_device(ctx, &o, g->d_exact[i]);

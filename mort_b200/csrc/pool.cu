@@ -70,8 +70,8 @@ __device__ __forceinline__ void list_push(uint16_t* list, unsigned* count, bool 
 
 // A finished sample goes straight into the exact frame.  Black samples (most of them in the scenes with a black
 // background) add nothing and cost nothing.
-__device__ __forceinline__ void add_sample(const FrameParams& P, uint32_t pixel, f3 col) {
-    unsigned long long* dst = P.accum_exact + (size_t)pixel * 4;
+__device__ __forceinline__ void add_sample(const FrameParams& P, const Rng& g, f3 col) {
+    unsigned long long* dst = P.accum_exact + (size_t)g.pixel * 4 + (size_t)(g.k1 - P.frame) * P.frame_words;      // frame of a batch: its own exact frame
     if (isnan3(col)) { atomicAdd(dst + 3, 1ull); return; }
     long long dr = 0, dg = 0, db = 0; unsigned long long fl = 0ull;
     fx_add(dr, fl, col.x, 20); fx_add(dg, fl, col.y, 34); fx_add(db, fl, col.z, 48);
@@ -82,6 +82,13 @@ __device__ __forceinline__ void add_sample(const FrameParams& P, uint32_t pixel,
 }
 
 struct Lane { Path path; Rng g; };
+// Philox identity of a path <-> its three pool words.  A launch may render a BATCH of frames (the reference's frame loop,
+// mort.cu:93-120, as one launch): the frame-in-batch index rides in the upper bits of the pixel word.
+__device__ __forceinline__ void rng_load(const FrameParams& P, const Pool& S, unsigned slot, Rng& g) {
+    const uint32_t w = S.u(W_PIX, slot);
+    g.k0 = P.seed; g.k1 = P.frame + (P.frame_shift ? (w >> P.frame_shift) : 0u); g.pixel = w & P.pix_mask;
+    g.sample = S.u(W_SMP, slot); g.block = S.u(W_BLK, slot);
+}
 
 // Brings a lane to a path whose next segment must be traced: a path that reached the bounce limit or whose ray went NaN is
 // finished here (camera.cuh:161-163; render.cu's path_segment does the same checks before its closest-hit query), and a
@@ -94,8 +101,8 @@ __device__ __forceinline__ bool settle(const FrameParams& P, Lane& L, bool check
     for (;;) {
         if (check) {
             f3 col;
-            if (path_exhausted(P.cam, L.path, col)) { add_sample(P, L.g.pixel, col); need_new = true; }
-            else if (ray_is_nan(L.path.ray)) { add_sample(P, L.g.pixel, mk3(NAN, NAN, NAN)); need_new = true; }
+            if (path_exhausted(P.cam, L.path, col)) { add_sample(P, L.g, col); need_new = true; }
+            else if (ray_is_nan(L.path.ray)) { add_sample(P, L.g, mk3(NAN, NAN, NAN)); need_new = true; }
             else live = true;
             check = false;
         }
@@ -109,11 +116,13 @@ __device__ __forceinline__ bool settle(const FrameParams& P, Lane& L, bool check
             need_new = false;
             const unsigned long long gidx = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
             if (gidx < P.total_samples) {
-                const unsigned long long pl = gidx / (unsigned long long)P.n_subset;
-                const int k = (int)(gidx - pl * (unsigned long long)P.n_subset);
+                const unsigned long long fb = P.frame_shift ? gidx / P.frame_samples : 0ull;      // frame of the batch
+                const unsigned long long fi = gidx - fb * P.frame_samples;
+                const unsigned long long pl = fi / (unsigned long long)P.n_subset;
+                const int k = (int)(fi - pl * (unsigned long long)P.n_subset);
                 const int row = k / P.cam.sqrt_spp;
-                const int pixel = tile_to_global((int)pl, 8 * P.cam.width, P.tile_mod, P.tile_rem);
-                path_start(P.cam, P.seed, P.frame, pixel, k - row * P.cam.sqrt_spp, P.sj_rem + row * P.sj_mod, L.path, L.g);
+                const int pixel = tile_to_global((int)pl, P.band_px, P.tile_mod, P.tile_rem);
+                path_start(P.cam, P.seed, P.frame + (uint32_t)fb, pixel, k - row * P.cam.sqrt_spp, P.sj_rem + row * P.sj_mod, L.path, L.g);
                 n_smp++;
                 check = true;
             }
@@ -122,11 +131,11 @@ __device__ __forceinline__ bool settle(const FrameParams& P, Lane& L, bool check
     return live;
 }
 
-__device__ __forceinline__ void store_path(const Pool& S, unsigned s, const Lane& L) {
+__device__ __forceinline__ void store_path(const FrameParams& P, const Pool& S, unsigned s, const Lane& L) {
     S.f(W_OX, s) = L.path.ray.o.x; S.f(W_OY, s) = L.path.ray.o.y; S.f(W_OZ, s) = L.path.ray.o.z;
     S.f(W_DX, s) = L.path.ray.d.x; S.f(W_DY, s) = L.path.ray.d.y; S.f(W_DZ, s) = L.path.ray.d.z; S.f(W_TM, s) = L.path.ray.tm;
     S.f(W_TX, s) = L.path.thr.x; S.f(W_TY, s) = L.path.thr.y; S.f(W_TZ, s) = L.path.thr.z; S.u(W_DEPTH, s) = (uint32_t)L.path.depth;
-    S.u(W_PIX, s) = L.g.pixel; S.u(W_SMP, s) = L.g.sample; S.u(W_BLK, s) = L.g.block;
+    S.u(W_PIX, s) = L.g.pixel | (P.frame_shift ? (L.g.k1 - P.frame) << P.frame_shift : 0u); S.u(W_SMP, s) = L.g.sample; S.u(W_BLK, s) = L.g.block;
 }
 __device__ __forceinline__ void load_ray(const Pool& S, unsigned s, Ray& r) {
     r.o = mk3(S.f(W_OX, s), S.f(W_OY, s), S.f(W_OZ, s)); r.d = mk3(S.f(W_DX, s), S.f(W_DY, s), S.f(W_DZ, s)); r.tm = S.f(W_TM, s);
@@ -140,7 +149,7 @@ __device__ __forceinline__ bool shade_chunk(const FrameParams& P, const Pool& S,
     if (valid) {
         load_ray(S, slot, L.path.ray);
         L.path.thr = mk3(S.f(W_TX, slot), S.f(W_TY, slot), S.f(W_TZ, slot)); L.path.depth = (int)S.u(W_DEPTH, slot);
-        L.g.k0 = P.seed; L.g.k1 = P.frame; L.g.pixel = S.u(W_PIX, slot); L.g.sample = S.u(W_SMP, slot); L.g.block = S.u(W_BLK, slot);
+        rng_load(P, S, slot, L.g);
         SegHit sh; sh.h.t = S.f(W_HT, slot); sh.h.prim = S.u(W_HPRIM, slot); sh.h.a = S.f(W_HA, slot); sh.h.b = S.f(W_HB, slot);
         R4 sb = {0.f, 0.f, 0.f, 0.f};
         if (kClass == CLASS_DIFFUSE || kClass == CLASS_DIFFUSE_COLD || kClass == CLASS_DIELECTRIC) {            // the bounce's stage block, reserved by the trace phase
@@ -149,13 +158,13 @@ __device__ __forceinline__ bool shade_chunk(const FrameParams& P, const Pool& S,
         }
         f3 color = mk3(0, 0, 0);
         const int st = segment_shade<kClass>(P.sc, P.cam, sh, L.path, L.g, sb, color);
-        if (st == SEG_DONE) { add_sample(P, L.g.pixel, color); done = true; }
+        if (st == SEG_DONE) { add_sample(P, L.g, color); done = true; }
     } else {
         L.path.ray.o = L.path.ray.d = L.path.thr = mk3(0, 0, 0); L.path.ray.tm = 0.f; L.path.depth = 0;
         rng_init(L.g, P.seed, P.frame, 0, 0);
     }
     const bool live = settle(P, L, valid && !done, valid && done, n_smp);
-    if (live) store_path(S, slot, L);
+    if (live) store_path(P, S, slot, L);
     return live;
 }
 
@@ -163,7 +172,7 @@ __device__ __forceinline__ bool shade_chunk(const FrameParams& P, const Pool& S,
 template <int kLinear>
 __device__ __forceinline__ int trace_lane(const FrameParams& P, const Pool& S, unsigned slot, unsigned& n_seg) {
     Ray r; load_ray(S, slot, r);
-    Rng g; g.k0 = P.seed; g.k1 = P.frame; g.pixel = S.u(W_PIX, slot); g.sample = S.u(W_SMP, slot); g.block = S.u(W_BLK, slot);
+    Rng g; rng_load(P, S, slot, g);
     const uint32_t stage = g.block; g.block++;        // canonical stream: the stage block precedes the segment's media draws
     SegHit sh;
     segment_trace<false, kLinear>(P.sc, nullptr, 0, r, g, sh);
@@ -240,7 +249,7 @@ __device__ __forceinline__ void trace_refill(const FrameParams& P, const Pool& S
 }
 // the rest of the segment for a path whose closest surface hit is in the pool: -> material class
 __device__ __forceinline__ int classify_lane(const FrameParams& P, const Pool& S, unsigned slot, unsigned& n_seg) {
-    Rng g; g.k0 = P.seed; g.k1 = P.frame; g.pixel = S.u(W_PIX, slot); g.sample = S.u(W_SMP, slot); g.block = S.u(W_BLK, slot);
+    Rng g; rng_load(P, S, slot, g);
     const uint32_t stage = g.block; g.block++;
     Hit h; h.t = S.f(W_HT, slot); h.prim = S.u(W_HPRIM, slot); h.a = S.f(W_HA, slot); h.b = S.f(W_HB, slot);
     SegHit sh;
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(NT, MINB) pool_kernel(const __grid_constant__ 
         L.path.ray.o = L.path.ray.d = L.path.thr = mk3(0, 0, 0); L.path.ray.tm = 0.f; L.path.depth = 0;
         rng_init(L.g, P.seed, P.frame, 0, 0);
         const bool live = settle(P, L, false, s < NP, n_smp);
-        if (live) store_path(S, (unsigned)s, L);
+        if (live) store_path(P, S, (unsigned)s, L);
         list_push(S.list(L_LIVE0), &ctl.t_n[0], live, (unsigned)s);
     }
     __syncthreads();
@@ -424,15 +433,15 @@ __global__ void __launch_bounds__(256) resolve_exact_tiles_kernel(const ulonglon
     const ulonglong2 a = ex[2 * g], b = ex[2 * g + 1];
     out[g] = fx_resolve((long long)a.x, (long long)a.y, (long long)b.x, b.y);
 }
-cudaError_t zero_exact_launch(unsigned long long* d_exact, int n_local, int width, int tile_mod, int tile_rem, cudaStream_t st) {
+cudaError_t zero_exact_launch(unsigned long long* d_exact, int n_local, int band_px, int tile_mod, int tile_rem, cudaStream_t st) {
     if (n_local <= 0) return cudaSuccess;
     if (tile_mod <= 1) return cudaMemsetAsync(d_exact, 0, (size_t)n_local * 32, st);
-    zero_exact_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(reinterpret_cast<ulonglong2*>(d_exact), n_local, 8 * width, tile_mod, tile_rem);
+    zero_exact_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(reinterpret_cast<ulonglong2*>(d_exact), n_local, band_px, tile_mod, tile_rem);
     return cudaGetLastError();
 }
-cudaError_t resolve_exact_tiles_launch(const unsigned long long* d_exact, int n_local, int width, int tile_mod, int tile_rem, float4* d_accum, cudaStream_t st) {
+cudaError_t resolve_exact_tiles_launch(const unsigned long long* d_exact, int n_local, int band_px, int tile_mod, int tile_rem, float4* d_accum, cudaStream_t st) {
     if (n_local <= 0) return cudaSuccess;
-    resolve_exact_tiles_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ulonglong2*>(d_exact), n_local, 8 * width, tile_mod > 1 ? tile_mod : 1, tile_rem, d_accum);
+    resolve_exact_tiles_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ulonglong2*>(d_exact), n_local, band_px, tile_mod > 1 ? tile_mod : 1, tile_rem, d_accum);
     return cudaGetLastError();
 }
 

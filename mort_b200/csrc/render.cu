@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) mega_kernel(const __grid_cons
     const unsigned lt_mask = (1u << lane) - 1u;
     const int PT = P.lanes_per_pixel;                     // pixels per warp task (1..MEGA_PMAX)
     const int sqrt_spp = P.cam.sqrt_spp, n_subset = P.n_subset;
-    const int band_px = 8 * P.cam.width;
+    const int band_px = P.band_px;
     unsigned n_seg = 0, n_smp = 0;                        // per task, flushed to the 64-bit global counters at task end
 
     // A warp task = PT consecutive pixels = PT * n_subset samples in pixel-major order.  Lanes pull the next

@@ -18,7 +18,8 @@ struct FrameParams {
     int32_t lanes_per_pixel;        // megakernel: pixels per warp task (1..16)
     int32_t min_task_px;            // megakernel: smallest task the guided tail hands out (== lanes_per_pixel: fixed-size tasks)
     int32_t n_pixels;               // pixels THIS call renders (all of them, or the rank's 8-row bands)
-    int32_t tile_mod, tile_rem;     // tile split: local pixel index -> global pixel through 8-row bands b = k * tile_mod + tile_rem
+    int32_t tile_mod, tile_rem;     // tile split: local pixel index -> global pixel through bands b = k * tile_mod + tile_rem
+    int32_t band_px;                // pixels per band = band rows (8 unless opts.tile_rows says otherwise) x width
     int32_t n_staged;               // BVH nodes copied to shared memory per block
     int32_t accumulate;             // exact frames only: add this call's sums to what accum_exact already holds
     float4* accum;                  // W*H (null when accum_exact is used)
@@ -30,7 +31,10 @@ struct FrameParams {
     int32_t pool_overlap;           // tree scenes: classify starts on traced paths while other warps still trace (no barrier between the two)
     int32_t pool_refill;            // trace phase: lanes refill mid-traversal when at least this many of a warp's lanes are idle (0 = never)
     unsigned long long* work64;     // head of the call's sample index space [0, total_samples)
-    unsigned long long total_samples;   // n_pixels * n_subset
+    unsigned long long total_samples;   // n_frames * n_pixels * n_subset
+    unsigned long long frame_samples;   // n_pixels * n_subset
+    unsigned long long frame_words;     // exact-frame words between consecutive frames of a batch (W * H * 4)
+    uint32_t pix_mask; int32_t frame_shift;   // batch of frames in one launch: a path's pixel word = pixel | frame-in-batch << frame_shift (0: single frame)
 };
 
 struct LaunchShape { int threads, blocks, smem_bytes; };
@@ -44,8 +48,8 @@ struct PoolShape { int threads, min_blocks, pool_paths, tree; };
 cudaError_t pool_query(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes);
 cudaError_t pool_launch(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st);
 // zero / resolve the exact frame over the pixels THIS call renders (all of them, or the rank's 8-row bands)
-cudaError_t zero_exact_launch(unsigned long long* d_exact, int n_pixels_local, int width, int tile_mod, int tile_rem, cudaStream_t st);
-cudaError_t resolve_exact_tiles_launch(const unsigned long long* d_exact, int n_pixels_local, int width, int tile_mod, int tile_rem, float4* d_accum, cudaStream_t st);
+cudaError_t zero_exact_launch(unsigned long long* d_exact, int n_pixels_local, int band_px, int tile_mod, int tile_rem, cudaStream_t st);
+cudaError_t resolve_exact_tiles_launch(const unsigned long long* d_exact, int n_pixels_local, int band_px, int tile_mod, int tile_rem, float4* d_accum, cudaStream_t st);
 
 // wavefront (wavefront.cu)
 struct WavefrontBuffers;            // opaque SoA queues

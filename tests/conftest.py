@@ -61,3 +61,11 @@ def trimmed_rmse(a, b, trim=0.005):
     d2 = ((a - b) ** 2).sum(axis=1)
     keep = d2 <= np.quantile(d2, 1.0 - trim)
     return np.sqrt(((a[keep] - b[keep]) ** 2).mean(axis=0))
+
+
+def bin8(img, ok):
+    """8x8-binned means of an (H, W, 3) image over the pixels `ok` marks valid -> (means, valid-pixel counts) (as scripts/curate_golden.py)."""
+    H8, W8 = img.shape[0] // 8 * 8, img.shape[1] // 8 * 8
+    v = np.where(ok[:H8, :W8, None], img[:H8, :W8, :3], 0.0).reshape(H8 // 8, 8, W8 // 8, 8, 3).sum(axis=(1, 3))
+    n = ok[:H8, :W8].reshape(H8 // 8, 8, W8 // 8, 8).sum(axis=(1, 3))
+    return v / np.maximum(n, 1)[..., None], n

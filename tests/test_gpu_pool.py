@@ -106,3 +106,27 @@ def test_pool_through_the_host_buffer_call(renderer):
     b = renderer.render(seed=3, mode=MODE_POOL)
     assert np.array_equal(a.accum, b.accum, equal_nan=True) and np.array_equal(a.rgba8, b.rgba8)
     assert b.stats["last_kernel_launches"] >= 3
+
+
+def test_a_batch_of_frames_in_one_launch_equals_the_frames_one_by_one(renderer):
+    """opts.n_frames: the reference's frame loop (mort.cu:93-120) as ONE launch; frame k of the batch = the frame with key frame + k"""
+    import torch
+    from mort_b200.api import MODE_MEGAKERNEL, MODE_POOL, MortError
+    renderer.build_scene(1).override_camera(width=80, spp=9, depth=20).commit()
+    st = renderer.stats
+    H, W = st["height"], st["width"]
+    batch = torch.zeros(3, H, W, 4, dtype=torch.int64, device="cuda")
+    renderer.render_device(batch.data_ptr(), seed=4, frame=5, mode=MODE_POOL, exact_accum=1, n_frames=3)
+    torch.cuda.synchronize()
+    assert renderer.stats["last_samples"] == 3 * H * W * 9
+    for k in range(3):
+        one, _ = _exact(renderer, H, W, seed=4, frame=5 + k, mode=MODE_MEGAKERNEL)
+        assert torch.equal(batch[k], one), f"frame {k} of the batch"
+    fl = torch.zeros(3, H, W, 4, dtype=torch.float32, device="cuda")
+    renderer.render_device(fl.data_ptr(), seed=4, frame=5, mode=MODE_POOL, n_frames=3)
+    ref = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
+    renderer.resolve_exact_device(batch[2].contiguous().data_ptr(), ref.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(fl[2], nan=-1.0), torch.nan_to_num(ref, nan=-1.0))
+    with pytest.raises(MortError):
+        renderer.render_device(batch.data_ptr(), mode=MODE_MEGAKERNEL, exact_accum=1, n_frames=3)
