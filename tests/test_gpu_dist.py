@@ -28,7 +28,18 @@ r.set_stream(torch.cuda.current_stream().cuda_stream)
 acc = torch.zeros(st["height"], st["width"], 4, dtype=torch.int64, device="cuda")
 mod, rem = D.sample_split(rank, world)
 r.render_device(acc.data_ptr(), seed=5, frame=2, sample_mod=mod, sample_rem=rem, exact_accum=1)
-tot = D.combine(acc, how=os.environ["MORT_HOW"])
+how = os.environ["MORT_HOW"]
+if how == "cabi":          # the collective behind the C ABI (mort_comm_*): torch.distributed only carries the 128-byte NCCL id
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(Renderer.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, src=0)
+    r.comm_attach(idt.cpu().numpy().tobytes(), world, rank)
+    r.comm_reduce_exact(acc.data_ptr(), 0)
+    torch.cuda.synchronize()
+    tot = acc if rank == 0 else None
+else:
+    tot = D.combine(acc, how=how)
 if rank == 0:
     full = torch.zeros_like(acc)
     r.render_device(full.data_ptr(), seed=5, frame=2, exact_accum=1)
@@ -38,7 +49,7 @@ dist.barrier(); dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("how", ["reduce", "gather"])
+@pytest.mark.parametrize("how", ["reduce", "gather", "cabi"])
 def test_two_gpu_sample_split_matches_single_gpu(how, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
