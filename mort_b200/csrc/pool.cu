@@ -240,8 +240,23 @@ __device__ __forceinline__ void trace_refill(const FrameParams& P, const Pool& S
             if (__ballot_sync(full, have) == 0u) break;
         }
         for (;;) {                                        // traversal burst: until enough lanes have run dry
+#if defined(MORT_POSTPONE)
+            uint32_t pend = MORT_CHILD_EMPTY;
+            while (!(T.cur & MORT_LEAF_BIT)) trav_node<false>(P.sc, nullptr, 0, T, stack, tmin, best.t);
+            if (T.cur != MORT_CHILD_EMPTY) {
+                pend = T.cur; T.cur = trav_pop(T, stack, best.t);
+                while (!(T.cur & MORT_LEAF_BIT)) trav_node<false>(P.sc, nullptr, 0, T, stack, tmin, best.t);
+            }
+#pragma unroll 1
+            for (int k = 0; k < 2; k++) {
+                const uint32_t L = k == 0 ? pend : T.cur;
+                if (L != MORT_CHILD_EMPTY) leaf_intersect(P.sc, L, r, tmin, best, 0, 0x7FFFFFFF);
+            }
+            if (T.cur != MORT_CHILD_EMPTY) T.cur = trav_pop(T, stack, best.t);
+#else
             while (!(T.cur & MORT_LEAF_BIT)) trav_node<false>(P.sc, nullptr, 0, T, stack, tmin, best.t);
             if (T.cur != MORT_CHILD_EMPTY) trav_leaf(P.sc, T, stack, r, tmin, best, 0, 0x7FFFFFFF);
+#endif
             const unsigned act = __ballot_sync(full, T.cur != MORT_CHILD_EMPTY);
             if (act == 0u || (!exhausted && 32 - __popc(act) >= want)) break;
         }

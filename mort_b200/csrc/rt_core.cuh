@@ -448,10 +448,29 @@ MORT_HD bool closest_hit(const DeviceScene& sc, const Bvh4Node* staged, int n_st
     // the loop exits: the warp's lanes test nodes together and intersect leaves together instead of drifting
     // apart for the whole traversal (lane utilisation 6.6/32 with the former single loop).
     MORT_COUNT(queries, 1);
+#if defined(MORT_POSTPONE)
+    // experiment (Aila & Laine's "speculative traversal"): the first leaf a lane reaches is postponed while it descends to a second
+    // one, so the lanes of a warp leave the node loop less often
+    while (T.cur != MORT_CHILD_EMPTY) {
+        uint32_t pend = MORT_CHILD_EMPTY;
+        while (!(T.cur & MORT_LEAF_BIT)) trav_node<kStaged>(sc, staged, n_staged, T, stack, tmin, best.t);
+        if (T.cur != MORT_CHILD_EMPTY) {
+            pend = T.cur; T.cur = trav_pop(T, stack, best.t);
+            while (!(T.cur & MORT_LEAF_BIT)) trav_node<kStaged>(sc, staged, n_staged, T, stack, tmin, best.t);
+        }
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            const uint32_t L = k == 0 ? pend : T.cur;
+            if (L != MORT_CHILD_EMPTY) leaf_intersect(sc, L, r, tmin, best, order_lo, order_hi);
+        }
+        if (T.cur != MORT_CHILD_EMPTY) T.cur = trav_pop(T, stack, best.t);
+    }
+#else
     while (T.cur != MORT_CHILD_EMPTY) {
         while (!(T.cur & MORT_LEAF_BIT)) trav_node<kStaged>(sc, staged, n_staged, T, stack, tmin, best.t);
         if (T.cur != MORT_CHILD_EMPTY) trav_leaf(sc, T, stack, r, tmin, best, order_lo, order_hi);
     }
+#endif
     return best.prim != MORT_PRIM_NONE;
 }
 
