@@ -98,6 +98,38 @@ int mort_get_camera_record(mort_ctx* ctx, mscn_camera* out);               /* ev
 /* ---- commit = world::toDevice (world.cuh:98-102): flatten, SAH-build the 4-wide BVH, upload ------------ */
 int mort_commit(mort_ctx* ctx);
 
+/* ---- tree build on the GPU, refit, motion-aware bounds ----------------------------
+ * The reference builds its BVH on the host with a median split and a bubble sort, at most 1024 nodes (objects.cuh:521,528-661),
+ * and bounds a moving sphere by the union of its end boxes (objects.cuh:46-55).  Here the binned-SAH build also runs on
+ * the GPU (gpu_build.cu) and gives the SAME tree as the host builder, node for node; MORT_BUILD_AUTO uses it from 16384
+ * leaves up.  Options apply to the next mort_commit. */
+enum { MORT_BUILD_AUTO = 0, MORT_BUILD_HOST = 1, MORT_BUILD_GPU = 2 };
+typedef struct {
+    int32_t builder;        /* MORT_BUILD_* */
+    int32_t max_leaf;       /* primitives per leaf, 1..4 (0 = 4) */
+    float k_trav;           /* SAH cost of a node step relative to one sphere test (0 = 1.0) */
+    int32_t host_threads;   /* host builder: 0 = all cores */
+    int32_t gpu_small;      /* GPU builder: subtrees of at most this many primitives are built by one thread each (0 = 64) */
+    int32_t gpu_flags;      /* GPU builder: bit 0 = plain per-thread atomics (no warp / block aggregation) */
+    int32_t motion_bounds;  /* 1 = node boxes of subtrees with moving spheres are stored at time 0 and time 1 and interpolated at the ray's
+                               time (tighter than the reference's union box; hits are unchanged: the sphere test itself is exact) */
+    int32_t reserved;
+} mort_build_opts;
+typedef struct {
+    int32_t built_on_gpu, gpu_levels, gpu_small_subtrees, bvh2_nodes;
+    int32_t motion_nodes, refits, reserved[2];
+    double flatten_ms, build_ms, gpu_stream_ms, refit_ms;   /* commit: host flattening without the build; the build; its stream time; last mort_refit */
+    uint64_t gpu_workspace_bytes;
+} mort_build_info;
+int mort_set_build_opts(mort_ctx* ctx, const mort_build_opts* opts);         /* NULL = defaults */
+int mort_get_build_info(mort_ctx* ctx, mort_build_info* out);
+/* Dynamic scenes: move / resize a sphere of the committed scene (center1 = NULL: a static sphere), then mort_refit: the
+ * topology of the tree is kept, the primitive boxes and every node box are recomputed bottom-up on the GPU from the device
+ * records (one kernel per tree level).  Hits after a refit equal those of a fresh commit of the edited scene (the tree is
+ * merely less tight).  MORT_ERR_STATE without a committed scene. */
+int mort_update_sphere(mort_ctx* ctx, mort_handle sphere, const float center0[3], const float center1[3], float radius);
+int mort_refit(mort_ctx* ctx);
+
 /* ---- render (renderKernel, mort.cu:44-47,99-106; Camera::render, camera.cuh:178-208) ------------------- */
 /* Three schedulers over the same per-ray code, Philox stream and estimator:
  *   MEGAKERNEL  persistent warps, a lane owns a path from camera to termination (render.cu)
@@ -169,6 +201,13 @@ int mort_tonemap_device(mort_ctx* ctx, const void* d_accum, int samples_per_pixe
 /* Host-buffer frame (the reference-facing call): renders, tone-maps and copies back.  rgba8_out: W*H*4 bytes,
  * bottom-up (may be NULL); accum_out: W*H*4 floats (may be NULL). */
 int mort_render(mort_ctx* ctx, const mort_render_opts* opts, uint8_t* rgba8_out, float* accum_out);
+
+/* ---- image files (host buffers; no context, no device) ------------------------------------------------------------------
+ * rgba8: the frame as mort_render returns it (bottom-up rows, camera.cuh:70-78).  The extension picks the format: ".ppm" (binary
+ * P6, top-down) or ".png" (8-bit RGB, top-down).  mort_write_pfm: accum4 = W*H float4 sums, written as scale * rgb, rows bottom-up
+ * (PFM's own order), NaN-poisoned pixels stay NaN. */
+int mort_write_image(const char* path, const uint8_t* rgba8, int width, int height);
+int mort_write_pfm(const char* path, const float* accum4, int width, int height, float scale);
 
 /* ---- multi-GPU: shard by samples or tiles, ONE collective per frame -----------------------------
  * The reference is single-GPU (one renderKernel launch per frame, mort.cu:99-106).  Here every GPU renders its share of

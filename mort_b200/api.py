@@ -64,6 +64,24 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class BuildOpts(C.Structure):
+    _fields_ = [("builder", C.c_int32), ("max_leaf", C.c_int32), ("k_trav", C.c_float), ("host_threads", C.c_int32),
+                ("gpu_small", C.c_int32), ("gpu_flags", C.c_int32), ("motion_bounds", C.c_int32), ("reserved", C.c_int32)]
+
+
+class BuildInfo(C.Structure):
+    _fields_ = [("built_on_gpu", C.c_int32), ("gpu_levels", C.c_int32), ("gpu_small_subtrees", C.c_int32), ("bvh2_nodes", C.c_int32),
+                ("motion_nodes", C.c_int32), ("refits", C.c_int32), ("reserved", C.c_int32 * 2),
+                ("flatten_ms", C.c_double), ("build_ms", C.c_double), ("gpu_stream_ms", C.c_double), ("refit_ms", C.c_double),
+                ("gpu_workspace_bytes", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+BUILD_AUTO, BUILD_HOST, BUILD_GPU = 0, 1, 2
+
+
 class GroupStats(C.Structure):
     _fields_ = [("n_gpus", C.c_int32), ("split", C.c_int32), ("kernel_ms_max", C.c_double), ("kernel_ms_min", C.c_double),
                 ("collective_ms", C.c_double), ("collective_bytes", C.c_uint64), ("segments", C.c_uint64), ("samples", C.c_uint64)]
@@ -84,10 +102,10 @@ ABI_SYMBOLS = [
     "mort_add_constant_medium", "mort_add_list", "mort_list_add", "mort_add_bvh", "mort_add_box", "mort_add_rotated_box",
     "mort_host_rand",
     "mort_get_camera", "mort_set_camera", "mort_override_camera", "mort_get_camera_record",
-    "mort_commit", "mort_default_render_opts", "mort_render_device", "mort_resolve_exact_device", "mort_tonemap_device", "mort_render",
+    "mort_commit", "mort_set_build_opts", "mort_get_build_info", "mort_update_sphere", "mort_refit", "mort_default_render_opts", "mort_render_device", "mort_resolve_exact_device", "mort_tonemap_device", "mort_render",
     "mort_accumulate_exact_device", "mort_scene_fingerprint", "mort_save_checkpoint", "mort_load_checkpoint",
     "mort_render_progressive", "mort_reset_progressive",
-    "mort_trace", "mort_get_stats",
+    "mort_trace", "mort_get_stats", "mort_write_image", "mort_write_pfm",
     "mort_comm_unique_id", "mort_comm_attach", "mort_comm_detach", "mort_comm_reduce_exact",
     "mort_group_create", "mort_group_destroy", "mort_group_size", "mort_group_ctx", "mort_group_last_error", "mort_group_render", "mort_group_get_stats",
 ]
@@ -122,6 +140,8 @@ def load_library():
         "mort_get_camera": [P, C.POINTER(CameraDesc)], "mort_set_camera": [P, C.POINTER(CameraDesc)],
         "mort_override_camera": [P, I, Fl, I, I], "mort_get_camera_record": [P, P],
         "mort_commit": [P], "mort_default_render_opts": [C.POINTER(RenderOpts)],
+        "mort_set_build_opts": [P, C.POINTER(BuildOpts)], "mort_get_build_info": [P, C.POINTER(BuildInfo)],
+        "mort_update_sphere": [P, H, F3, F3, Fl], "mort_refit": [P],
         "mort_render_device": [P, C.POINTER(RenderOpts), P], "mort_resolve_exact_device": [P, P, P], "mort_tonemap_device": [P, P, I, P],
         "mort_accumulate_exact_device": [P, P, P], "mort_scene_fingerprint": [P, C.POINTER(C.c_uint64)],
         "mort_save_checkpoint": [P, C.c_char_p, P, C.c_uint32, C.c_uint32],
@@ -132,6 +152,7 @@ def load_library():
     sig.update({"mort_comm_unique_id": [P], "mort_comm_attach": [P, P, I, I], "mort_comm_detach": [P], "mort_comm_reduce_exact": [P, P, I],
                 "mort_group_create": [I, C.POINTER(C.c_int), C.POINTER(P)], "mort_group_destroy": [P], "mort_group_size": [P],
                 "mort_group_render": [P, C.POINTER(RenderOpts), I, P, P], "mort_group_get_stats": [P, C.POINTER(GroupStats)]})
+    sig.update({"mort_write_image": [C.c_char_p, P, I, I], "mort_write_pfm": [C.c_char_p, P, I, I, Fl]})
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
@@ -144,6 +165,21 @@ def load_library():
     L.mort_group_ctx.restype = P
     _lib = L
     return L
+
+
+def write_image(path, rgba8: np.ndarray):
+    """.ppm / .png from a bottom-up (H, W, 4) uint8 frame (mort_write_image; no device involved)."""
+    a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+    rc = load_library().mort_write_image(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0])
+    if rc != 0:
+        raise MortError(f"mort_write_image({path}) failed with {rc}")
+
+
+def write_pfm(path, accum: np.ndarray, scale: float):
+    a = np.ascontiguousarray(accum, dtype=np.float32)
+    rc = load_library().mort_write_pfm(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0], float(scale))
+    if rc != 0:
+        raise MortError(f"mort_write_pfm({path}) failed with {rc}")
 
 
 def _f3(v):
@@ -296,6 +332,31 @@ class Renderer:
 
     def commit(self):
         self._ck(self._L.mort_commit(self._h))
+        return self
+
+    # -- tree build on the GPU / refit / motion-aware bounds --
+    def set_build_opts(self, **kw):
+        """builder=BUILD_AUTO|BUILD_HOST|BUILD_GPU, max_leaf, k_trav, host_threads, gpu_small, gpu_flags, motion_bounds; applies to the next commit."""
+        o = BuildOpts()
+        for k, v in kw.items():
+            if not hasattr(o, k):
+                raise MortError(f"unknown build option {k}")
+            setattr(o, k, v)
+        self._ck(self._L.mort_set_build_opts(self._h, C.byref(o)))
+        return self
+
+    @property
+    def build_info(self) -> dict:
+        b = BuildInfo()
+        self._ck(self._L.mort_get_build_info(self._h, C.byref(b)))
+        return b.asdict()
+
+    def update_sphere(self, handle, center0, center1=None, radius=1.0):
+        self._ck(self._L.mort_update_sphere(self._h, handle, _f3(center0), _f3(center1) if center1 is not None else None, float(radius)))
+        return self
+
+    def refit(self):
+        self._ck(self._L.mort_refit(self._h))
         return self
 
     # -- render --

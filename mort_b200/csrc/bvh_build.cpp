@@ -12,200 +12,128 @@
 #include <cstdlib>
 #include <cstring>
 #include <future>
+#include <string>
 #include <limits>
+#include <memory>
 #include <queue>
 #include <thread>
 
+#include <atomic>
+
+#include "bvh_sah.hpp"
 #include "flatten.hpp"
 
 namespace mort {
 namespace {
 
-struct Box {
-    float lo[3], hi[3];
-    void reset() { for (int a = 0; a < 3; a++) { lo[a] = std::numeric_limits<float>::infinity(); hi[a] = -lo[a]; } }
-    void grow(const float* l, const float* h) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], l[a]); hi[a] = std::max(hi[a], h[a]); } }
-    void grow(const Box& b) { grow(b.lo, b.hi); }
-    float area() const {
-        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-        if (dx < 0 || dy < 0 || dz < 0) return 0;
-        return 2.f * (dx * dy + dy * dz + dz * dx);
-    }
-};
-
-struct Node2 { Box box; int left = -1, right = -1, first = 0, count = 0, type = 0; };
-
-constexpr int kBins = 16;
-static float kTrav = 1.0f;                 // cost of one more (binary) node relative to one sphere test; MORT_KTRAV overrides (experiments)
-inline float prim_cost(int type) { return type == MORT_OBJ_QUAD ? 1.3f : 1.0f; }
+inline float node_area(const Node2& n) { return sah_area(n.lo, n.hi); }
 
 // Subtrees over disjoint index ranges are independent, so the top `par_levels` levels hand their left child to another
-// thread and splice the two node arrays afterwards.  The tree (and therefore the 4-wide layout, which is rebuilt
-// breadth-first from the child links) does not depend on the thread count.
+// thread.  Nodes come out of one preallocated array through an atomic cursor: their numbering depends on the thread timing,
+// the tree does not (bvh_sah.hpp), and the 4-wide layout is rebuilt breadth-first from the child links.
 constexpr int kParallelMinPrims = 1 << 14;
+
+struct AtomicAlloc {
+    std::atomic<int>* next;
+    int pair() { return next->fetch_add(2); }
+};
 
 struct Builder {
     const std::vector<BuildPrim>& prims;
     std::vector<int> idx;
-    std::vector<Node2> nodes;
-    int max_leaf = MORT_MAX_LEAF;
-    explicit Builder(const std::vector<BuildPrim>& p) : prims(p) {
-        if (const char* e = getenv("MORT_MAX_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 8) max_leaf = v; }   // experiments only
-        if (const char* e = getenv("MORT_KTRAV")) { float v = (float)atof(e); if (v > 0) kTrav = v; }
+    std::unique_ptr<Node2[]> nodes;      // 2n + 1, uninitialised: every node is written before it is read
+    std::atomic<int> next{1};
+    SahParams P;
+    Builder(const std::vector<BuildPrim>& p, const SahParams& par) : prims(p), P(par) {
         idx.resize(p.size());
         for (size_t i = 0; i < p.size(); i++) idx[i] = (int)i;
-        nodes.reserve(p.size() * 2 + 1);
+        nodes.reset(new Node2[p.size() * 2 + 1]);
     }
-    float centroid(int i, int a) const { return 0.5f * (prims[i].lo[a] + prims[i].hi[a]); }
-
-    static void splice(std::vector<Node2>& dst, const std::vector<Node2>& src) {
-        const int off = (int)dst.size();
-        for (Node2 n : src) { if (n.left >= 0) n.left += off; if (n.right >= 0) n.right += off; dst.push_back(n); }
-    }
-
-    // builds the subtree over idx[b, e) into `nodes` (appending); returns its root's index in `nodes`
-    int build(std::vector<Node2>& nodes, int b, int e, int par_levels) {
-        int me = (int)nodes.size();
-        nodes.emplace_back();
-        Box box, cbox; box.reset(); cbox.reset();
-        bool homogeneous = true; float cost_sum = 0;
-        for (int i = b; i < e; i++) {
-            const BuildPrim& p = prims[idx[i]];
-            box.grow(p.lo, p.hi);
-            float c[3] = {centroid(idx[i], 0), centroid(idx[i], 1), centroid(idx[i], 2)};
-            cbox.grow(c, c);
-            homogeneous = homogeneous && p.type == prims[idx[b]].type;
-            cost_sum += prim_cost(p.type);
+    // one node of the top levels: the same statistics, sweep and decision as sah_build_subtree, with the two children built concurrently
+    void build(int me, int b, int e, int par_levels) {
+        if (par_levels <= 0 || e - b < kParallelMinPrims) {
+            AtomicAlloc A{&next};
+            sah_build_subtree(prims.data(), idx.data(), nodes.get(), me, b, e, P, A);
+            return;
         }
-        nodes[me].box = box;
-        int n = e - b;
-        bool can_leaf = n <= max_leaf && homogeneous;
-
-        // best binned SAH split
-        float best_cost = std::numeric_limits<float>::infinity(); int best_axis = -1, best_bin = -1;
-        float parent_area = std::max(box.area(), 1e-30f);
-        if (n >= 2) {
-            for (int a = 0; a < 3; a++) {
-                float ext = cbox.hi[a] - cbox.lo[a];
-                if (!(ext > 0)) continue;
-                Box bb[kBins]; int cnt[kBins]; float cst[kBins];
-                for (int k = 0; k < kBins; k++) { bb[k].reset(); cnt[k] = 0; cst[k] = 0; }
-                float scale = kBins / ext;
-                for (int i = b; i < e; i++) {
-                    int k = std::min(kBins - 1, std::max(0, (int)((centroid(idx[i], a) - cbox.lo[a]) * scale)));
-                    bb[k].grow(prims[idx[i]].lo, prims[idx[i]].hi); cnt[k]++; cst[k] += prim_cost(prims[idx[i]].type);
-                }
-                float right_area[kBins], right_cost[kBins]; Box r; r.reset(); float rc = 0;
-                for (int k = kBins - 1; k > 0; k--) { r.grow(bb[k]); rc += cst[k]; right_area[k] = r.area(); right_cost[k] = rc; }
-                Box l; l.reset(); float lc = 0; int ln = 0;
-                for (int k = 0; k < kBins - 1; k++) {
-                    l.grow(bb[k]); lc += cst[k]; ln += cnt[k];
-                    if (ln == 0 || ln == n) continue;
-                    float c = kTrav + (l.area() * lc + right_area[k + 1] * right_cost[k + 1]) / parent_area;
-                    if (c < best_cost) { best_cost = c; best_axis = a; best_bin = k; }
-                }
+        SahNodeStats S; sah_stats_clear(S);
+        for (int i = b; i < e; i++) sah_stats_add(S, prims[idx[i]], idx[i]);
+        Node2 N; sah_node_set_box(N, S);
+        float best_cost = INFINITY; int best_axis = -1, best_bin = -1, best_left = 0;
+        const float parent_area = std::max(sah_area(S.lo, S.hi), 1e-30f);
+        for (int a = 0; a < 3; a++) {
+            if (!sah_axis_open(S, a)) continue;
+            SahBins B; sah_bins_clear(B);
+            const float scale = sah_axis_scale(S, a), lo = S.clo[a];
+            for (int i = b; i < e; i++) {
+                const BuildPrim& p = prims[idx[i]];
+                const int k = sah_bin_of(sah_centroid(p, a), lo, scale);
+                sah_grow(B.lo[k], B.hi[k], p.lo, p.hi); B.cnt[k]++; B.cst[k] += sah_prim_cost(p.type);
             }
+            sah_sweep_axis(a, B, S.n, parent_area, P.k_trav, best_cost, best_axis, best_bin, best_left);
         }
-        if (can_leaf && (best_axis < 0 || cost_sum <= best_cost)) {
-            nodes[me].first = b; nodes[me].count = n; nodes[me].type = prims[idx[b]].type;
-            return me;
-        }
-        int mid;
-        if (best_axis >= 0) {
-            float ext = cbox.hi[best_axis] - cbox.lo[best_axis], scale = kBins / ext, lo = cbox.lo[best_axis];
-            int a = best_axis, bin = best_bin;
-            auto it = std::partition(idx.begin() + b, idx.begin() + e, [&](int i) {
-                int k = std::min(kBins - 1, std::max(0, (int)((centroid(i, a) - lo) * scale)));
-                return k <= bin;
-            });
-            mid = (int)(it - idx.begin());
-        } else if (!homogeneous) {
-            int t0 = prims[idx[b]].type;
-            auto it = std::partition(idx.begin() + b, idx.begin() + e, [&](int i) { return prims[i].type == t0; });
-            mid = (int)(it - idx.begin());
-        } else {
-            mid = b + n / 2;      // coincident centroids: any balanced split
-        }
-        if (mid <= b || mid >= e) mid = b + n / 2;
-        if (par_levels > 0 && n >= kParallelMinPrims) {
-            std::vector<Node2> L, R;
-            auto left = std::async(std::launch::async, [&] { return build(L, b, mid, par_levels - 1); });
-            const int r = build(R, mid, e, par_levels - 1);
-            const int l = left.get();
-            const int off_l = (int)nodes.size(); splice(nodes, L);
-            const int off_r = (int)nodes.size(); splice(nodes, R);
-            nodes[me].left = off_l + l; nodes[me].right = off_r + r;
-            return me;
-        }
-        int l = build(nodes, b, mid, 0);
-        int r = build(nodes, mid, e, 0);
-        nodes[me].left = l; nodes[me].right = r;
-        return me;
+        int n_ref_left = 0;
+        if (best_axis < 0 && sah_homogeneous(S)) { const int pv = sah_ref_pivot(S); for (int i = b; i < e; i++) n_ref_left += idx[i] < pv ? 1 : 0; }
+        const SahSplit d = sah_decide(S, P, best_cost, best_axis, best_bin, best_left, n_ref_left);      // never a leaf: n >= kParallelMinPrims > max_leaf
+        auto it = std::partition(idx.begin() + b, idx.begin() + e, [&](int i) { return sah_goes_left(d, prims[i], i); });
+        const int mid = (int)(it - idx.begin());
+        const int c = next.fetch_add(2);
+        N.left = c; N.right = c + 1;
+        nodes[me] = N;
+        auto left = std::async(std::launch::async, [&] { build(c, b, mid, par_levels - 1); });
+        build(c + 1, mid, e, par_levels - 1);
+        left.get();
     }
 };
 
 }  // namespace
 
-void build_bvh4(const std::vector<BuildPrim>& prims, std::vector<Bvh4Node>& out, std::vector<int>& order_out, BuildStats& stats) {
+void build_bvh4(const std::vector<BuildPrim>& prims, std::vector<Bvh4Node>& out, std::vector<int>& order_out, BuildStats& stats, const BuildOptions& opt) {
     auto t0 = std::chrono::steady_clock::now();
-    out.clear(); order_out.clear();
-    const float inf = std::numeric_limits<float>::infinity();
-    auto clear_node = [&](Bvh4Node& n) {
-        for (int k = 0; k < 4; k++) {
-            n.lox[k] = n.loy[k] = n.loz[k] = inf; n.hix[k] = n.hiy[k] = n.hiz[k] = -inf;
-            n.child[k] = MORT_CHILD_EMPTY; n.spare[k] = 0;
-        }
-    };
-    if (prims.empty()) { Bvh4Node n; clear_node(n); out.push_back(n); stats.n_nodes = 1; return; }
+    out.clear(); order_out.clear(); stats.level_first.clear();
+    if (prims.empty()) { Bvh4Node n; bvh4_clear_node(n); out.push_back(n); stats.n_nodes = 1; stats.level_first = {0, 1}; return; }
 
-    Builder B(prims);
-    // 2^levels concurrent subtrees at most; MORT_BUILD_THREADS=1 forces the serial build
-    unsigned hw = std::thread::hardware_concurrency(); if (hw == 0) hw = 1;
-    if (const char* e = getenv("MORT_BUILD_THREADS")) { int v = atoi(e); if (v >= 1) hw = (unsigned)v; }
+    const SahParams P = {opt.max_leaf >= 1 && opt.max_leaf <= 8 ? opt.max_leaf : MORT_MAX_LEAF, opt.k_trav > 0 ? opt.k_trav : 1.0f};
+    Builder B(prims, P);
+    // 2^levels concurrent subtrees at most; threads = 1 forces the serial build
+    unsigned hw = opt.threads > 0 ? (unsigned)opt.threads : std::thread::hardware_concurrency(); if (hw == 0) hw = 1;
     int levels = 0; while ((1u << levels) < hw && levels < 6) levels++;
-    int root = B.build(B.nodes, 0, (int)prims.size(), levels);
+    const int root = 0;
+    B.build(root, 0, (int)prims.size(), levels);
     order_out = B.idx;
-    stats.n_bvh2_nodes = (int)B.nodes.size();
+    stats.n_bvh2_nodes = B.next.load();
+    const Node2* N2 = B.nodes.get();
 
+    // collapse, breadth-first: a 4-wide node's index is its position in the queue order, so levels are contiguous
     struct Item { int n2, n4, depth; };
     std::queue<Item> q;
-    out.emplace_back(); clear_node(out[0]);
+    out.emplace_back(); bvh4_clear_node(out[0]);
     q.push(Item{root, 0, 1});
-    double sah = 0; float root_area = std::max(B.nodes[root].box.area(), 1e-30f);
+    double sah = 0; const float root_area = std::max(node_area(N2[root]), 1e-30f);
     int max_depth4 = 1, leaf_slots = 0;
+    stats.level_first.push_back(0);
     while (!q.empty()) {
         Item it = q.front(); q.pop();
-        max_depth4 = std::max(max_depth4, it.depth);
-        int ch[4]; int nc = 0;
-        const Node2& n2 = B.nodes[it.n2];
-        if (n2.count > 0) ch[nc++] = it.n2;                 // the whole scene is one leaf
-        else { ch[nc++] = n2.left; ch[nc++] = n2.right; }
-        while (nc < 4) {
-            int pick = -1; float best = -1;
-            for (int k = 0; k < nc; k++) if (B.nodes[ch[k]].count == 0 && B.nodes[ch[k]].box.area() > best) { best = B.nodes[ch[k]].box.area(); pick = k; }
-            if (pick < 0) break;
-            int c = ch[pick];
-            ch[pick] = B.nodes[c].left; ch[nc++] = B.nodes[c].right;
-        }
-        sah += kTrav * B.nodes[it.n2].box.area() / root_area;
+        if (it.depth > max_depth4) { max_depth4 = it.depth; stats.level_first.push_back(it.n4); }
+        int ch[4];
+        const int nc = bvh4_open_children(N2, it.n2, ch);
+        sah += (double)bvh4_node_sah(N2[it.n2], P.k_trav, root_area);
         for (int k = 0; k < nc; k++) {
-            const Node2& c = B.nodes[ch[k]];
-            Bvh4Node& dst = out[it.n4];
-            dst.lox[k] = c.box.lo[0]; dst.loy[k] = c.box.lo[1]; dst.loz[k] = c.box.lo[2];
-            dst.hix[k] = c.box.hi[0]; dst.hiy[k] = c.box.hi[1]; dst.hiz[k] = c.box.hi[2];
+            const Node2& c = N2[ch[k]];
+            bvh4_set_child_box(out[it.n4], k, c);
             if (c.count > 0) {
-                uint32_t w = MORT_LEAF_BIT | (c.type == MORT_OBJ_QUAD ? MORT_LEAF_QUAD_BIT : 0u) | ((uint32_t)(c.count - 1) << 27) | (uint32_t)c.first;
-                out[it.n4].child[k] = w;
+                out[it.n4].child[k] = bvh4_leaf_word(c);
                 leaf_slots++;
-                sah += c.count * prim_cost(c.type) * c.box.area() / root_area;
+                sah += (double)bvh4_leaf_sah(c, root_area);
             } else {
                 int n4 = (int)out.size();
-                out.emplace_back(); clear_node(out.back());
+                out.emplace_back(); bvh4_clear_node(out.back());
                 out[it.n4].child[k] = (uint32_t)n4;
                 q.push(Item{ch[k], n4, it.depth + 1});
             }
         }
     }
+    stats.level_first.push_back((int)out.size());
     stats.n_nodes = (int)out.size(); stats.max_depth = max_depth4; stats.n_leaf_slots = leaf_slots; stats.sah_cost = sah;
     stats.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }

@@ -13,7 +13,9 @@
 #include <vector>
 
 #include "flatten.hpp"
+#include "gpu_build.hpp"
 #include "mort_b200.h"
+#include "refit.hpp"
 #include "render.hpp"
 #include "scene.hpp"
 
@@ -194,12 +196,88 @@ int mort_override_camera(mort_ctx* ctx, int w, float aspect, int spp, int depth)
 int mort_get_camera_record(mort_ctx* ctx, mscn_camera* out) { CTX_CHECK(ctx && out); ctx->scene.cam.to_record(*out); return MORT_OK; }
 
 // ---- commit ---------------------------------------------------------------------------------------------
+// tree builder handed to flatten_scene: the GPU builder (gpu_build.cu) for large scenes, the host builder otherwise
+static bool commit_builder(void* user, const std::vector<BuildPrim>& prims, std::vector<Bvh4Node>& nodes, std::vector<int>& order, BuildStats& stats,
+                           const BuildOptions& opt, std::string* err) {
+    mort_ctx* ctx = static_cast<mort_ctx*>(user);
+    const int b = ctx->build_opts.builder;
+    const bool gpu = b == MORT_BUILD_GPU || (b == MORT_BUILD_AUTO && prims.size() >= 16384);
+    if (!gpu) { build_bvh4(prims, nodes, order, stats, opt); return true; }
+    return gpu_build_bvh4(prims, nodes, order, stats, opt, ctx->stream, ctx->build_opts.gpu_flags, err);
+}
+static BuildOptions build_options(const mort_ctx* ctx) {
+    BuildOptions o;
+    const mort_build_opts& b = ctx->build_opts;
+    if (b.max_leaf >= 1 && b.max_leaf <= MORT_MAX_LEAF) o.max_leaf = b.max_leaf;
+    if (b.k_trav > 0) o.k_trav = b.k_trav;
+    o.threads = b.host_threads > 0 ? b.host_threads : 0;
+    o.gpu_small = b.gpu_small > 0 ? b.gpu_small : 0;
+    return o;
+}
+// bottom-up bounds pass on the device records (refit.cu).  union_pass: the tree every kernel reads (needed after edits; a fresh build
+// already holds these boxes).  motion: the time-0 / time-1 copy that motion.cu's kernels interpolate.
+static int run_refit(mort_ctx* ctx, bool union_pass, bool motion) {
+    const FlatScene& f = ctx->flat;
+    const size_t ns = f.spheres.size(), nq = f.quads.size(), nb = f.nodes.size() * sizeof(Bvh4Node);
+    for (int t = 0; t < (motion ? 2 : 1); t++) {
+        if (!ctx->d_sphere_box[t] && ns) CU(ctx->arena.alloc(ns * 24, &ctx->d_sphere_box[t]));
+        if (!ctx->d_quad_box[t] && nq) CU(ctx->arena.alloc(nq * 24, &ctx->d_quad_box[t]));
+    }
+    if (!ctx->d_extent) { void* p = nullptr; CU(ctx->arena.alloc(256, &p)); ctx->d_extent = static_cast<unsigned*>(p); }
+    if (motion && !ctx->d_node_t1) {
+        void* p = nullptr; CU(ctx->arena.alloc(nb, &p)); ctx->d_node_t0 = static_cast<Bvh4Node*>(p);
+        CU(ctx->arena.alloc(nb, &p)); ctx->d_node_t1 = static_cast<Bvh4Node*>(p);
+        CU(cudaMemcpyAsync(ctx->d_node_t0, ctx->dscene.nodes, nb, cudaMemcpyDeviceToDevice, ctx->stream));      // child words + the inverted boxes of empty slots
+    }
+    RefitArgs a;
+    a.n_nodes = (int)f.nodes.size();
+    a.spheres = ctx->dscene.spheres; a.quads = ctx->dscene.quads; a.instances = ctx->dscene.instances; a.n_spheres = (int)ns; a.n_quads = (int)nq;
+    for (int t = 0; t < 2; t++) { a.sphere_box[t] = ctx->d_sphere_box[t]; a.quad_box[t] = ctx->d_quad_box[t]; }
+    a.extent_key = ctx->d_extent; a.level_first = f.stats.level_first;
+    const Camera& c = ctx->scene.cam;
+    a.cam_center[0] = c.center.x; a.cam_center[1] = c.center.y; a.cam_center[2] = c.center.z;
+    float pad = 0.f, extent = 0.f;
+    if (union_pass) {
+        a.nodes = const_cast<Bvh4Node*>(ctx->dscene.nodes); a.node_t1 = nullptr; a.motion = false;
+        CU(refit_run(a, ctx->stream, &pad, &extent));
+        ctx->flat.stats.pad = pad; ctx->flat.stats.scene_extent = extent;
+    }
+    if (motion) {
+        a.nodes = ctx->d_node_t0; a.node_t1 = ctx->d_node_t1; a.motion = true;
+        CU(refit_run(a, ctx->stream, &pad, &extent));
+        ctx->motion_active = true; ctx->motion_nodes = (int)f.nodes.size();
+    }
+    return MORT_OK;
+}
+
+int mort_set_build_opts(mort_ctx* ctx, const mort_build_opts* o) {
+    CTX_CHECK(ctx);
+    mort_build_opts d; memset(&d, 0, sizeof(d));
+    if (o) d = *o;
+    if (d.builder < MORT_BUILD_AUTO || d.builder > MORT_BUILD_GPU || d.max_leaf < 0 || d.max_leaf > MORT_MAX_LEAF || d.k_trav < 0 || d.gpu_small < 0)
+        return fail(ctx, MORT_ERR_ARG, "mort_set_build_opts: builder 0..2, max_leaf 0..4, k_trav >= 0, gpu_small >= 0");
+    ctx->build_opts = d; invalidate(ctx);
+    return MORT_OK;
+}
+int mort_get_build_info(mort_ctx* ctx, mort_build_info* out) {
+    CTX_CHECK(ctx && out);
+    memset(out, 0, sizeof(*out));
+    const BuildStats& b = ctx->flat.stats;
+    out->built_on_gpu = b.built_on_gpu; out->gpu_levels = b.gpu_levels; out->gpu_small_subtrees = b.gpu_small_subtrees; out->bvh2_nodes = b.n_bvh2_nodes;
+    out->motion_nodes = ctx->motion_active ? ctx->motion_nodes : 0; out->refits = ctx->refits;
+    out->flatten_ms = ctx->flatten_ms; out->build_ms = b.build_ms; out->gpu_stream_ms = b.gpu_kernel_ms; out->refit_ms = ctx->refit_ms;
+    out->gpu_workspace_bytes = b.gpu_workspace_bytes;
+    return MORT_OK;
+}
+
 int mort_commit(mort_ctx* ctx) {
     CTX_CHECK(ctx);
     invalidate(ctx);                                      // a failed re-commit must not leave a "committed" context over freed memory
     CU(cudaSetDevice(ctx->device));
     std::string e;
-    if (!flatten_scene(ctx->scene, ctx->flat, &e)) return fail(ctx, MORT_ERR_SCENE, e);
+    const auto tf = std::chrono::steady_clock::now();
+    if (!flatten_scene(ctx->scene, ctx->flat, &e, build_options(ctx), commit_builder, ctx)) return fail(ctx, MORT_ERR_SCENE, e);
+    ctx->flatten_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tf).count() - ctx->flat.stats.build_ms;
     // the traversal stack holds 48 entries and a 4-wide node pushes at most 3: refuse (loudly) a tree it could overflow on
     if (!ctx->flat.linear && ctx->flat.stats.max_depth * 3 > 48)
         return fail(ctx, MORT_ERR_SCENE, "BVH deeper than 16 levels: the traversal stack (48 entries) could overflow; scene rejected");
@@ -210,6 +288,9 @@ int mort_commit(mort_ctx* ctx) {
     if (ctx->stream != ctx->own_stream) CU(cudaStreamSynchronize(ctx->own_stream));
     ctx->arena.release();
     memset(&ctx->dscene, 0, sizeof(ctx->dscene));
+    for (int t = 0; t < 2; t++) ctx->d_sphere_box[t] = ctx->d_quad_box[t] = nullptr;      // arena-owned: gone
+    ctx->d_node_t0 = ctx->d_node_t1 = nullptr; ctx->d_extent = nullptr; ctx->motion_active = false; ctx->motion_nodes = 0;
+    ctx->sphere_dirty.assign(ctx->scene.spheres.size(), 0); ctx->n_dirty = 0; ctx->refits = 0; ctx->refit_ms = 0;
     DeviceScene d; memset(&d, 0, sizeof(d));
     const FlatScene& f = ctx->flat;
     CU(ctx->arena.upload(f.nodes, &d.nodes)); d.n_nodes = (int)f.nodes.size();
@@ -246,7 +327,54 @@ int mort_commit(mort_ctx* ctx) {
     for (const ImageRec& im : ctx->scene.images) { int32_t wh[2] = {im.width, im.height}; mix(wh, sizeof(wh)); mixv(im.rgb); }
     int32_t fl[5] = {f.light_kind, f.post_media_order, f.two_pass, f.empty, f.linear}; mix(fl, sizeof(fl));
     ctx->geometry_hash = h;                              // the camera is mixed in on demand: it may move without a new commit
+    // motion-aware node boxes: one bottom-up pass over the uploaded tree (the topology was built from the union boxes)
+    if (ctx->build_opts.motion_bounds && !f.linear && f.n_moving > 0) { const int rc = run_refit(ctx, false, true); if (rc != MORT_OK) return rc; }
     ctx->committed = true;
+    return MORT_OK;
+}
+
+// ---- dynamic scenes: edit + refit -------------------------------------------------------------------------------------------
+int mort_update_sphere(mort_ctx* ctx, mort_handle sphere, const float c0[3], const float c1[3], float radius) {
+    CTX_CHECK(ctx && c0);
+    if (sphere.type != MORT_OBJ_SPHERE || sphere.idx < 0 || sphere.idx >= (int)ctx->scene.spheres.size()) return fail(ctx, MORT_ERR_ARG, "mort_update_sphere: not a sphere handle");
+    if (!(radius == radius) || !(c0[0] == c0[0] && c0[1] == c0[1] && c0[2] == c0[2]) || (c1 && !(c1[0] == c1[0] && c1[1] == c1[1] && c1[2] == c1[2])))
+        return fail(ctx, MORT_ERR_ARG, "mort_update_sphere: NaN");
+    const V3 a = v3(c0); V3 b; if (c1) b = v3(c1);
+    ctx->scene.update_sphere(sphere.idx, a, c1 ? &b : nullptr, radius);
+    // a sphere copied into a light or a medium-boundary record, or a scene that was not committed: only a new commit will do
+    if (!ctx->committed || (size_t)sphere.idx >= ctx->flat.sphere_pinned.size() || ctx->flat.sphere_pinned[sphere.idx] || ctx->sphere_dirty.size() != ctx->scene.spheres.size()) { invalidate(ctx); return MORT_OK; }
+    if (!ctx->sphere_dirty[sphere.idx]) { ctx->sphere_dirty[sphere.idx] = 1; ctx->n_dirty++; }
+    return MORT_OK;
+}
+int mort_refit(mort_ctx* ctx) {
+    CTX_CHECK(ctx);
+    if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "mort_refit: no committed scene (a changed light / medium-boundary sphere or a structural change needs mort_commit)");
+    CU(cudaSetDevice(ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    FlatScene& f = ctx->flat;
+    if (ctx->n_dirty > 0) {
+        // patch the device records of the edited spheres (a sphere slot may appear in several records: instanced lists)
+        size_t lo = f.spheres.size(), hi = 0;
+        uint64_t h = ctx->geometry_hash;
+        auto mix = [&h](const void* p, size_t n) { const uint8_t* b = static_cast<const uint8_t*>(p); for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+        for (size_t r = 0; r < f.spheres.size(); r++) {
+            const int slot = f.sphere_info[r].obj_idx;
+            if (slot < 0 || (size_t)slot >= ctx->sphere_dirty.size() || !ctx->sphere_dirty[slot]) continue;
+            const mscn_sphere& sp = ctx->scene.spheres[slot];
+            SphereGeom& g = f.spheres[r];
+            g.cx = sp.center[0]; g.cy = sp.center[1]; g.cz = sp.center[2]; g.r = sp.radius;
+            g.vx = sp.moves ? sp.center_vec[0] : 0.f; g.vy = sp.moves ? sp.center_vec[1] : 0.f; g.vz = sp.moves ? sp.center_vec[2] : 0.f;
+            lo = std::min(lo, r); hi = std::max(hi, r + 1);
+            mix(&r, sizeof(r)); mix(&g, sizeof(g));
+        }
+        if (hi > lo) CU(cudaMemcpyAsync(const_cast<SphereGeom*>(ctx->dscene.spheres) + lo, f.spheres.data() + lo, (hi - lo) * sizeof(SphereGeom), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->geometry_hash = h;
+        std::fill(ctx->sphere_dirty.begin(), ctx->sphere_dirty.end(), 0); ctx->n_dirty = 0;
+    }
+    if (!f.linear) { const int rc = run_refit(ctx, true, ctx->motion_active); if (rc != MORT_OK) return rc; }
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->refits++;
+    ctx->refit_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return MORT_OK;
 }
 
@@ -374,12 +502,14 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         p.pool_refill = o.pool_refill < 0 ? 0 : (o.pool_refill == 0 ? (tree && media ? 16 : 0) : std::min(31, o.pool_refill));
         p.pool_overlap = (o.pool_flags & 1) ? 0 : ((o.pool_flags & 2) ? 1 : (media && ps.min_blocks == 1 ? 1 : 0));
         int occ = 0, regs = 0, smem = 0;
-        CU(pool_query(ps, &occ, &regs, &smem));
+        const bool motion = ctx->motion_active && tree;      // kernels of motion.cu over the time-0 boxes + their change to time 1
+        if (motion) { p.sc.nodes = ctx->d_node_t0; p.sc.node_dt = ctx->d_node_t1; }
+        CU(motion ? pool_query_motion(ps, &occ, &regs, &smem) : pool_query(ps, &occ, &regs, &smem));
         if (occ < 1) return fail(ctx, MORT_ERR_ARG, "mort_render: a pool of " + std::to_string(ps.pool_paths) + " paths (" + std::to_string(smem) + " B) does not fit in a block's shared memory");
         const int bps = std::min(occ, ps.min_blocks);
         CU(cudaMemsetAsync(ctx->d_work64, 0, sizeof(unsigned long long), ctx->stream));
         if (!o.accumulate || !o.exact_accum) CU(zero_exact_launch(target, p.n_pixels * n_frames, p.band_px, p.tile_mod, p.tile_rem, ctx->stream));
-        CU(pool_launch(p, ps, bps * ctx->prop.multiProcessorCount, ctx->stream));
+        CU(motion ? pool_launch_motion(p, ps, bps * ctx->prop.multiProcessorCount, ctx->stream) : pool_launch(p, ps, bps * ctx->prop.multiProcessorCount, ctx->stream));
         launches = 2;
         if (!o.exact_accum) { CU(resolve_exact_tiles_launch(target, p.n_pixels * n_frames, p.band_px, p.tile_mod, p.tile_rem, reinterpret_cast<float4*>(d_accum), ctx->stream)); launches = 3; }
         ctx->stats.threads_per_block = ps.threads; ctx->stats.blocks_per_sm = bps; ctx->stats.regs_per_thread = regs; ctx->stats.staged_nodes = 0;
@@ -595,7 +725,12 @@ int mort_trace(mort_ctx* ctx, const float* rays7, int n, mhit_record* out, mhit_
     if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * sizeof(mhit_record));
     if (e == cudaSuccess && probes && nm) e = cudaMalloc(&d_pr, (size_t)n * nm * sizeof(mhit_medium_probe));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays7, (size_t)n * 28, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = trace_launch(ctx->dscene, d_rays, n, d_out, d_pr, (flags & MORT_TRACE_BRUTE_FORCE) ? 1 : 0, ctx->d_mat_offsets, ctx->stream);
+    if (e == cudaSuccess) {
+        if (ctx->motion_active && !(flags & MORT_TRACE_BRUTE_FORCE)) {      // through the interpolated boxes, like the renders of this scene
+            DeviceScene ms = ctx->dscene; ms.nodes = ctx->d_node_t0; ms.node_dt = ctx->d_node_t1;
+            e = trace_launch_motion(ms, d_rays, n, d_out, d_pr, 0, ctx->d_mat_offsets, ctx->stream);
+        } else e = trace_launch(ctx->dscene, d_rays, n, d_out, d_pr, (flags & MORT_TRACE_BRUTE_FORCE) ? 1 : 0, ctx->d_mat_offsets, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(mhit_record), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && d_pr) e = cudaMemcpyAsync(probes, d_pr, (size_t)n * nm * sizeof(mhit_medium_probe), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -25,6 +25,14 @@ struct DeviceArena {                 // every device allocation of one committed
         *out = reinterpret_cast<const T*>(p);
         return e;
     }
+    cudaError_t alloc(size_t n_bytes, void** out) {
+        *out = nullptr;
+        if (n_bytes == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(out, n_bytes);
+        if (e != cudaSuccess) { *out = nullptr; return e; }
+        ptrs.push_back(*out); bytes += n_bytes;
+        return cudaSuccess;
+    }
     void release() { for (void* p : ptrs) cudaFree(p); ptrs.clear(); bytes = 0; }
 };
 
@@ -59,6 +67,15 @@ struct mort_ctx {
     unsigned long long* d_pool_exact = nullptr; size_t pool_exact_pixels = 0;   // block wavefront: exact frame behind a float4 request
     unsigned long long* d_work64 = nullptr;     // block wavefront: head of the sample index space
     uint64_t prog_fingerprint = 0; uint32_t prog_frames = 0, prog_seed = 0;
+    // tree build / refit / motion bounds
+    mort_build_opts build_opts = {};
+    double flatten_ms = 0, refit_ms = 0;
+    int refits = 0, motion_nodes = 0;
+    bool motion_active = false;                                   // d_node_t0 / d_node_t1 hold the tree's boxes at time 0 and their change to time 1
+    Bvh4Node* d_node_t0 = nullptr;
+    void* d_sphere_box[2] = {nullptr, nullptr}; void* d_quad_box[2] = {nullptr, nullptr};   // refit work buffers (arena-owned, allocated on first use)
+    Bvh4Node* d_node_t1 = nullptr; unsigned* d_extent = nullptr;
+    std::vector<uint8_t> sphere_dirty; int n_dirty = 0;           // mort_update_sphere since the last refit / commit
 };
 
 #define CTX_CHECK(c) do { if (!(c)) return MORT_ERR_ARG; } while (0)

@@ -90,6 +90,7 @@ struct CameraParams {                        // camera.cuh fields a kernel needs
 
 struct DeviceScene {
     const Bvh4Node* nodes; int32_t n_nodes;
+    const Bvh4Node* node_dt;                 // motion-aware bounds: box at time 1 minus box at time 0 per child (nodes then holds the time-0 boxes); else null
     const SphereGeom* spheres; const PrimInfo* sphere_info; int32_t n_spheres;
     const QuadRec* quads; int32_t n_quads;
     const uint8_t* sphere_cls; const uint8_t* quad_cls;   // shade class (SHADE_*) of each record's material: one byte decides a hit's shading queue

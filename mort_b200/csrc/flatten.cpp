@@ -137,7 +137,7 @@ void camera_params(const Camera& c, CameraParams& o) {
     o.width = c.image_width; o.height = c.image_height; o.sqrt_spp = c.sqrt_spp; o.bounce_limit = c.bounce_limit;
 }
 
-bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
+bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const BuildOptions& opt, BvhBuildFn build, void* build_user) {
     out = FlatScene();
     Flattener F(s, out);
     auto fail = [&](const std::string& m) { if (err) *err = m; return false; };
@@ -162,6 +162,7 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
         out.noises.push_back(n);
     }
 
+    out.sphere_pinned.assign(s.spheres.size(), 0);
     // ---- visible leaves in world::hit order (world.cuh:110-168) ----
     std::vector<Chain> chains;
     int top_type = 0, top_idx = 0;
@@ -228,6 +229,7 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
                 B.type = type; B.inst = F.instance_of(c);
                 if (type == MORT_OBJ_SPHERE) {
                     const mscn_sphere& sp = s.spheres[idx];
+                    out.sphere_pinned[idx] = 1;
                     B.a[0][0] = sp.center[0]; B.a[0][1] = sp.center[1]; B.a[0][2] = sp.center[2]; B.a[0][3] = sp.radius;
                     if (sp.moves) { B.a[1][0] = sp.center_vec[0]; B.a[1][1] = sp.center_vec[1]; B.a[1][2] = sp.center_vec[2]; }
                 } else fill_quad_rows(s.quads[idx], B.a);
@@ -245,7 +247,7 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
     auto light_prim = [&](int type, int idx) {
         LightPrim L; memset(&L, 0, sizeof(L)); L.kind = LIGHT_INVALID;
         if (type == MORT_OBJ_SPHERE && idx >= 0 && idx < (int)s.spheres.size()) {
-            L.kind = LIGHT_SPHERE; const mscn_sphere& sp = s.spheres[idx];
+            L.kind = LIGHT_SPHERE; const mscn_sphere& sp = s.spheres[idx]; out.sphere_pinned[idx] = 1;
             L.a[0][0] = sp.center[0]; L.a[0][1] = sp.center[1]; L.a[0][2] = sp.center[2]; L.a[0][3] = sp.radius;
         } else if (type == MORT_OBJ_QUAD && idx >= 0 && idx < (int)s.quads.size()) {
             L.kind = LIGHT_QUAD; fill_quad_rows(s.quads[idx], L.a); L.area = s.quads[idx].area; L.D = s.quads[idx].D;
@@ -274,11 +276,15 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
         BuildPrim& p = prims[i];
         F.leaf_world_box(out.leaves[i].type, out.leaves[i].idx, chains[i], p.lo, p.hi);
         p.type = out.leaves[i].type; p.ref = (int)i;
-        for (int a = 0; a < 3; a++) { M = fmaxf(M, fabsf(p.lo[a])); M = fmaxf(M, fabsf(p.hi[a])); }
+        if (p.type == MORT_OBJ_SPHERE && s.spheres[out.leaves[i].idx].moves) out.n_moving++;
+        for (int a = 0; a < 3; a++) {
+            if (!(p.lo[a] <= p.hi[a])) return fail("a primitive has a NaN coordinate (no box bounds it)");
+            M = fmaxf(M, fabsf(p.lo[a])); M = fmaxf(M, fabsf(p.hi[a]));
+        }
         // The reference's BVH boxes stop containing an object when its bubble sort physically swapped something a wrapper
         // points at, or a list grew after it was wrapped (objects.cuh:630-661, 463-469): the reference then culls that object
         // view-dependently.  That is not reproducible without running its BVH; refuse instead of rendering something else.
-        for (int a = 0; a < 3; a++) {
+        for (int a = 0; a < 3 && !s.edited; a++) {          // (an edited scene, mort_update_sphere, has left the reference's build behind)
             const float tol = 1e-4f * fmaxf(1.0f, fmaxf(fabsf(p.lo[a]), fabsf(p.hi[a])));
             if (p.lo[a] < gates[i].lo[a] - tol || p.hi[a] > gates[i].hi[a] + tol)
                 return fail("a bvh node box of the reference's build does not contain an object below it (a wrapper's target was moved by the "
@@ -315,9 +321,11 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err) {
         Bvh4Node n; memset(&n, 0, sizeof(n));
         for (int k = 0; k < 4; k++) { n.lox[k] = n.loy[k] = n.loz[k] = INFINITY; n.hix[k] = n.hiy[k] = n.hiz[k] = -INFINITY; n.child[k] = MORT_CHILD_EMPTY; }
         out.nodes.assign(1, n);
-        out.stats.n_nodes = 1; out.stats.max_depth = 0;
+        out.stats.n_nodes = 1; out.stats.max_depth = 0; out.stats.level_first = {0, 1};
     } else {
-        build_bvh4(prims, out.nodes, order, out.stats);
+        std::string berr;
+        if (build) { if (!build(build_user, prims, out.nodes, order, out.stats, opt, &berr)) return fail("tree build: " + berr); }
+        else build_bvh4(prims, out.nodes, order, out.stats, opt);
     }
 
     // ---- emit primitive records in leaf order; rewrite leaf child words to per-type record indices ----

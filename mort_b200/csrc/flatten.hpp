@@ -19,6 +19,14 @@ struct BuildStats {
     int n_leaves = 0, n_nodes = 0, n_bvh2_nodes = 0, max_depth = 0, n_leaf_slots = 0;
     double sah_cost = 0, build_ms = 0;
     float pad = 0, scene_extent = 0;
+    std::vector<int> level_first;              // 4-wide nodes are laid out breadth-first: level d = [level_first[d], level_first[d+1])
+    int built_on_gpu = 0, gpu_levels = 0, gpu_small_subtrees = 0;
+    size_t gpu_workspace_bytes = 0; double gpu_kernel_ms = 0;   // GPU builder: workspace, CUDA-event time of its kernels
+};
+struct BuildOptions {
+    int max_leaf = MORT_MAX_LEAF; float k_trav = 1.0f;
+    int threads = 0;            // host builder: 0 = all cores
+    int gpu_small = 0;          // GPU builder: subtrees of at most this many primitives are built by one thread each (0 = 64)
 };
 
 struct FlatScene {
@@ -34,19 +42,25 @@ struct FlatScene {
     std::vector<BoundaryPrim> boundary;
     std::vector<LightPrim> lights;
     std::vector<LeafRef> leaves;               // visit order (kept for tests / stats)
+    std::vector<uint8_t> sphere_pinned;        // per sphere slot: copied into a light or medium-boundary record (mort_update_sphere then needs a new commit)
+    int n_moving = 0;                          // leaves that are moving spheres
     int light_kind = LIGHT_NONE;
     int post_media_order = 0, two_pass = 0, empty = 1, linear = 0;
     CameraParams cam;
     BuildStats stats;
 };
 
-bool flatten_scene(const Scene& s, FlatScene& out, std::string* err);
-void camera_params(const Camera& c, CameraParams& out);
-
 // bvh_build.cpp: binned SAH over boxes -> BVH2 -> collapse to 4-wide, breadth-first layout.
 struct BuildPrim { float lo[3], hi[3]; int type; int ref; };   // ref = index into FlatScene::leaves
+// A tree builder: boxes in, 4-wide nodes (leaf words = positions in order_out) + the leaf order out.  The host builder
+// (build_bvh4) is the default; capi.cu passes the GPU builder (gpu_build.cu) for large scenes.  Both give the same tree.
+typedef bool (*BvhBuildFn)(void* user, const std::vector<BuildPrim>& prims, std::vector<Bvh4Node>& nodes, std::vector<int>& order_out,
+                           BuildStats& stats, const BuildOptions& opt, std::string* err);
+bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const BuildOptions& opt = BuildOptions(), BvhBuildFn build = nullptr, void* build_user = nullptr);
+void camera_params(const Camera& c, CameraParams& out);
+
 struct Bvh4Leaf { int first, count, type; };                    // range in `order_out`
 void build_bvh4(const std::vector<BuildPrim>& prims, std::vector<Bvh4Node>& nodes, std::vector<int>& order_out,
-                BuildStats& stats);
+                BuildStats& stats, const BuildOptions& opt = BuildOptions());
 
 }  // namespace mort

@@ -14,7 +14,8 @@
 
 static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
                             "            [--mode mega|wave|pool] [--stage N] [--bps blocks/SM] [--tpb threads] [--pool paths/block] [--field G [--fieldcam 0|1]]\n"
-                            "            [--assets DIR] [--out image.ppm] [--hdr image.pfm] [--device K] [--load scene.mscn] [--dump scene.mscn]\n"
+                            "            [--builder auto|host|gpu] [--motion-bounds] [--gpu-small N] [--gpu-flags N]   tree build (GPU from 16384 leaves up by default)\n"
+                            "            [--assets DIR] [--out image.ppm|image.png] [--hdr image.pfm] [--device K] [--load scene.mscn] [--dump scene.mscn]\n"
                             "            [--scene-file scene.txt] [--dump-text scene.txt]\n"
                             "            [--accumulate [--checkpoint FILE [--resume]]]\n"
                             "            [--gpus N [--split sample|tile]]   N GPUs of this box, one NCCL reduce of the partial frames per frame\n"); return -1; }
@@ -25,6 +26,7 @@ int main(int argc, char** argv) {
     int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = 0, mode = MORT_MODE_POOL, bps = 0, tpb = 0, field = 0, fieldcam = 0, pool = 0, refill = 0, gpus = 1, split = MORT_SPLIT_SAMPLE, xflags = 0;
     float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr, load, dump, ckpt, text_in, text_out;
     bool accumulate = false, resume = false;
+    mort_build_opts bo; memset(&bo, 0, sizeof(bo));
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         auto nx = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(-1); } return argv[++i]; };
@@ -39,6 +41,8 @@ int main(int argc, char** argv) {
         else if (a == "--bps") bps = atoi(nx()); else if (a == "--tpb") tpb = atoi(nx());
         else if (a == "--field") field = atoi(nx()); else if (a == "--fieldcam") fieldcam = atoi(nx());
         else if (a == "--gpus") gpus = atoi(nx()); else if (a == "--split") { std::string m = nx(); split = m == "tile" ? MORT_SPLIT_TILE : MORT_SPLIT_SAMPLE; }
+        else if (a == "--builder") { std::string m = nx(); bo.builder = m == "host" ? MORT_BUILD_HOST : m == "gpu" ? MORT_BUILD_GPU : MORT_BUILD_AUTO; }
+        else if (a == "--motion-bounds") bo.motion_bounds = 1; else if (a == "--gpu-small") bo.gpu_small = atoi(nx()); else if (a == "--gpu-flags") bo.gpu_flags = atoi(nx());
         else if (a == "--pool") pool = atoi(nx()); else if (a == "--xflags") xflags = atoi(nx()); else if (a == "--refill") refill = atoi(nx());
         else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : m == "mega" ? MORT_MODE_MEGAKERNEL : MORT_MODE_POOL; }
         else return usage();
@@ -54,6 +58,7 @@ int main(int argc, char** argv) {
             int rc = !text_in.empty() ? mort_load_scene_text(c, text_in.c_str(), assets.c_str()) : !load.empty() ? mort_load_scene(c, load.c_str(), assets.c_str())
                      : field > 0 ? mort_build_sphere_field(c, field, 69420, fieldcam) : mort_build_scene(c, scene, assets.c_str());
             if (rc == MORT_OK) rc = mort_override_camera(c, width, aspect, spp, depth);
+            if (rc == MORT_OK) rc = mort_set_build_opts(c, &bo);
             if (rc == MORT_OK) rc = mort_commit(c);
             if (rc != MORT_OK) { fprintf(stderr, "mort: rank %d: %s\n", r, mort_last_error(c)); mort_group_destroy(g); return 3; }
         }
@@ -73,13 +78,7 @@ int main(int argc, char** argv) {
                "\"collective_ms\":%.3f,\"collective_mb\":%.1f,\"msamples_per_s\":%.3f,\"mrays_per_s\":%.3f}\n",
                scene, gpus, split == MORT_SPLIT_TILE ? "tile" : "sample", st.width, st.height, st.sqrt_spp * st.sqrt_spp, st.bounce_limit, ms, gs.kernel_ms_max, gs.kernel_ms_min,
                gs.collective_ms, gs.collective_bytes / 1048576.0, (double)gs.samples / (ms * 1e3), (double)gs.segments / (ms * 1e3));
-        if (!out.empty()) {
-            FILE* f = fopen(out.c_str(), "wb");
-            if (!f) { perror(out.c_str()); mort_group_destroy(g); return 4; }
-            fprintf(f, "P6\n%d %d\n255\n", st.width, st.height);
-            for (int y = st.height - 1; y >= 0; y--) for (int x = 0; x < st.width; x++) fwrite(&img[4 * ((size_t)y * st.width + x)], 1, 3, f);
-            fclose(f);
-        }
+        if (!out.empty() && mort_write_image(out.c_str(), img.data(), st.width, st.height) != MORT_OK) { fprintf(stderr, "mort: cannot write %s (.ppm or .png)\n", out.c_str()); mort_group_destroy(g); return 4; }
         mort_group_destroy(g);
         return 0;
     }
@@ -93,7 +92,9 @@ int main(int argc, char** argv) {
     if (mort_override_camera(ctx, width, aspect, spp, depth) != MORT_OK) return die("camera");
     if (!dump.empty() && mort_dump_scene(ctx, dump.c_str()) != MORT_OK) return die("dump");
     if (!text_out.empty() && mort_dump_scene_text(ctx, text_out.c_str()) != MORT_OK) return die("dump-text");
+    if (mort_set_build_opts(ctx, &bo) != MORT_OK) return die("build options");
     if (mort_commit(ctx) != MORT_OK) return die("commit");
+    mort_build_info bi; mort_get_build_info(ctx, &bi);
     mort_stats st; mort_get_stats(ctx, &st);
     std::vector<uint8_t> img((size_t)st.width * st.height * 4);
     std::vector<float> acc(hdr.empty() ? 0 : (size_t)st.width * st.height * 4);
@@ -121,24 +122,14 @@ int main(int argc, char** argv) {
         printf("Avg. time per frame: %3.1f ms\n", total / (f + 1));
     }
     double samples = (double)st.width * st.height * st.sqrt_spp * st.sqrt_spp;
-    printf("{\"scene\":%d,\"width\":%d,\"height\":%d,\"spp_eff\":%d,\"depth\":%d,\"ms\":%.3f,\"msamples_per_s\":%.3f,\"mrays_per_s\":%.3f,\"nodes\":%d,\"leaves\":%d,\"regs\":%d,\"bps\":%d,\"build_ms\":%.2f}\n",
+    printf("{\"scene\":%d,\"width\":%d,\"height\":%d,\"spp_eff\":%d,\"depth\":%d,\"ms\":%.3f,\"msamples_per_s\":%.3f,\"mrays_per_s\":%.3f,\"nodes\":%d,\"leaves\":%d,\"regs\":%d,\"bps\":%d,\"build_ms\":%.2f,\"flatten_ms\":%.2f,\"upload_ms\":%.2f,\"built_on_gpu\":%d,\"gpu_stream_ms\":%.2f,\"gpu_levels\":%d,\"motion_nodes\":%d,\"sah\":%.4f}\n",
            scene, st.width, st.height, st.sqrt_spp * st.sqrt_spp, st.bounce_limit, st.last_render_ms, samples / (st.last_render_ms * 1e3),
-           (double)st.last_segments / (st.last_render_ms * 1e3), st.n_nodes, st.n_leaves, st.regs_per_thread, st.blocks_per_sm, st.build_ms);
-    if (!out.empty()) {
-        FILE* f = fopen(out.c_str(), "wb");
-        if (!f) { perror(out.c_str()); mort_destroy(ctx); return 4; }
-        fprintf(f, "P6\n%d %d\n255\n", st.width, st.height);
-        for (int y = st.height - 1; y >= 0; y--) for (int x = 0; x < st.width; x++) fwrite(&img[4 * ((size_t)y * st.width + x)], 1, 3, f);
-        fclose(f);
-    }
-    if (!hdr.empty()) {
-        // linear radiance as PFM (rows bottom-up — the frame's own order, camera.cuh:70-78); NaN-poisoned pixels stay NaN
-        FILE* f = fopen(hdr.c_str(), "wb");
-        if (!f) { perror(hdr.c_str()); mort_destroy(ctx); return 4; }
-        fprintf(f, "PF\n%d %d\n-1.0\n", st.width, st.height);
-        const float inv = (float)(1.0 / ((double)st.sqrt_spp * st.sqrt_spp * frames_total));
-        for (size_t i = 0; i < (size_t)st.width * st.height; i++) { float px[3] = {acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv}; fwrite(px, 4, 3, f); }
-        fclose(f);
+           (double)st.last_segments / (st.last_render_ms * 1e3), st.n_nodes, st.n_leaves, st.regs_per_thread, st.blocks_per_sm, st.build_ms,
+           bi.flatten_ms, st.upload_ms, bi.built_on_gpu, bi.gpu_stream_ms, bi.gpu_levels, bi.motion_nodes, st.sah_cost);
+    if (!out.empty() && mort_write_image(out.c_str(), img.data(), st.width, st.height) != MORT_OK) { fprintf(stderr, "mort: cannot write %s (.ppm or .png)\n", out.c_str()); mort_destroy(ctx); return 4; }
+    // linear radiance as PFM (rows bottom-up — the frame's own order, camera.cuh:70-78); NaN-poisoned pixels stay NaN
+    if (!hdr.empty() && mort_write_pfm(hdr.c_str(), acc.data(), st.width, st.height, (float)(1.0 / ((double)st.sqrt_spp * st.sqrt_spp * frames_total))) != MORT_OK) {
+        fprintf(stderr, "mort: cannot write %s\n", hdr.c_str()); mort_destroy(ctx); return 4;
     }
     mort_destroy(ctx);
     return 0;

@@ -25,6 +25,7 @@
 #include "accum.cuh"
 #include "render.hpp"
 #include "rt_core.cuh"
+#include "trace_body.cuh"
 
 namespace mort {
 
@@ -198,7 +199,7 @@ __device__ __forceinline__ void trace_refill(const FrameParams& P, const Pool& S
     const unsigned lt = (1u << lane) - 1u;
     const float tmin = 0.001f;
     StackEntry stack[MORT_STACK];
-    Trav T; T.idx = T.idy = T.idz = T.oix = T.oiy = T.oiz = 0.f; T.nxo = 0; T.nyo = 4; T.nzo = 8; T.cur = MORT_CHILD_EMPTY; T.sp = 0;
+    Trav T; T.idx = T.idy = T.idz = T.oix = T.oiy = T.oiz = 0.f; T.nxo = 0; T.nyo = 4; T.nzo = 8; T.cur = MORT_CHILD_EMPTY; T.sp = 0; MORT_SET_TM(T, 0.f);
     Ray r; r.o = r.d = mk3(0, 0, 0); r.tm = 0.f;
     Hit best; best.t = INFINITY; best.prim = MORT_PRIM_NONE; best.a = best.b = 0.f;
     unsigned slot = 0; bool have = false;
@@ -404,13 +405,22 @@ PoolFn pool_variant_of(const PoolShape& s) {
     if (s.threads >= 384) return s.min_blocks >= 2 ? (PoolFn)pool_kernel<384, 2, kTree> : (PoolFn)pool_kernel<384, 1, kTree>;
     return s.min_blocks >= 3 ? (PoolFn)pool_kernel<256, 3, kTree> : (PoolFn)pool_kernel<256, 2, kTree>;
 }
+#if defined(MORT_MOTION_BOUNDS)
+PoolFn pool_variant(const PoolShape& s) { return pool_variant_of<true>(s); }         // motion boxes live in a tree
+#else
 PoolFn pool_variant(const PoolShape& s) { return s.tree ? pool_variant_of<true>(s) : pool_variant_of<false>(s); }
+#endif
 int pool_threads(const PoolShape& s) { return s.threads >= 1024 ? 1024 : s.threads >= 768 ? 768 : s.threads >= 640 ? 640 : s.threads >= 512 ? 512 : s.threads >= 384 ? 384 : 256; }
 int pool_smem(const PoolShape& s) { return s.pool_paths * (kPoolWords * 4 + kPoolLists * 2); }
 
 }  // namespace
 
-cudaError_t pool_query(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes) {
+#if defined(MORT_MOTION_BOUNDS)
+#define POOL_EXPORT(name) name##_motion
+#else
+#define POOL_EXPORT(name) name
+#endif
+cudaError_t POOL_EXPORT(pool_query)(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes) {
     PoolFn fn = pool_variant(want);
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, (const void*)fn);
@@ -423,7 +433,7 @@ cudaError_t pool_query(const PoolShape& want, int* blocks_per_sm, int* regs, int
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void*)fn, pool_threads(want), (size_t)smem);
 }
 
-cudaError_t pool_launch(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st) {
+cudaError_t POOL_EXPORT(pool_launch)(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st) {
     PoolFn fn = pool_variant(shape);
     const int smem = pool_smem(shape);
     cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -432,6 +442,21 @@ cudaError_t pool_launch(const FrameParams& p, const PoolShape& shape, int blocks
     return cudaLaunchKernel((const void*)fn, dim3(blocks), dim3(pool_threads(shape)), args, (size_t)smem, st);
 }
 
+#if defined(MORT_MOTION_BOUNDS)
+// parity hook for scenes committed with motion boxes: the same record as render.cu's trace_kernel, through THIS unit's traversal
+__global__ void __launch_bounds__(128) trace_motion_kernel(const __grid_constant__ DeviceScene sc, const float* __restrict__ rays, int n,
+                                                           mhit_record* __restrict__ out, mhit_medium_probe* __restrict__ probes,
+                                                           int brute_force, const int32_t* __restrict__ mat_offsets) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) trace_one(sc, rays, i, out, probes, brute_force, mat_offsets);
+}
+cudaError_t trace_launch_motion(const DeviceScene& sc, const float* d_rays, int n, mhit_record* d_out, mhit_medium_probe* d_probes,
+                                int brute_force, const int32_t* d_mat_offsets, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    trace_motion_kernel<<<(n + 127) / 128, 128, 0, st>>>(sc, d_rays, n, d_out, d_probes, brute_force, d_mat_offsets);
+    return cudaGetLastError();
+}
+#else
 // ------------------------------------------------------------------------------------------------------
 // zero / resolve the exact frame over the pixels one call renders (all of them, or a rank's 8-row bands)
 // ------------------------------------------------------------------------------------------------------
@@ -459,5 +484,6 @@ cudaError_t resolve_exact_tiles_launch(const unsigned long long* d_exact, int n_
     resolve_exact_tiles_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ulonglong2*>(d_exact), n_local, band_px, tile_mod > 1 ? tile_mod : 1, tile_rem, d_accum);
     return cudaGetLastError();
 }
+#endif
 
 }  // namespace mort

@@ -47,6 +47,9 @@ cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, int min_
 struct PoolShape { int threads, min_blocks, pool_paths, tree; };
 cudaError_t pool_query(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes);
 cudaError_t pool_launch(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st);
+// the same kernel compiled with motion-aware node boxes (motion.cu): p.sc.nodes = boxes at time 0, p.sc.node_dt = change to time 1
+cudaError_t pool_query_motion(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes);
+cudaError_t pool_launch_motion(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st);
 // zero / resolve the exact frame over the pixels THIS call renders (all of them, or the rank's 8-row bands)
 cudaError_t zero_exact_launch(unsigned long long* d_exact, int n_pixels_local, int band_px, int tile_mod, int tile_rem, cudaStream_t st);
 cudaError_t resolve_exact_tiles_launch(const unsigned long long* d_exact, int n_pixels_local, int band_px, int tile_mod, int tile_rem, float4* d_accum, cudaStream_t st);
@@ -61,6 +64,8 @@ cudaError_t wavefront_render(const FrameParams& p, WavefrontBuffers* buf, int n_
 // parity hook + tone pipeline (render.cu)
 cudaError_t trace_launch(const DeviceScene& sc, const float* d_rays, int n, mhit_record* d_out, mhit_medium_probe* d_probes,
                          int brute_force, const int32_t* d_mat_offsets, cudaStream_t st);
+cudaError_t trace_launch_motion(const DeviceScene& sc, const float* d_rays, int n, mhit_record* d_out, mhit_medium_probe* d_probes,
+                                int brute_force, const int32_t* d_mat_offsets, cudaStream_t st);
 cudaError_t accumulate_exact_launch(unsigned long long* d_sum, const unsigned long long* d_frame, int n_pixels, cudaStream_t st);
 cudaError_t resolve_exact_launch(const unsigned long long* d_exact, int n_pixels, float4* d_accum, cudaStream_t st);
 cudaError_t tonemap_launch(const float4* d_accum, int n_pixels, float scale, uint8_t* d_rgba8, cudaStream_t st);

@@ -339,11 +339,19 @@ MORT_HD float safe_rcp_dir(float d) {
 #else
 #define MORT_SET_TOP(T, e) ((void)0)
 #endif
+#if defined(MORT_MOTION_BOUNDS)
+#define MORT_SET_TM(T, v) ((T).tm = (v))
+#else
+#define MORT_SET_TM(T, v) ((void)0)
+#endif
 struct Trav {
     float idx, idy, idz, oix, oiy, oiz;                 // 1 / d and o / d per axis: a slab plane is one FMA
     int nxo, nyo, nzo;                                   // float offsets of the ray's near-plane rows inside a Bvh4Node (far = 12/20/28 - near)
     uint32_t cur;                                        // node index | leaf word | MORT_CHILD_EMPTY = finished
     int sp;
+#if defined(MORT_MOTION_BOUNDS)
+    float tm;                                            // ray time
+#endif
     StackEntry top;                                      // copy of stack[sp - 1]: a pop hands it out at once and starts loading the entry below
 };
 MORT_HD void trav_begin(Trav& T, const Ray& r) {
@@ -352,7 +360,7 @@ MORT_HD void trav_begin(Trav& T, const Ray& r) {
     // per-ray octant: which of the node's lo/hi planes is the entry ("near") plane on each axis.  Picking the
     // rows by address replaces 12 of the 18 min/max per child (float offsets into Bvh4Node: lo rows at 0/4/8, hi at 12/16/20).
     T.nxo = T.idx < 0.f ? 12 : 0; T.nyo = T.idy < 0.f ? 16 : 4; T.nzo = T.idz < 0.f ? 20 : 8;
-    T.cur = 0; T.sp = 0; T.top.child = MORT_CHILD_EMPTY; T.top.t = 0.f;       // root
+    T.cur = 0; T.sp = 0; MORT_SET_TM(T, r.tm); T.top.child = MORT_CHILD_EMPTY; T.top.t = 0.f;       // root
 }
 // entries whose entry distance is beyond the current best cannot contain a closer-or-equal hit
 MORT_HD uint32_t trav_pop(Trav& T, const StackEntry* stack, float best_t) {
@@ -398,6 +406,25 @@ MORT_HD void trav_node(const DeviceScene& sc, const Bvh4Node* staged, int n_stag
         nx = ld4(n + nxo); ny = ld4(n + nyo); nz = ld4(n + nzo); fx = ld4(n + fxo); fy = ld4(n + fyo); fz = ld4(n + fzo); chf = ld4(n + 24);
     }
     (void)staged; (void)n_staged;
+    // Motion-aware bounds (mort_build_opts.motion_bounds; the reference bounds a moving sphere by the union of its end boxes,
+    // objects.cuh:46-55): sc.nodes then holds every child box at time 0 and sc.node_dt the difference to the box at time 1, and the
+    // box a ray is tested against is the one at ITS time.  Centres move linearly and radii are constant, so lerp(box0, box1, t)
+    // contains every primitive below at time t; parents hold unions of their children's end boxes, which contain the union of
+    // the lerps.  One FMA per plane.  Compiled only into the kernels of motion.cu (a run-time branch here cost the 64-register
+    // kernels 260 B of extra spills, ptxas -v), which are launched only for scenes committed with motion boxes.
+#if defined(MORT_MOTION_BOUNDS)
+    {
+        const float* m = reinterpret_cast<const float*>(sc.node_dt + cur);
+        const float tm = T.tm;
+        F4 d;
+        d = ld4(m + nxo); nx.x = fmaf(tm, d.x, nx.x); nx.y = fmaf(tm, d.y, nx.y); nx.z = fmaf(tm, d.z, nx.z); nx.w = fmaf(tm, d.w, nx.w);
+        d = ld4(m + nyo); ny.x = fmaf(tm, d.x, ny.x); ny.y = fmaf(tm, d.y, ny.y); ny.z = fmaf(tm, d.z, ny.z); ny.w = fmaf(tm, d.w, ny.w);
+        d = ld4(m + nzo); nz.x = fmaf(tm, d.x, nz.x); nz.y = fmaf(tm, d.y, nz.y); nz.z = fmaf(tm, d.z, nz.z); nz.w = fmaf(tm, d.w, nz.w);
+        d = ld4(m + fxo); fx.x = fmaf(tm, d.x, fx.x); fx.y = fmaf(tm, d.y, fx.y); fx.z = fmaf(tm, d.z, fx.z); fx.w = fmaf(tm, d.w, fx.w);
+        d = ld4(m + fyo); fy.x = fmaf(tm, d.x, fy.x); fy.y = fmaf(tm, d.y, fy.y); fy.z = fmaf(tm, d.z, fy.z); fy.w = fmaf(tm, d.w, fy.w);
+        d = ld4(m + fzo); fz.x = fmaf(tm, d.x, fz.x); fz.y = fmaf(tm, d.y, fz.y); fz.z = fmaf(tm, d.z, fz.z); fz.w = fmaf(tm, d.w, fz.w);
+    }
+#endif
     float tn[4]; uint32_t cw[4] = {(uint32_t)f2i_bits(chf.x), (uint32_t)f2i_bits(chf.y), (uint32_t)f2i_bits(chf.z), (uint32_t)f2i_bits(chf.w)};
     const float nxa[4] = {nx.x, nx.y, nx.z, nx.w}, nya[4] = {ny.x, ny.y, ny.z, ny.w}, nza[4] = {nz.x, nz.y, nz.z, nz.w};
     const float fxa[4] = {fx.x, fx.y, fx.z, fx.w}, fya[4] = {fy.x, fy.y, fy.z, fy.w}, fza[4] = {fz.x, fz.y, fz.z, fz.w};

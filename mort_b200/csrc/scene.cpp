@@ -244,6 +244,17 @@ Handle Scene::add_moving_sphere(V3 c1, V3 c2, float r, Handle mat, bool skip) {
     spheres.push_back(s);
     return Handle{MORT_OBJ_SPHERE, (int)spheres.size() - 1};
 }
+bool Scene::update_sphere(int idx, V3 c1, const V3* c2, float r) {
+    if (idx < 0 || idx >= (int)spheres.size()) return false;
+    mscn_sphere& s = spheres[idx];
+    put3(s.center, c1); s.radius = r;
+    V3 rv(r, r, r); float b1[6];
+    box_from_points(b1, c1 - rv, c1 + rv);
+    if (c2) { float b2[6]; s.moves = 1; put3(s.center_vec, *c2 - c1); box_from_points(b2, *c2 - rv, *c2 + rv); box_union(s.bbox, b1, b2); }
+    else { s.moves = 0; put3(s.center_vec, V3(0, 0, 0)); memcpy(s.bbox, b1, sizeof(b1)); }
+    edited = true; journal_complete = false;            // the journal no longer describes the arrays
+    return true;
+}
 Handle Scene::add_quad(V3 Q, V3 u, V3 v, Handle mat, bool skip) {
     jlog(*this, "quad " + fs3(Q) + " " + fs3(u) + " " + fs3(v) + " " + handle_token(mat, 'm') + hid(skip));
     mscn_quad q; memset(&q, 0, sizeof(q));

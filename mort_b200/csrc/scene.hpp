@@ -100,6 +100,7 @@ public:
     // ---- hittables (objects.cuh) ----
     Handle add_sphere(V3 c, float r, Handle mat, bool skip = false);
     Handle add_moving_sphere(V3 c1, V3 c2, float r, Handle mat, bool skip = false);
+    bool update_sphere(int idx, V3 c1, const V3* c2, float r);          // dynamic scenes: new centre(s) / radius for an existing sphere (marks the scene edited)
     Handle add_quad(V3 Q, V3 u, V3 v, Handle mat, bool skip = false);
     Handle add_translate(Handle obj, V3 offset, bool skip = false);
     Handle add_rotate_y(Handle obj, float theta_deg, bool skip = false);
@@ -139,6 +140,7 @@ public:
     std::vector<ImageRec> images;
     std::vector<mscn_noise> noises;
     bool bvh_mode = false;
+    bool edited = false;                                 // a primitive changed after construction (mort_update_sphere): the reference-BVH boxes are stale
     Camera cam;
     std::string error;
     // Journal of the builder calls in the order they were made, one scene-text statement each (scene_text.cpp).

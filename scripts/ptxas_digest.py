@@ -17,7 +17,7 @@ def main():
     args = [a for a in args if a != "--sass"]
     src, extra = args[0], args[1:]
     obj = "/tmp/ptxas_digest_" + os.path.basename(src) + ".o"
-    cmd = ["nvcc", "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xptxas", "-v", "-Xcompiler", "-fPIC",
+    cmd = ["nvcc", "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-Xptxas", "-v", "-Xcompiler", "-fPIC",
            "-I" + CSRC, "-I" + os.path.join(ROOT, "include")] + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
     out = subprocess.run(cmd, capture_output=True, text=True).stderr
     cur = None

@@ -40,10 +40,23 @@ def hostsim():
     out = os.path.join(ROOT, "tests", "hostsim", "hostsim.bin")
     src = [os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")] + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in
                                                                       ("scene.cpp", "scenes.cpp", "scene_text.cpp", "flatten.cpp", "bvh_build.cpp")]
-    deps = src + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in ("rt_core.cuh", "device_types.h", "flatten.hpp", "scene.hpp")]
+    deps = src + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in ("rt_core.cuh", "device_types.h", "flatten.hpp", "scene.hpp", "bvh_sah.hpp")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "mort_b200", "csrc"),
                                "-I" + os.path.join(ROOT, "include")] + src + ["-o", out])
+    return out
+
+
+@pytest.fixture(scope="session")
+def buildsim():
+    """Test-only serial run of the GPU tree builder's and the refit pass's per-thread bodies (tests/hostsim/buildsim.cpp)."""
+    out = os.path.join(ROOT, "tests", "hostsim", "buildsim.bin")
+    src = [os.path.join(ROOT, "tests", "hostsim", "buildsim.cpp")] + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in
+                                                                       ("scene.cpp", "scenes.cpp", "scene_text.cpp", "flatten.cpp", "bvh_build.cpp")]
+    deps = src + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in ("bvh_sah.hpp", "gpu_build_core.cuh", "gpu_build_driver.hpp", "refit_core.cuh", "device_types.h", "flatten.hpp", "scene.hpp")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "mort_b200", "csrc"),
+                               "-I" + os.path.join(ROOT, "include")] + src + ["-o", out, "-lpthread"])
     return out
 
 
