@@ -136,7 +136,9 @@ int mort_refit(mort_ctx* ctx);
  *   WAVEFRONT   one kernel per stage over SoA queues in HBM (wavefront.cu)
  *   POOL        block wavefront: one persistent kernel, every thread block alternates trace / (classify /) shade phases over a
  *               pool of paths in its shared memory, shading sorted by material class (pool.cu)
- * MEGAKERNEL and POOL accumulate exactly (integers) and render bit-identical frames. */
+ * MEGAKERNEL and POOL accumulate exactly (integers) and render bit-identical frames.
+ * A scene in which a constant_medium is reached through translate / rotate_y / list wrappers (hitDispatch allows it, objects.cuh:875-877;
+ * no shipped scene does it) is always rendered by the block wavefront's general-media build (stages.cu), whatever `mode` says. */
 enum { MORT_MODE_MEGAKERNEL = 0, MORT_MODE_WAVEFRONT = 1, MORT_MODE_POOL = 2 };
 typedef struct {
     uint32_t seed, frame;          /* Philox key; the reference's seed is 69420 (mort.cu:707) */

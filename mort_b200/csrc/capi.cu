@@ -67,9 +67,7 @@ int mort_create(int cuda_device, mort_ctx** out) {
         delete ctx; return MORT_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    const char* fix = getenv("MORT_STACK_FIX");            // experiments: create (default) | render | off
-    ctx->stack_fix = fix ? (strcmp(fix, "off") == 0 ? 0 : (strcmp(fix, "render") == 0 ? 2 : 1)) : 1;
-    if (ctx->stack_fix == 1) raise_stack_limit();
+    raise_stack_limit();                                   // (when to do it was an experiment: profiles/r01_stack_limit_ab.jsonl)
     *out = ctx;
     return MORT_OK;
 }
@@ -81,7 +79,7 @@ int mort_destroy(mort_ctx* ctx) {
     if (ctx->comm) mort_comm_detach(ctx);
     ctx->arena.release();
     wavefront_free(ctx->wave);
-    cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_mat_offsets); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgba); cudaFree(ctx->d_prog); cudaFree(ctx->d_pool_exact); cudaFree(ctx->d_work64);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_work); cudaFree(ctx->d_mat_offsets); cudaFree(ctx->d_accum); cudaFree(ctx->d_rgba); cudaFree(ctx->d_prog); cudaFree(ctx->d_pool_exact); cudaFree(ctx->d_work64); cudaFree(ctx->d_trace);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -309,6 +307,7 @@ int mort_commit(mort_ctx* ctx) {
     CU(ctx->arena.upload(imgs, &d.images)); d.n_images = (int)imgs.size();
     CU(ctx->arena.upload(f.noises, &d.noises)); d.n_noises = (int)f.noises.size();
     CU(ctx->arena.upload(f.media, &d.media)); d.n_media = (int)f.media.size();
+    d.n_media_top = 0; for (const Medium& M : f.media) d.n_media_top += M.top_level ? 1 : 0;
     CU(ctx->arena.upload(f.boundary, &d.boundary)); d.n_boundary = (int)f.boundary.size();
     CU(ctx->arena.upload(f.lights, &d.lights)); d.n_lights = (int)f.lights.size(); d.light_kind = f.light_kind;
     d.post_media_order = f.post_media_order; d.two_pass = f.two_pass; d.empty = f.empty; d.linear = f.linear;
@@ -402,6 +401,9 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "mort_render: scene not committed (call mort_commit)");
     mort_render_opts o; if (opts_in) o = *opts_in; else mort_default_render_opts(&o);
     CU(cudaSetDevice(ctx->device));
+    // a scene with media nested in wrappers / lists is rendered by the one kernel that carries that visit order (stages.cu)
+    const bool general_media = ctx->flat.two_pass == 2;
+    if (general_media) { o.mode = MORT_MODE_POOL; o.threads_per_block = 512; o.blocks_per_sm = 2; o.pool_paths = 1024; o.pool_refill = -1; }
     const CameraParams& cam = ctx->flat.cam;
     if (o.sample_mod < 1 || o.sample_rem < 0 || o.sample_rem >= o.sample_mod) return fail(ctx, MORT_ERR_ARG, "mort_render: bad sample split");
     FrameParams p; memset(&p, 0, sizeof(p));
@@ -420,14 +422,12 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         p.n_pixels = n;
     }
     // pixels per warp task: enough samples per task (~2048) to amortise the end-of-task tail, at most 16 pixels
-    int task_samples = 2048;
-    if (const char* e = getenv("MORT_TASK_SAMPLES")) { int v = atoi(e); if (v >= 32) task_samples = v; }   // experiments only
+    const int task_samples = 2048;                                    // (swept 256..8192 in profiles/r01_task_sweep.jsonl)
     int PT = p.n_subset > 0 ? (task_samples + p.n_subset - 1) / p.n_subset : 1;
     PT = std::max(1, std::min(16, PT));
     p.lanes_per_pixel = PT;
     // guided tail: tasks shrink to >= 256 samples (8 per lane) in the last round of the frame
     p.min_task_px = p.n_subset > 0 ? std::max(1, std::min(PT, (256 + p.n_subset - 1) / p.n_subset)) : PT;
-    if (const char* e = getenv("MORT_TAIL")) { if (atoi(e) == 0) p.min_task_px = PT; }                    // experiments only
     if (o.exact_accum && o.mode == MORT_MODE_WAVEFRONT) return fail(ctx, MORT_ERR_ARG, "mort_render: exact_accum needs the megakernel or the block wavefront");
     if (o.accumulate && !o.exact_accum) return fail(ctx, MORT_ERR_ARG, "mort_render: accumulate needs exact_accum (float sums are not order-independent)");
     p.accumulate = o.accumulate ? 1 : 0;
@@ -446,7 +446,6 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     if (n_staged > max_stage) return fail(ctx, MORT_ERR_ARG, "mort_render: stage_nodes exceeds the shared memory of a block (" + std::to_string(max_stage) + " nodes at most)");
     p.n_staged = n_staged;
 
-    if (ctx->stack_fix == 2) { raise_stack_limit(); ctx->stack_fix = 0; }
     CU(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), ctx->stream));
     uint64_t launches = 0;
@@ -502,14 +501,15 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
         p.pool_refill = o.pool_refill < 0 ? 0 : (o.pool_refill == 0 ? (tree && media ? 16 : 0) : std::min(31, o.pool_refill));
         p.pool_overlap = (o.pool_flags & 1) ? 0 : ((o.pool_flags & 2) ? 1 : (media && ps.min_blocks == 1 ? 1 : 0));
         int occ = 0, regs = 0, smem = 0;
-        const bool motion = ctx->motion_active && tree;      // kernels of motion.cu over the time-0 boxes + their change to time 1
+        const bool motion = ctx->motion_active && tree && !general_media;      // kernels of motion.cu over the time-0 boxes + their change to time 1
         if (motion) { p.sc.nodes = ctx->d_node_t0; p.sc.node_dt = ctx->d_node_t1; }
-        CU(motion ? pool_query_motion(ps, &occ, &regs, &smem) : pool_query(ps, &occ, &regs, &smem));
+        CU(general_media ? pool_query_stages(ps, &occ, &regs, &smem) : motion ? pool_query_motion(ps, &occ, &regs, &smem) : pool_query(ps, &occ, &regs, &smem));
         if (occ < 1) return fail(ctx, MORT_ERR_ARG, "mort_render: a pool of " + std::to_string(ps.pool_paths) + " paths (" + std::to_string(smem) + " B) does not fit in a block's shared memory");
         const int bps = std::min(occ, ps.min_blocks);
         CU(cudaMemsetAsync(ctx->d_work64, 0, sizeof(unsigned long long), ctx->stream));
         if (!o.accumulate || !o.exact_accum) CU(zero_exact_launch(target, p.n_pixels * n_frames, p.band_px, p.tile_mod, p.tile_rem, ctx->stream));
-        CU(motion ? pool_launch_motion(p, ps, bps * ctx->prop.multiProcessorCount, ctx->stream) : pool_launch(p, ps, bps * ctx->prop.multiProcessorCount, ctx->stream));
+        const int grid = bps * ctx->prop.multiProcessorCount;
+        CU(general_media ? pool_launch_stages(p, ps, grid, ctx->stream) : motion ? pool_launch_motion(p, ps, grid, ctx->stream) : pool_launch(p, ps, grid, ctx->stream));
         launches = 2;
         if (!o.exact_accum) { CU(resolve_exact_tiles_launch(target, p.n_pixels * n_frames, p.band_px, p.tile_mod, p.tile_rem, reinterpret_cast<float4*>(d_accum), ctx->stream)); launches = 3; }
         ctx->stats.threads_per_block = ps.threads; ctx->stats.blocks_per_sm = bps; ctx->stats.regs_per_thread = regs; ctx->stats.staged_nodes = 0;
@@ -719,12 +719,18 @@ int mort_trace(mort_ctx* ctx, const float* rays7, int n, mhit_record* out, mhit_
     if (!ctx->committed) return fail(ctx, MORT_ERR_STATE, "mort_trace: scene not committed");
     if (n == 0) return MORT_OK;
     CU(cudaSetDevice(ctx->device));
-    float* d_rays = nullptr; mhit_record* d_out = nullptr; mhit_medium_probe* d_pr = nullptr;
-    int nm = ctx->dscene.n_media;
-    cudaError_t e = cudaMalloc(&d_rays, (size_t)n * 28);
-    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * sizeof(mhit_record));
-    if (e == cudaSuccess && probes && nm) e = cudaMalloc(&d_pr, (size_t)n * nm * sizeof(mhit_medium_probe));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays7, (size_t)n * 28, cudaMemcpyHostToDevice, ctx->stream);
+    // one grow-only device buffer for the rays, the records and the probes (the parity tests call this thousands of times)
+    const int nm = ctx->dscene.n_media_top;
+    const size_t b_rays = ((size_t)n * 28 + 255) / 256 * 256, b_out = ((size_t)n * sizeof(mhit_record) + 255) / 256 * 256;
+    const size_t b_pr = (probes && nm) ? (size_t)n * nm * sizeof(mhit_medium_probe) : 0;
+    if (ctx->trace_bytes < b_rays + b_out + b_pr) {
+        cudaFree(ctx->d_trace); ctx->d_trace = nullptr; ctx->trace_bytes = 0;
+        CU(cudaMalloc(&ctx->d_trace, b_rays + b_out + b_pr)); ctx->trace_bytes = b_rays + b_out + b_pr;
+    }
+    char* base = static_cast<char*>(ctx->d_trace);
+    float* d_rays = reinterpret_cast<float*>(base); mhit_record* d_out = reinterpret_cast<mhit_record*>(base + b_rays);
+    mhit_medium_probe* d_pr = b_pr ? reinterpret_cast<mhit_medium_probe*>(base + b_rays + b_out) : nullptr;
+    cudaError_t e = cudaMemcpyAsync(d_rays, rays7, (size_t)n * 28, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         if (ctx->motion_active && !(flags & MORT_TRACE_BRUTE_FORCE)) {      // through the interpolated boxes, like the renders of this scene
             DeviceScene ms = ctx->dscene; ms.nodes = ctx->d_node_t0; ms.node_dt = ctx->d_node_t1;
@@ -734,7 +740,6 @@ int mort_trace(mort_ctx* ctx, const float* rays7, int n, mhit_record* out, mhit_
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(mhit_record), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && d_pr) e = cudaMemcpyAsync(probes, d_pr, (size_t)n * nm * sizeof(mhit_medium_probe), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_rays); cudaFree(d_out); cudaFree(d_pr);
     if (e != cudaSuccess) return fail(ctx, MORT_ERR_CUDA, std::string("mort_trace: ") + cudaGetErrorString(e));
     return MORT_OK;
 }
@@ -747,7 +752,7 @@ int mort_get_stats(mort_ctx* ctx, mort_stats* out) {
     s.width = c.image_width; s.height = c.image_height; s.sqrt_spp = c.sqrt_spp; s.bounce_limit = c.bounce_limit;
     const FlatScene& f = ctx->flat;
     s.n_leaves = f.stats.n_leaves; s.n_spheres = (int)f.spheres.size(); s.n_quads = (int)f.quads.size(); s.n_nodes = f.stats.n_nodes; s.bvh_depth = f.stats.max_depth;
-    s.n_media = (int)f.media.size(); s.n_instances = (int)f.instances.size(); s.n_materials = (int)f.materials.size(); s.n_textures = (int)f.textures.size();
+    s.n_media = ctx->dscene.n_media_top; s.n_instances = (int)f.instances.size(); s.n_materials = (int)f.materials.size(); s.n_textures = (int)f.textures.size();
     s.sah_cost = f.stats.sah_cost; s.build_ms = f.stats.build_ms; s.upload_ms = ctx->upload_ms;
     s.sm_count = ctx->prop.multiProcessorCount; s.device_bytes = ctx->arena.bytes;
     *out = s;

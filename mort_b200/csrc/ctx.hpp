@@ -61,7 +61,7 @@ struct mort_ctx {
     mort_stats stats;
     double upload_ms = 0;
     uint64_t geometry_hash = 0;
-    int stack_fix = 1;
+    void* d_trace = nullptr; size_t trace_bytes = 0;              // mort_trace: rays + records + probes (grow-only)
     void* comm = nullptr; int comm_world = 1, comm_rank = 0;      // NCCL communicator of a multi-process job (group.cu)
     unsigned long long* d_prog = nullptr; size_t prog_pixels = 0;   // progressive exact image (mort_render_progressive)
     unsigned long long* d_pool_exact = nullptr; size_t pool_exact_pixels = 0;   // block wavefront: exact frame behind a float4 request

@@ -72,10 +72,14 @@ struct alignas(32) LightPrim {
 };
 
 // A constant_medium: boundary primitives in the reference's visit order (a flattened list).
-struct alignas(32) Medium {
+struct alignas(32) Medium {                  // one VISIT of a constant_medium in world::hit's order (a medium reachable twice has two records)
     double neg_inv_density;
     int32_t mat_gid; int32_t first, count;  // range in boundary[]
-    int32_t obj_idx; int32_t cls; int32_t pad;   // cls: shade class of the phase material
+    int32_t obj_idx; int32_t cls;            // reference slot; shade class of the phase material
+    int32_t inst;                            // wrappers above the medium (-1: none): the frame its ray length and its record are taken in
+    int32_t after_lo, after_hi;              // visit-order window of the leaves between this medium and the next one (two_pass == 2)
+    int32_t top_level;                       // reached by world::hit's own medium loop (mort_trace reports boundary probes for these)
+    int32_t pad[5];
 };
 struct alignas(32) BoundaryPrim {           // same geometry as SphereGeom / QuadRec, one union-sized record
     int32_t type; int32_t inst; int32_t pad[2];
@@ -99,11 +103,12 @@ struct DeviceScene {
     const Texture* textures; int32_t n_textures;
     const ImageDesc* images; int32_t n_images;
     const NoiseTables* noises; int32_t n_noises;
-    const Medium* media; int32_t n_media;
+    const Medium* media; int32_t n_media;    // visits in world::hit's order
+    int32_t n_media_top;                     // of which reached by world::hit's own medium loop (the ones mort_trace probes)
     const BoundaryPrim* boundary; int32_t n_boundary;
     const LightPrim* lights; int32_t n_lights; int32_t light_kind;
     int32_t post_media_order;                // leaves with order >= this are visited after the media (top-level lists)
-    int32_t two_pass;                        // 1 when media and post-media leaves coexist
+    int32_t two_pass;                        // 1: media, then post-media leaves (a second pass); 2: media anywhere in the visit order (windowed passes)
     int32_t empty;                           // no visible primitive at all
     int32_t linear;                          // few leaves: records sorted by instance, scanned linearly (no tree)
 };

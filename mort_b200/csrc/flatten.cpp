@@ -46,7 +46,7 @@ struct Flattener {
     }
 
     // hitDispatch recursion (objects.cuh:858-887) unrolled into a list of leaves in visit order
-    template <class F> void collect(int type, int idx, Chain c, int depth, F&& emit) {
+    template <class F, class G> void collect(int type, int idx, Chain c, int depth, F&& emit, G&& emit_medium) {
         if (depth > 16) { err = "object nesting deeper than 16 levels (cycle?)"; return; }
         switch (type) {
             case MORT_OBJ_SPHERE:
@@ -59,18 +59,19 @@ struct Flattener {
                 if (idx < 0 || idx >= (int)s.translates.size()) { err = "translate handle out of range"; return; }
                 if (c.n >= MORT_INSTANCE_OPS) { err = "more than 7 nested translate/rotate_y wrappers are not supported"; return; }
                 c.kind[c.n] = MORT_OBJ_TRANSLATE; c.idx[c.n++] = idx;
-                collect(s.translates[idx].obj_type, s.translates[idx].obj_idx, c, depth + 1, emit); break;
+                collect(s.translates[idx].obj_type, s.translates[idx].obj_idx, c, depth + 1, emit, emit_medium); break;
             case MORT_OBJ_ROTATE_Y:
                 if (idx < 0 || idx >= (int)s.rotates.size()) { err = "rotate_y handle out of range"; return; }
                 if (c.n >= MORT_INSTANCE_OPS) { err = "more than 7 nested translate/rotate_y wrappers are not supported"; return; }
                 c.kind[c.n] = MORT_OBJ_ROTATE_Y; c.idx[c.n++] = idx;
-                collect(s.rotates[idx].obj_type, s.rotates[idx].obj_idx, c, depth + 1, emit); break;
+                collect(s.rotates[idx].obj_type, s.rotates[idx].obj_idx, c, depth + 1, emit, emit_medium); break;
             case MORT_OBJ_HITTABLE_LIST:
                 if (idx < 0 || idx >= (int)s.lists.size()) { err = "list handle out of range"; return; }
-                for (const Handle& h : s.lists[idx].items) collect(h.type, h.idx, c, depth + 1, emit);
+                for (const Handle& h : s.lists[idx].items) collect(h.type, h.idx, c, depth + 1, emit, emit_medium);
                 break;
-            case MORT_OBJ_CONSTANT_MEDIUM:
-                err = "constant_medium nested inside another object is not supported (only top-level media)"; return;
+            case MORT_OBJ_CONSTANT_MEDIUM:                  // hitDispatch reaches a medium through wrappers and lists (objects.cuh:875-877)
+                if (idx < 0 || idx >= (int)s.media.size()) { err = "medium handle out of range"; return; }
+                emit_medium(idx, c); break;
             default: break;       // hitDispatch has no case for a BVH or unknown tags: never hit
         }
     }
@@ -177,6 +178,15 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const Build
         LeafRef L; L.type = type; L.idx = idx; L.inst = F.instance_of(c); L.order = (int)out.leaves.size(); L.top_type = top_type; L.top_idx = top_idx;
         out.leaves.push_back(L); chains.push_back(c); gates.push_back(cur_gate);
     };
+    // media in the order world::hit reaches them: the top-level loop (world.cuh:154-160) and, through wrappers and lists, hitDispatch
+    // (objects.cuh:875-877).  `pos` = leaves visited before the medium: what it is clipped against.
+    struct MediumVisit { int medium, pos; Chain chain; bool top; };
+    std::vector<MediumVisit> visits;
+    bool under_bvh = false;
+    auto emit_m = [&](int m, const Chain& c) {
+        if (under_bvh) { F.err = "a constant_medium below a bvh is not supported (the reference culls it with its own node boxes)"; return; }
+        visits.push_back(MediumVisit{m, (int)out.leaves.size(), c, false});
+    };
     Chain none;
     for (size_t b = 0; b < s.bvhs.size(); b++) {
         if (s.bvhs[b].skip || s.bvhs[b].nodes.empty()) continue;
@@ -199,48 +209,56 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const Build
             cur_gate = g;
             if (nd.is_internal) { stack.push_back(Visit{nd.right_idx, dead, g}); stack.push_back(Visit{nd.left_idx, dead, g}); }
             else if (!dead) {
-                F.collect(nd.left_type, nd.left_idx, none, 0, emit);
-                if (nd.right_type != nd.left_type || nd.right_idx != nd.left_idx) F.collect(nd.right_type, nd.right_idx, none, 0, emit);
+                under_bvh = true;
+                F.collect(nd.left_type, nd.left_idx, none, 0, emit, emit_m);
+                if (nd.right_type != nd.left_type || nd.right_idx != nd.left_idx) F.collect(nd.right_type, nd.right_idx, none, 0, emit, emit_m);
+                under_bvh = false;
             }
         }
     }
     cur_gate = open_gate;
     if (!s.bvh_mode) {                       // world.cuh:118-120: with a BVH in the world nothing else is visible
-        for (size_t i = 0; i < s.spheres.size(); i++) if (!s.spheres[i].skip) { top_type = MORT_OBJ_SPHERE; top_idx = (int)i; F.collect(MORT_OBJ_SPHERE, (int)i, none, 0, emit); }
-        for (size_t i = 0; i < s.quads.size(); i++) if (!s.quads[i].skip) { top_type = MORT_OBJ_QUAD; top_idx = (int)i; F.collect(MORT_OBJ_QUAD, (int)i, none, 0, emit); }
-        for (size_t i = 0; i < s.translates.size(); i++) if (!s.translates[i].skip) { top_type = MORT_OBJ_TRANSLATE; top_idx = (int)i; F.collect(MORT_OBJ_TRANSLATE, (int)i, none, 0, emit); }
-        for (size_t i = 0; i < s.rotates.size(); i++) if (!s.rotates[i].skip) { top_type = MORT_OBJ_ROTATE_Y; top_idx = (int)i; F.collect(MORT_OBJ_ROTATE_Y, (int)i, none, 0, emit); }
-        out.post_media_order = (int)out.leaves.size();
-        for (size_t i = 0; i < s.lists.size(); i++) if (!s.lists[i].skip) { top_type = MORT_OBJ_HITTABLE_LIST; top_idx = (int)i; F.collect(MORT_OBJ_HITTABLE_LIST, (int)i, none, 0, emit); }
-    } else {
-        out.post_media_order = (int)out.leaves.size();
+        for (size_t i = 0; i < s.spheres.size(); i++) if (!s.spheres[i].skip) { top_type = MORT_OBJ_SPHERE; top_idx = (int)i; F.collect(MORT_OBJ_SPHERE, (int)i, none, 0, emit, emit_m); }
+        for (size_t i = 0; i < s.quads.size(); i++) if (!s.quads[i].skip) { top_type = MORT_OBJ_QUAD; top_idx = (int)i; F.collect(MORT_OBJ_QUAD, (int)i, none, 0, emit, emit_m); }
+        for (size_t i = 0; i < s.translates.size(); i++) if (!s.translates[i].skip) { top_type = MORT_OBJ_TRANSLATE; top_idx = (int)i; F.collect(MORT_OBJ_TRANSLATE, (int)i, none, 0, emit, emit_m); }
+        for (size_t i = 0; i < s.rotates.size(); i++) if (!s.rotates[i].skip) { top_type = MORT_OBJ_ROTATE_Y; top_idx = (int)i; F.collect(MORT_OBJ_ROTATE_Y, (int)i, none, 0, emit, emit_m); }
+        for (size_t m = 0; m < s.media.size(); m++) if (!s.media[m].skip) visits.push_back(MediumVisit{(int)m, (int)out.leaves.size(), none, true});
+        for (size_t i = 0; i < s.lists.size(); i++) if (!s.lists[i].skip) { top_type = MORT_OBJ_HITTABLE_LIST; top_idx = (int)i; F.collect(MORT_OBJ_HITTABLE_LIST, (int)i, none, 0, emit, emit_m); }
     }
     if (!F.err.empty()) return fail(F.err);
+    out.post_media_order = visits.empty() ? (int)out.leaves.size() : visits[0].pos;
 
-    // ---- media (only reachable at top level, and not at all in bvh_mode) ----
-    if (!s.bvh_mode)
-        for (size_t m = 0; m < s.media.size(); m++) {
-            if (s.media[m].skip) continue;
-            Medium M; memset(&M, 0, sizeof(M));
-            M.neg_inv_density = s.media[m].neg_inv_density; M.mat_gid = mat_gid(s, s.media[m].mat_type, s.media[m].mat_idx);
-            M.first = (int)out.boundary.size(); M.obj_idx = (int)m;
-            auto emit_b = [&](int type, int idx, const Chain& c) {
-                BoundaryPrim B; memset(&B, 0, sizeof(B));
-                B.type = type; B.inst = F.instance_of(c);
-                if (type == MORT_OBJ_SPHERE) {
-                    const mscn_sphere& sp = s.spheres[idx];
-                    out.sphere_pinned[idx] = 1;
-                    B.a[0][0] = sp.center[0]; B.a[0][1] = sp.center[1]; B.a[0][2] = sp.center[2]; B.a[0][3] = sp.radius;
-                    if (sp.moves) { B.a[1][0] = sp.center_vec[0]; B.a[1][1] = sp.center_vec[1]; B.a[1][2] = sp.center_vec[2]; }
-                } else fill_quad_rows(s.quads[idx], B.a);
-                out.boundary.push_back(B);
-            };
-            F.collect(s.media[m].obj_type, s.media[m].obj_idx, none, 0, emit_b);
-            if (!F.err.empty()) return fail(F.err);
-            M.count = (int)out.boundary.size() - M.first;
-            out.media.push_back(M);
-        }
-    out.two_pass = (!out.media.empty() && out.post_media_order < (int)out.leaves.size()) ? 1 : 0;
+    // ---- media records, in visit order; each carries the window of leaves visited between it and the next medium ----
+    bool general = false;
+    for (size_t v = 0; v < visits.size(); v++) {
+        const MediumVisit& V = visits[v];
+        const int m = V.medium;
+        general = general || V.pos != visits[0].pos || V.chain.n > 0 || !V.top;
+        Medium M; memset(&M, 0, sizeof(M));
+        M.neg_inv_density = s.media[m].neg_inv_density; M.mat_gid = mat_gid(s, s.media[m].mat_type, s.media[m].mat_idx);
+        M.first = (int)out.boundary.size(); M.obj_idx = m;
+        M.inst = F.instance_of(V.chain); M.top_level = V.top ? 1 : 0;
+        M.after_lo = V.pos; M.after_hi = v + 1 < visits.size() ? visits[v + 1].pos : 0x7FFFFFFF;
+        auto emit_b = [&](int type, int idx, const Chain& c) {
+            BoundaryPrim B; memset(&B, 0, sizeof(B));
+            B.type = type; B.inst = F.instance_of(c);
+            if (type == MORT_OBJ_SPHERE) {
+                const mscn_sphere& sp = s.spheres[idx];
+                out.sphere_pinned[idx] = 1;
+                B.a[0][0] = sp.center[0]; B.a[0][1] = sp.center[1]; B.a[0][2] = sp.center[2]; B.a[0][3] = sp.radius;
+                if (sp.moves) { B.a[1][0] = sp.center_vec[0]; B.a[1][1] = sp.center_vec[1]; B.a[1][2] = sp.center_vec[2]; }
+            } else fill_quad_rows(s.quads[idx], B.a);
+            out.boundary.push_back(B);
+        };
+        auto no_medium = [&](int, const Chain&) { F.err = "a constant_medium whose boundary contains another constant_medium is not supported"; };
+        F.collect(s.media[m].obj_type, s.media[m].obj_idx, V.chain, 0, emit_b, no_medium);      // the boundary sits below the medium's own wrappers
+        if (!F.err.empty()) return fail(F.err);
+        M.count = (int)out.boundary.size() - M.first;
+        out.media.push_back(M);
+    }
+    // 0: one traversal; 1: the shipped form (all media between the surfaces and the top-level lists: a second pass over the lists);
+    // 2: media anywhere in the visit order (nested in wrappers / lists): one windowed pass per medium (rt_core.cuh: media_stages)
+    out.two_pass = out.media.empty() ? 0 : (general ? 2 : (out.post_media_order < (int)out.leaves.size() ? 1 : 0));
     out.empty = out.leaves.empty() ? 1 : 0;
 
     // ---- light handle (camera.cuh:118-133, objects.cuh:947-979) ----

@@ -407,16 +407,24 @@ PoolFn pool_variant_of(const PoolShape& s) {
 }
 #if defined(MORT_MOTION_BOUNDS)
 PoolFn pool_variant(const PoolShape& s) { return pool_variant_of<true>(s); }         // motion boxes live in a tree
+#elif defined(MORT_GENERAL_MEDIA)
+PoolFn pool_variant(const PoolShape&) { return (PoolFn)pool_kernel<512, 2, false>; } // one shape: the generic kernel (run-time linear / tree flag)
 #else
 PoolFn pool_variant(const PoolShape& s) { return s.tree ? pool_variant_of<true>(s) : pool_variant_of<false>(s); }
 #endif
+#if defined(MORT_GENERAL_MEDIA)
+int pool_threads(const PoolShape&) { return 512; }
+#else
 int pool_threads(const PoolShape& s) { return s.threads >= 1024 ? 1024 : s.threads >= 768 ? 768 : s.threads >= 640 ? 640 : s.threads >= 512 ? 512 : s.threads >= 384 ? 384 : 256; }
+#endif
 int pool_smem(const PoolShape& s) { return s.pool_paths * (kPoolWords * 4 + kPoolLists * 2); }
 
 }  // namespace
 
 #if defined(MORT_MOTION_BOUNDS)
 #define POOL_EXPORT(name) name##_motion
+#elif defined(MORT_GENERAL_MEDIA)
+#define POOL_EXPORT(name) name##_stages
 #else
 #define POOL_EXPORT(name) name
 #endif
@@ -456,6 +464,7 @@ cudaError_t trace_launch_motion(const DeviceScene& sc, const float* d_rays, int 
     trace_motion_kernel<<<(n + 127) / 128, 128, 0, st>>>(sc, d_rays, n, d_out, d_probes, brute_force, d_mat_offsets);
     return cudaGetLastError();
 }
+#elif defined(MORT_GENERAL_MEDIA)
 #else
 // ------------------------------------------------------------------------------------------------------
 // zero / resolve the exact frame over the pixels one call renders (all of them, or a rank's 8-row bands)

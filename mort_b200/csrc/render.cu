@@ -185,10 +185,6 @@ cudaError_t mega_launch(const FrameParams& p, const LaunchShape& shape, int min_
         cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, shape.smem_bytes);
         if (e != cudaSuccess) return e;
     }
-    if (const char* e = getenv("MORT_CARVEOUT")) {          // experiments only: shared-memory share of the unified L1 (percent)
-        cudaError_t ce = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-        if (ce != cudaSuccess) return ce;
-    }
     void* args[] = {(void*)&p};
     return cudaLaunchKernel((const void*)fn, dim3(shape.blocks), dim3(shape.threads), args, (size_t)shape.smem_bytes, st);
 }

@@ -50,6 +50,9 @@ cudaError_t pool_launch(const FrameParams& p, const PoolShape& shape, int blocks
 // the same kernel compiled with motion-aware node boxes (motion.cu): p.sc.nodes = boxes at time 0, p.sc.node_dt = change to time 1
 cudaError_t pool_query_motion(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes);
 cudaError_t pool_launch_motion(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st);
+// the same kernel (one shape: 512 threads x 2 blocks) compiled with media anywhere in world::hit's visit order (stages.cu)
+cudaError_t pool_query_stages(const PoolShape& want, int* blocks_per_sm, int* regs, int* smem_bytes);
+cudaError_t pool_launch_stages(const FrameParams& p, const PoolShape& shape, int blocks, cudaStream_t st);
 // zero / resolve the exact frame over the pixels THIS call renders (all of them, or the rank's 8-row bands)
 cudaError_t zero_exact_launch(unsigned long long* d_exact, int n_pixels_local, int band_px, int tile_mod, int tile_rem, cudaStream_t st);
 cudaError_t resolve_exact_tiles_launch(const unsigned long long* d_exact, int n_pixels_local, int band_px, int tile_mod, int tile_rem, float4* d_accum, cudaStream_t st);

@@ -594,7 +594,13 @@ MORT_HD bool medium_hit(const DeviceScene& sc, const Medium& m, const Ray& r, fl
     if (t2 > tmax) t2 = tmax;
     if (t1 >= t2) return false;
     if (t1 < 0) t1 = 0;
+#if defined(MORT_GENERAL_MEDIA)
+    f3 mo = r.o, md = r.d;
+    ray_to_object(sc.instances, m.inst, mo, md);                                  // the medium sees the ray its wrappers hand down (objects.cuh:268-366)
+    float ray_length = xsqrt(xdot(md, md));
+#else
     float ray_length = xsqrt(xdot(r.d, r.d));
+#endif
     float inside = (t2 - t1) * ray_length;
     double hit_distance = m.neg_inv_density * (double)logf(rng_block(g).x);       // aligned draw (rng_align in the oracle)
     if (hit_distance > (double)inside) return false;
@@ -619,6 +625,30 @@ MORT_HD_NOINLINE MediaOut media_scan(const DeviceScene& sc, Ray r, float tmin, f
     return o;
 }
 
+#if defined(MORT_GENERAL_MEDIA)
+// Compiled only into the kernels of stages.cu (and the test-only host build): the kernels every shipped scene runs do not carry
+// this code (with it inlined next to the shipped form, ptxas spilled 268 instead of 132 bytes in the config-3 kernel).
+// media anywhere in the visit order (a constant_medium inside a translate / rotate_y / list, objects.cuh:875-877): every medium is
+// clipped against what world::hit has found BEFORE it reaches the medium, and the leaves it visits afterwards only win with t <= the
+// medium's event — one windowed closest-hit pass per medium that has leaves behind it.  Cold (no shipped scene), out of line.
+struct StagesOut { Rng g; Hit h; int med; float t; bool any; };
+MORT_HD_NOINLINE StagesOut media_stages(const DeviceScene& sc, Ray r, float tmin, bool any, Hit h, Rng g) {
+    StagesOut o; o.med = -1; o.t = 0.f;
+    float closest = any ? h.t : INFINITY;
+    for (int m = 0; m < sc.n_media; m++) {
+        const Medium& M = sc.media[m];
+        float t;
+        if (medium_hit(sc, M, r, tmin, closest, g, t)) { o.med = m; o.t = t; closest = t; }
+        if (M.after_hi > M.after_lo) {
+            Hit h2; closest_hit<false>(sc, nullptr, 0, r, tmin, closest, h2, M.after_lo, M.after_hi);
+            if (h2.prim != MORT_PRIM_NONE) { h = h2; any = true; o.med = -1; closest = h2.t; }
+        }
+    }
+    o.g = g; o.h = h; o.any = any;
+    return o;
+}
+#endif
+
 // world::hit (world.cuh:104-171) in two stages so the megakernel and the wavefront kernels share it:
 //   segment_trace  : surfaces, then media clipped to the closest surface, then top-level lists -> SegHit
 //   segment_record : the hit_record of the winner (surface primitive or medium event)
@@ -630,12 +660,18 @@ MORT_HD void segment_finish(const DeviceScene& sc, const Ray& r, Rng& g, bool an
     const float tmin = 0.001f;
     float closest = any ? h.t : INFINITY;
     int med = -1; float tmed = 0.f;
-    if (sc.n_media > 0) {                                   // cold for most scenes: kept out of line
+#if defined(MORT_GENERAL_MEDIA)
+    if (sc.two_pass == 2) {
+        const StagesOut so = media_stages(sc, r, tmin, any, h, g);
+        g = so.g; h = so.h; any = so.any; med = so.med; tmed = so.t;
+    } else
+#endif
+    if (sc.n_media > 0) {                            // cold for most scenes: kept out of line
         MediaOut mo = media_scan(sc, r, tmin, closest, g);
         g = mo.g; med = mo.med; tmed = mo.t;
         if (med >= 0) closest = tmed;
     }
-    if (sc.two_pass) {
+    if (sc.two_pass == 1) {
         Hit h2 = closest_hit_second_pass(sc, r, tmin, closest);
         if (h2.prim != MORT_PRIM_NONE) { h = h2; any = true; med = -1; }
     }
@@ -661,7 +697,14 @@ MORT_HD int seghit_material(const DeviceScene& sc, const SegHit& sh) {     // ma
 MORT_HD void segment_record(const DeviceScene& sc, const Ray& r, const SegHit& sh, Record& rec) {
     if (sh.h.prim == MORT_PRIM_MEDIUM) {                                 // objects.cuh:425-431
         int med = f2i_bits(sh.h.a);
+#if defined(MORT_GENERAL_MEDIA)
+        f3 mo = r.o, md = r.d;
+        ray_to_object(sc.instances, sc.media[med].inst, mo, md);         // the record is made in the medium's frame and handed up through its wrappers
+        rec.t = sh.h.t; rec.p = xat(mo, md, sh.h.t); rec.normal = mk3(1, 0, 0); rec.front_face = true;
+        record_to_world(sc.instances, sc.media[med].inst, rec.p, rec.normal);
+#else
         rec.t = sh.h.t; rec.p = xat(r.o, r.d, sh.h.t); rec.normal = mk3(1, 0, 0); rec.front_face = true;
+#endif
         rec.mat_gid = sc.media[med].mat_gid; rec.u = rec.v = 0.f; rec.sphere_uv = false;
         rec.leaf_type = MORT_OBJ_CONSTANT_MEDIUM; rec.leaf_idx = sc.media[med].obj_idx;
         return;

@@ -33,14 +33,15 @@ __device__ __forceinline__ void trace_one(const DeviceScene& sc, const float* __
     }
     out[i] = o;
     if (probes)
-        for (int m = 0; m < sc.n_media; m++) {
+        for (int m = 0, j = 0; m < sc.n_media; m++) {
+            if (!sc.media[m].top_level) continue;
             mhit_medium_probe p; p.hit1 = p.hit2 = 0; p.t1 = p.t2 = 0.f;
             float t1, t2;
             if (boundary_probe(sc, sc.media[m], r, -INFINITY, INFINITY, t1)) {
                 p.hit1 = 1; p.t1 = t1;
                 if (boundary_probe(sc, sc.media[m], r, (float)((double)t1 + 0.0001), INFINITY, t2)) { p.hit2 = 1; p.t2 = t2; }
             }
-            probes[(size_t)i * sc.n_media + m] = p;
+            probes[(size_t)i * sc.n_media_top + j] = p; j++;
         }
 }
 

@@ -289,6 +289,7 @@ static int medium_probe(const oracle_scene* S, const mscn_medium* m, const ray_t
 }
 static int medium_hit(const oracle_scene* S, const mscn_medium* m, const ray_t* r, float tmin, float tmax, hitrec* rec, rng_t* g) {    /* objects.cuh:396-434 */
     hitrec rec1, rec2; int h1;
+    if (!g) return 0;                              /* oracle_trace: surfaces only (the product's mort_trace has no medium loop either) */
     if (!medium_probe(S, m, r, &rec1, &rec2, g, &h1)) return 0;
     if (rec1.t < tmin) rec1.t = tmin;
     if (rec2.t > tmax) rec2.t = tmax;
@@ -385,7 +386,7 @@ int oracle_trace(const oracle_scene* S, const float* rays7, int n, mhit_record* 
         ray_t r = { V(q[0], q[1], q[2]), V(q[3], q[4], q[5]), q[6] };
         hitrec rec; memset(&rec, 0, sizeof(rec));
         int tt = -1, ti = -1;
-        int h = world_hit(S, &r, 0.001f, INFINITY, &rec, &g, 0, &tt, &ti);
+        int h = world_hit(S, &r, 0.001f, INFINITY, &rec, NULL, 0, &tt, &ti);      /* no RNG: media nested in wrappers / lists stay out as well */
         mhit_record o; memset(&o, 0, sizeof(o));
         o.hit = h; o.leaf_type = o.leaf_idx = o.top_type = o.top_idx = -1;
         if (h) {

@@ -42,8 +42,8 @@ def hostsim():
                                                                       ("scene.cpp", "scenes.cpp", "scene_text.cpp", "flatten.cpp", "bvh_build.cpp")]
     deps = src + [os.path.join(ROOT, "mort_b200", "csrc", f) for f in ("rt_core.cuh", "device_types.h", "flatten.hpp", "scene.hpp", "bvh_sah.hpp")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "mort_b200", "csrc"),
-                               "-I" + os.path.join(ROOT, "include")] + src + ["-o", out])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-DMORT_GENERAL_MEDIA", "-I" + os.path.join(ROOT, "mort_b200", "csrc"),
+                               "-I" + os.path.join(ROOT, "include")] + src + ["-o", out, "-lpthread"])
     return out
 
 

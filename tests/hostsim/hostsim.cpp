@@ -29,6 +29,7 @@ static DeviceScene make_device_scene(const Scene& s, const FlatScene& f, std::ve
     d.images = imgs.data(); d.n_images = (int)imgs.size();
     d.noises = f.noises.data(); d.n_noises = (int)f.noises.size();
     d.media = f.media.data(); d.n_media = (int)f.media.size();
+    d.n_media_top = 0; for (const Medium& M : f.media) d.n_media_top += M.top_level ? 1 : 0;
     d.boundary = f.boundary.data(); d.n_boundary = (int)f.boundary.size();
     d.lights = f.lights.data(); d.n_lights = (int)f.lights.size(); d.light_kind = f.light_kind;
     d.post_media_order = f.post_media_order; d.two_pass = f.two_pass; d.empty = f.empty; d.linear = f.linear;
@@ -60,7 +61,9 @@ int main(int argc, char** argv) {
         s.cam.initialize();
     }
     FlatScene f; std::string err;
-    if (!flatten_scene(s, f, &err)) { fprintf(stderr, "flatten: %s\n", err.c_str()); return 2; }
+    BuildOptions bo;                                   // (a test harness may read its environment; the product does not)
+    if (const char* e = getenv("MORT_BUILD_THREADS")) bo.threads = atoi(e);
+    if (!flatten_scene(s, f, &err, bo)) { fprintf(stderr, "flatten: %s\n", err.c_str()); return 2; }
     std::vector<ImageDesc> imgs;
     DeviceScene d = make_device_scene(s, f, imgs);
     fprintf(stderr, "leaves %d nodes %d (bvh2 %d) depth %d sah %.2f pad %g build %.2f ms two_pass %d media %d lights %d kind %d\n", f.stats.n_leaves, f.stats.n_nodes,
@@ -132,18 +135,19 @@ int main(int argc, char** argv) {
         std::vector<float> rays((size_t)n * 7); if (fread(rays.data(), 4, rays.size(), fi) != rays.size()) return 3; fclose(fi);
         bool brute = argc > 6 && !strcmp(argv[6], "brute");
         std::vector<mhit_record> out(n);
-        std::vector<mhit_medium_probe> probes((size_t)n * d.n_media);      // like trace_kernel (render.cu): both boundary probes of every kept medium
+        std::vector<mhit_medium_probe> probes((size_t)n * d.n_media_top);      // like trace_kernel (render.cu): both boundary probes of every kept medium
         for (int i = 0; i < n; i++) {
             const float* q = &rays[7 * (size_t)i];
             Ray r; r.o = mk3(q[0], q[1], q[2]); r.d = mk3(q[3], q[4], q[5]); r.tm = q[6];
-            for (int m = 0; m < d.n_media; m++) {
+            for (int m = 0, j = 0; m < d.n_media; m++) {
+                if (!d.media[m].top_level) continue;
                 mhit_medium_probe pr; pr.hit1 = pr.hit2 = 0; pr.t1 = pr.t2 = 0.f;
                 float t1, t2;
                 if (boundary_probe(d, d.media[m], r, -INFINITY, INFINITY, t1)) {
                     pr.hit1 = 1; pr.t1 = t1;
                     if (boundary_probe(d, d.media[m], r, (float)((double)t1 + 0.0001), INFINITY, t2)) { pr.hit2 = 1; pr.t2 = t2; }
                 }
-                probes[(size_t)i * d.n_media + m] = pr;
+                probes[(size_t)i * d.n_media_top + j] = pr; j++;
             }
             Hit h; bool any = brute ? closest_hit_brute(d, r, 0.001f, INFINITY, h) : closest_hit<false>(d, nullptr, 0, r, 0.001f, INFINITY, h);
             mhit_record o; memset(&o, 0, sizeof(o)); o.hit = any; o.leaf_type = o.leaf_idx = o.top_type = o.top_idx = -1;
@@ -159,7 +163,7 @@ int main(int argc, char** argv) {
             }
             out[i] = o;
         }
-        FILE* fo = fopen(argv[5], "wb"); uint32_t oh[4] = {MHIT_MAGIC, (uint32_t)n, (uint32_t)d.n_media, (uint32_t)f.stats.n_leaves};
+        FILE* fo = fopen(argv[5], "wb"); uint32_t oh[4] = {MHIT_MAGIC, (uint32_t)n, (uint32_t)d.n_media_top, (uint32_t)f.stats.n_leaves};
         fwrite(oh, 4, 4, fo); fwrite(rays.data(), 4, rays.size(), fo); fwrite(out.data(), sizeof(mhit_record), n, fo);
         if (!probes.empty()) fwrite(probes.data(), sizeof(mhit_medium_probe), probes.size(), fo);
         fclose(fo);

@@ -11,13 +11,14 @@ from test_scene_text import _random_scene_text
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("seed", range(300, 324))
+@pytest.mark.parametrize("seed", list(range(300, 324)) + list(range(1300, 1316)))
 def test_random_scene_through_the_abi(seed, tmp_path):
+    """seeds >= 1000: the generator nests media in wrappers and lists most of the time (media_stages in rt_core.cuh, all three schedulers)"""
     import oracle_binding as O
-    from mort_b200.api import MortError, Renderer
+    from mort_b200.api import MODE_MEGAKERNEL, MortError, Renderer
     rng = np.random.default_rng(seed)
     txt, dump = tmp_path / "s.txt", str(tmp_path / "s.mscn")
-    txt.write_text(_random_scene_text(rng))
+    txt.write_text(_random_scene_text(rng, 0.7 if seed >= 1000 else 0.1))
     with Renderer(0) as r:
         r.load_scene_text(str(txt))
         r.dump_scene(dump)
@@ -50,6 +51,9 @@ def test_random_scene_through_the_abi(seed, tmp_path):
         # a small frame against the oracle with the same stream
         r.override_camera(width=32, spp=9)
         fr = r.render(seed=5)
+        if seed >= 1000:                                  # the schedulers share the per-ray code: same exact frame from the pool and the megakernel
+            other = r.render(seed=5, mode=MODE_MEGAKERNEL)        # a scene with nested media goes to the general-media kernel whatever the mode
+            assert np.array_equal(other.accum, fr.accum, equal_nan=True)
         osc = O.OracleScene(dump)
         osc.override(width=32, spp=9)
         hdr, _, st = osc.render(seed=5, want_rgba8=False)

@@ -107,8 +107,9 @@ def test_scene_loaded_from_a_binary_dump_has_no_text_form(hostsim, tmp_path):
     assert p.returncode != 0 and "no text form" in p.stderr
 
 
-def _random_scene_text(rng):
-    """A random but valid scene file: every statement kind, forward references only to things that exist."""
+def _random_scene_text(rng, nested_media=0.1):
+    """A random but valid scene file: every statement kind, forward references only to things that exist.
+    nested_media: how often a wrapper / list / medium may pick ANY object (media included) instead of a plain one."""
     lines, tex, mat, obj, lists = [], [], [], [], []
     f = lambda lo=-5.0, hi=5.0: f"{rng.uniform(lo, hi):.6g}"
     v3 = lambda lo=-5.0, hi=5.0: " ".join(f(lo, hi) for _ in range(3))
@@ -132,7 +133,7 @@ def _random_scene_text(rng):
     for i in range(rng.integers(4, 12)):
         m, hid = rng.choice(mat), (" hidden" if rng.random() < 0.3 else "")
         k = rng.integers(0, 6)
-        shallow = [o for o in plain if depth[o] < 7] if rng.random() < 0.9 else list(obj)   # mostly stay inside what the product supports
+        shallow = [o for o in plain if depth[o] < 7] if rng.random() < 1.0 - nested_media else list(obj)   # mostly stay inside what the product supports
         name, d, is_medium = f"o{i}", 0, False
         if k == 0:
             lines.append(f"{name} = sphere {v3()} {f(0.1, 2)} {m}{hid}")
@@ -158,7 +159,7 @@ def _random_scene_text(rng):
         lines.append(f"box {v3()} {v3()} {rng.choice(mat)}")
     for i in range(rng.integers(1, 3)):
         lines.append(f"l{i} = list" + (" hidden" if rng.random() < 0.5 else ""))
-        pool = plain if rng.random() < 0.9 else obj
+        pool = plain if rng.random() < 1.0 - nested_media else obj
         for o in rng.choice(pool, size=min(len(pool), int(rng.integers(1, 5))), replace=False):
             lines.append(f"add l{i} {o}")
         lists.append(f"l{i}")
