@@ -186,7 +186,7 @@ __device__ __forceinline__ int trace_lane(const FrameParams& P, const Pool& S, u
 // TRACE phase for tree scenes with lane refill (Aila & Laine's persistent while-while, inside one block).  With fixed
 // 32-ray chunks a lane whose ray has left the tree idles until the slowest ray of its chunk is done: ncu of the phased
 // kernel on scene 8 shows the traversal code — 60 % of all warp instructions — running with 12.6 of 32 lanes
-// (profiles/r02_pool_phased.md).  Here the phase is split in two:
+// (profiles/r02_pool_kernel.md).  Here the phase is split in two:
 //   trace_refill   pure traversal.  As soon as `want` lanes of a warp are idle they store their hits (4 words) and take
 //                  new rays from the block's live list while the other lanes keep their traversal state in registers.
 //                  The refill is deliberately tiny (no RNG, no media, no material lookup, no list pushes): it runs with

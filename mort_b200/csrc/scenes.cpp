@@ -3,7 +3,7 @@
 //
 // Geometry, materials, camera and light handles follow /root/reference/mort.cu:129-631 (dispatch
 // mort.cu:649-689).  Two things that are NOT visible in that source but decide the bits of the layout
-// are reproduced deliberately and pinned by tests/test_scenes.py against the reference's own dumps:
+// are reproduced deliberately and pinned by tests/test_host_scene.py against the reference's own dumps:
 //   * the host random stream is glibc rand() unseeded (HostRng), and
 //   * draws that appear inside one argument list are consumed right-to-left,
 //     so every draw below is bound to a named temporary in the order the reference consumes it.
