@@ -7,7 +7,11 @@ import json
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-README = {l.split("|")[1].strip().strip("`"): l.split("|")[2].strip() for l in open(os.path.join(ROOT, "scripts", "r02", "README.md")) if l.startswith("| `gpu_r2_")}
+README = {}
+for l in open(os.path.join(ROOT, "scripts", "r02", "README.md")):
+    if l.startswith("| `gpu_r2_"):
+        for name in l.split("|")[1].split(","):
+            README[name.strip().strip("`")] = l.split("|")[2].strip()
 
 
 def workload(d, args):
