@@ -11,6 +11,11 @@
 namespace mort {
 namespace {
 
+// plain comparisons instead of fminf / fmaxf (libm calls without -ffast-math): a NaN coordinate falls through them into the
+// box and is refused by the check after leaf_world_box
+inline float fmin_(float a, float b) { return b < a ? b : a; }
+inline float fmax_(float a, float b) { return b > a ? b : a; }
+
 struct Chain { int n = 0; int kind[MORT_INSTANCE_OPS]; int idx[MORT_INSTANCE_OPS]; bool overflow = false;
     bool operator<(const Chain& o) const {
         if (n != o.n) return n < o.n;
@@ -21,6 +26,7 @@ struct Chain { int n = 0; int kind[MORT_INSTANCE_OPS]; int idx[MORT_INSTANCE_OPS
 struct Flattener {
     const Scene& s; FlatScene& out; std::string err;
     std::map<Chain, int> inst_ids;
+    std::vector<Chain> inst_chain;               // instance id -> its chain (what leaf_world_box needs; one entry per distinct chain, not per leaf)
     Flattener(const Scene& sc, FlatScene& o) : s(sc), out(o) {}
 
     int instance_of(const Chain& c) {
@@ -41,12 +47,13 @@ struct Flattener {
             memcpy(&I.a[k][3], &kind, 4);
         }
         int id = (int)out.instances.size();
-        out.instances.push_back(I); inst_ids[c] = id;
+        out.instances.push_back(I); inst_ids[c] = id; inst_chain.push_back(c);
         return id;
     }
 
     // hitDispatch recursion (objects.cuh:858-887) unrolled into a list of leaves in visit order
-    template <class F, class G> void collect(int type, int idx, Chain c, int depth, F&& emit, G&& emit_medium) {
+    template <class F, class G> void collect(int type, int idx, const Chain& c0, int depth, F&& emit, G&& emit_medium) {
+        const Chain& c = c0;
         if (depth > 16) { err = "object nesting deeper than 16 levels (cycle?)"; return; }
         switch (type) {
             case MORT_OBJ_SPHERE:
@@ -58,13 +65,13 @@ struct Flattener {
             case MORT_OBJ_TRANSLATE:
                 if (idx < 0 || idx >= (int)s.translates.size()) { err = "translate handle out of range"; return; }
                 if (c.n >= MORT_INSTANCE_OPS) { err = "more than 7 nested translate/rotate_y wrappers are not supported"; return; }
-                c.kind[c.n] = MORT_OBJ_TRANSLATE; c.idx[c.n++] = idx;
-                collect(s.translates[idx].obj_type, s.translates[idx].obj_idx, c, depth + 1, emit, emit_medium); break;
+                { Chain c2 = c; c2.kind[c2.n] = MORT_OBJ_TRANSLATE; c2.idx[c2.n++] = idx;
+                  collect(s.translates[idx].obj_type, s.translates[idx].obj_idx, c2, depth + 1, emit, emit_medium); } break;
             case MORT_OBJ_ROTATE_Y:
                 if (idx < 0 || idx >= (int)s.rotates.size()) { err = "rotate_y handle out of range"; return; }
                 if (c.n >= MORT_INSTANCE_OPS) { err = "more than 7 nested translate/rotate_y wrappers are not supported"; return; }
-                c.kind[c.n] = MORT_OBJ_ROTATE_Y; c.idx[c.n++] = idx;
-                collect(s.rotates[idx].obj_type, s.rotates[idx].obj_idx, c, depth + 1, emit, emit_medium); break;
+                { Chain c2 = c; c2.kind[c2.n] = MORT_OBJ_ROTATE_Y; c2.idx[c2.n++] = idx;
+                  collect(s.rotates[idx].obj_type, s.rotates[idx].obj_idx, c2, depth + 1, emit, emit_medium); } break;
             case MORT_OBJ_HITTABLE_LIST:
                 if (idx < 0 || idx >= (int)s.lists.size()) { err = "list handle out of range"; return; }
                 for (const Handle& h : s.lists[idx].items) collect(h.type, h.idx, c, depth + 1, emit, emit_medium);
@@ -89,7 +96,7 @@ struct Flattener {
     }
     void leaf_world_box(int type, int idx, const Chain& c, float lo[3], float hi[3]) const {
         for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; }
-        auto grow = [&](const float* p, float r) { for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], p[a] - r); hi[a] = fmaxf(hi[a], p[a] + r); } };
+        auto grow = [&](const float* p, float r) { for (int a = 0; a < 3; a++) { lo[a] = fmin_(lo[a], p[a] - r); hi[a] = fmax_(hi[a], p[a] + r); } };
         if (type == MORT_OBJ_SPHERE) {
             const mscn_sphere& sp = s.spheres[idx];
             float c0[3] = {sp.center[0], sp.center[1], sp.center[2]};
@@ -165,7 +172,6 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const Build
 
     out.sphere_pinned.assign(s.spheres.size(), 0);
     // ---- visible leaves in world::hit order (world.cuh:110-168) ----
-    std::vector<Chain> chains;
     int top_type = 0, top_idx = 0;
     // gate = intersection of the reference-BVH node boxes above a leaf (everything for leaves outside a bvh): the product
     // ignores those boxes, which is only right while they contain what hangs below them (checked after the world boxes
@@ -174,9 +180,10 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const Build
     Gate open_gate; for (int a = 0; a < 3; a++) { open_gate.lo[a] = -INFINITY; open_gate.hi[a] = INFINITY; }
     Gate cur_gate = open_gate;
     std::vector<Gate> gates;
+    { const size_t guess = s.spheres.size() + s.quads.size(); out.leaves.reserve(guess); gates.reserve(guess); }
     auto emit = [&](int type, int idx, const Chain& c) {
         LeafRef L; L.type = type; L.idx = idx; L.inst = F.instance_of(c); L.order = (int)out.leaves.size(); L.top_type = top_type; L.top_idx = top_idx;
-        out.leaves.push_back(L); chains.push_back(c); gates.push_back(cur_gate);
+        out.leaves.push_back(L); gates.push_back(cur_gate);
     };
     // media in the order world::hit reaches them: the top-level loop (world.cuh:154-160) and, through wrappers and lists, hitDispatch
     // (objects.cuh:875-877).  `pos` = leaves visited before the medium: what it is clipped against.
@@ -204,7 +211,7 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const Build
             const mscn_bvh_node& nd = s.bvhs[b].nodes[n];
             for (int a = 0; a < 3; a++) {
                 dead = dead || !(nd.bbox[2 * a + 1] > nd.bbox[2 * a]);
-                g.lo[a] = fmaxf(g.lo[a], nd.bbox[2 * a]); g.hi[a] = fminf(g.hi[a], nd.bbox[2 * a + 1]);
+                g.lo[a] = fmax_(g.lo[a], nd.bbox[2 * a]); g.hi[a] = fmin_(g.hi[a], nd.bbox[2 * a + 1]);
             }
             cur_gate = g;
             if (nd.is_internal) { stack.push_back(Visit{nd.right_idx, dead, g}); stack.push_back(Visit{nd.left_idx, dead, g}); }
@@ -292,18 +299,18 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const Build
     for (int a = 0; a < 3; a++) M = fmaxf(M, fabsf(cam.center[a]));
     for (size_t i = 0; i < out.leaves.size(); i++) {
         BuildPrim& p = prims[i];
-        F.leaf_world_box(out.leaves[i].type, out.leaves[i].idx, chains[i], p.lo, p.hi);
+        F.leaf_world_box(out.leaves[i].type, out.leaves[i].idx, out.leaves[i].inst >= 0 ? F.inst_chain[out.leaves[i].inst] : none, p.lo, p.hi);
         p.type = out.leaves[i].type; p.ref = (int)i;
         if (p.type == MORT_OBJ_SPHERE && s.spheres[out.leaves[i].idx].moves) out.n_moving++;
         for (int a = 0; a < 3; a++) {
             if (!(p.lo[a] <= p.hi[a])) return fail("a primitive has a NaN coordinate (no box bounds it)");
-            M = fmaxf(M, fabsf(p.lo[a])); M = fmaxf(M, fabsf(p.hi[a]));
+            M = fmax_(M, fabsf(p.lo[a])); M = fmax_(M, fabsf(p.hi[a]));
         }
         // The reference's BVH boxes stop containing an object when its bubble sort physically swapped something a wrapper
         // points at, or a list grew after it was wrapped (objects.cuh:630-661, 463-469): the reference then culls that object
         // view-dependently.  That is not reproducible without running its BVH; refuse instead of rendering something else.
         for (int a = 0; a < 3 && !s.edited; a++) {          // (an edited scene, mort_update_sphere, has left the reference's build behind)
-            const float tol = 1e-4f * fmaxf(1.0f, fmaxf(fabsf(p.lo[a]), fabsf(p.hi[a])));
+            const float tol = 1e-4f * fmax_(1.0f, fmax_(fabsf(p.lo[a]), fabsf(p.hi[a])));
             if (p.lo[a] < gates[i].lo[a] - tol || p.hi[a] > gates[i].hi[a] + tol)
                 return fail("a bvh node box of the reference's build does not contain an object below it (a wrapper's target was moved by the "
                             "build's in-place sort, or a list grew after it was wrapped): the reference culls it view-dependently; not reproducible");
@@ -348,6 +355,7 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const Build
 
     // ---- emit primitive records in leaf order; rewrite leaf child words to per-type record indices ----
     std::vector<int> rec_index(order.size());
+    { size_t ns = 0; for (const LeafRef& L : out.leaves) ns += L.type == MORT_OBJ_SPHERE ? 1 : 0; out.spheres.reserve(ns); out.sphere_info.reserve(ns); out.quads.reserve(out.leaves.size() - ns); }
     for (size_t i = 0; i < order.size(); i++) {
         const LeafRef& L = out.leaves[order[i]];
         if (L.type == MORT_OBJ_SPHERE) {
@@ -380,7 +388,8 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const Build
         }
     // ---- shade class per record (and per medium): the block wavefront's queue for a hit, decided by one byte ----
     auto tex_cold = [&](int gid) {
-        for (int guard = 0, stack_n = 1, stack[64] = {gid}; stack_n > 0 && guard < 64; guard++) {
+        int stack[64]; stack[0] = gid;
+        for (int guard = 0, stack_n = 1; stack_n > 0 && guard < 64; guard++) {
             const int t = stack[--stack_n];
             if (t < 0 || t >= (int)out.textures.size()) continue;
             const Texture& T = out.textures[t];
@@ -397,9 +406,12 @@ bool flatten_scene(const Scene& s, FlatScene& out, std::string* err, const Build
         if (M.type == MORT_MAT_DIELECTRIC) return SHADE_DIELECTRIC;
         return SHADE_TERMINAL;                                   // diffuse_light, unknown tags
     };
+    std::vector<uint8_t> cls_of(out.materials.size());
+    for (size_t g = 0; g < out.materials.size(); g++) cls_of[g] = shade_class((int)g);
+    auto cls = [&](int gid) -> uint8_t { return gid < 0 || gid >= (int)cls_of.size() ? (uint8_t)SHADE_TERMINAL : cls_of[gid]; };
     out.sphere_cls.resize(out.sphere_info.size()); out.quad_cls.resize(out.quads.size());
-    for (size_t i = 0; i < out.sphere_info.size(); i++) out.sphere_cls[i] = shade_class(out.sphere_info[i].mat_gid);
-    for (size_t i = 0; i < out.quads.size(); i++) out.quad_cls[i] = shade_class(out.quads[i].mat_gid);
+    for (size_t i = 0; i < out.sphere_info.size(); i++) out.sphere_cls[i] = cls(out.sphere_info[i].mat_gid);
+    for (size_t i = 0; i < out.quads.size(); i++) out.quad_cls[i] = cls(out.quads[i].mat_gid);
     for (Medium& M : out.media) M.cls = shade_class(M.mat_gid);
     camera_params(s.cam, out.cam);
     return true;
