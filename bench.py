@@ -237,6 +237,8 @@ def traffic_for(key):
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         e = tj.get(key)
+        if e and "dram_bytes_const" in e:              # capture of a shorter launch of the same kernel: const + per_sample x samples of THIS launch
+            return e, None
         return (e["dram_bytes_per_launch"], e.get("samples_per_launch")) if e else (None, None)
     except Exception:
         return None, None
@@ -432,7 +434,9 @@ def run_mort(a):
         achieved = per_gpu_rays_per_s * flop_per_ray / 1e12
         tkey = f"field{a.field}:{mode_name}" if a.field > 0 else f"scene{a.scene}:{mode_name}"
         traffic, traffic_samples = traffic_for(tkey) if world == 1 else (None, None)
-        if traffic and traffic_samples:                                         # the capture ran a shorter launch of the same kernel: scale to this launch
+        if isinstance(traffic, dict):
+            traffic = traffic["dram_bytes_const"] + traffic["dram_bytes_per_sample"] * samples_per_frame
+        elif traffic and traffic_samples:                                       # the capture ran a shorter launch of the same kernel: scale to this launch
             traffic = traffic * (samples_per_frame / traffic_samples)
         kname = {"mega": "mega_kernel", "pool": "pool_kernel", "wave": "wavefront kernels"}[mode_name]
         workload = (f"sphere field G={a.field} ({st2['n_leaves']} leaves, camera {a.fieldcam})" if a.field > 0 else
@@ -452,7 +456,7 @@ def run_mort(a):
                     "note": "per step: kernel-parameter block up (the scene is resident, as in the reference's frame loop), RGBA8 frame down to pinned host memory"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel variant, this round)", "kernel": kname,
+                         "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel variant, this round; extrapolated from a shorter launch: profiles/r02_traffic.json)", "kernel": kname,
                          "kernel_ms_per_launch": kernel_ms_per_launch,
                          "how": f"algorithmic {flop_per_ray:.0f} FLOP per path segment (SURVEY.md §8d, {flop_cfg}) x segments per launch / CUDA-event kernel time; "
                                 f"peak = {st['sm_count']} SMs x 128 lanes x 2 x median SM clock under load (the path is neither HBM- nor tensor-bound)",
