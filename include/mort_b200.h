@@ -139,7 +139,8 @@ int mort_refit(mort_ctx* ctx);
  * MEGAKERNEL and POOL accumulate exactly (integers) and render bit-identical frames.
  * A scene in which a constant_medium is reached through translate / rotate_y / list wrappers (hitDispatch allows it, objects.cuh:875-877;
  * no shipped scene does it) is always rendered by the block wavefront's general-media build (stages.cu), whatever `mode` says. */
-enum { MORT_MODE_MEGAKERNEL = 0, MORT_MODE_WAVEFRONT = 1, MORT_MODE_POOL = 2 };
+enum { MORT_MODE_MEGAKERNEL = 0, MORT_MODE_WAVEFRONT = 1, MORT_MODE_POOL = 2,
+       MORT_MODE_AUTO = 3 /* MEGAKERNEL or POOL, whichever measured faster for the committed scene's class (the `mort` CLI's default) */ };
 typedef struct {
     uint32_t seed, frame;          /* Philox key; the reference's seed is 69420 (mort.cu:707) */
     int32_t mode;                  /* MORT_MODE_* (default: MORT_MODE_POOL) */

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MORT_B200_LIB") or os.path.join(_HERE, "libmort_b200.so")     # the override is for A/B builds of the same library (experiments)
 ASSET_DIR = os.path.join(_HERE, "assets")
 
-MODE_MEGAKERNEL, MODE_WAVEFRONT, MODE_POOL = 0, 1, 2
+MODE_MEGAKERNEL, MODE_WAVEFRONT, MODE_POOL, MODE_AUTO = 0, 1, 2, 3
 TRACE_BVH, TRACE_BRUTE_FORCE = 0, 1
 
 

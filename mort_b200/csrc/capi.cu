@@ -404,6 +404,16 @@ int mort_render_device(mort_ctx* ctx, const mort_render_opts* opts_in, void* d_a
     // a scene with media nested in wrappers / lists is rendered by the one kernel that carries that visit order (stages.cu)
     const bool general_media = ctx->flat.two_pass == 2;
     if (general_media) { o.mode = MORT_MODE_POOL; o.threads_per_block = 512; o.blocks_per_sm = 2; o.pool_paths = 1024; o.pool_refill = -1; }
+    if (o.mode == MORT_MODE_AUTO) {
+        // Per scene class, from the two schedulers' measured rates on the ten shipped scenes (BASELINE.md sections 3 and 4; they render the same
+        // exact frame, so this is a speed choice only).  The megakernel wins where a path is a few cheap segments in a linear-scan scene — no
+        // light sampling, no noise texture (scenes 2, 3, 5: 5623 / 24 499 / 7214 against 4205 / 10 260 / 4814 Msamples/s) — and on linear-scan
+        // scenes with media (scene 7: 1239 against 1143); the block wavefront wins everywhere else (scenes 1, 4, 6, 8, 9, the sphere fields).
+        const FlatScene& fs = ctx->flat;
+        const bool light_free = fs.light_kind == LIGHT_NONE && fs.noises.empty();
+        o.mode = (o.n_frames <= 1 && fs.linear && (light_free || !fs.media.empty())) ? MORT_MODE_MEGAKERNEL : MORT_MODE_POOL;
+        if (o.mode == MORT_MODE_MEGAKERNEL) { o.threads_per_block = 0; o.blocks_per_sm = 0; }      // pool shapes do not apply
+    }
     const CameraParams& cam = ctx->flat.cam;
     if (o.sample_mod < 1 || o.sample_rem < 0 || o.sample_rem >= o.sample_mod) return fail(ctx, MORT_ERR_ARG, "mort_render: bad sample split");
     FrameParams p; memset(&p, 0, sizeof(p));

@@ -13,7 +13,7 @@
 #include "mort_b200.h"
 
 static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [--aspect A] [--spp S] [--depth D] [--seed X] [--frames F]\n"
-                            "            [--mode mega|wave|pool] [--stage N] [--bps blocks/SM] [--tpb threads] [--pool paths/block] [--field G [--fieldcam 0|1]]\n"
+                            "            [--mode auto|mega|wave|pool] [--stage N] [--bps blocks/SM] [--tpb threads] [--pool paths/block] [--field G [--fieldcam 0|1]]\n"
                             "            [--builder auto|host|gpu] [--motion-bounds] [--gpu-small N] [--gpu-flags N]   tree build (GPU from 16384 leaves up by default)\n"
                             "            [--assets DIR] [--out image.ppm|image.png] [--hdr image.pfm] [--device K] [--load scene.mscn] [--dump scene.mscn]\n"
                             "            [--scene-file scene.txt] [--dump-text scene.txt]\n"
@@ -23,7 +23,7 @@ static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [
 int main(int argc, char** argv) {
     if (argc < 2) return usage();                       // mort.cu:638-641
     int scene = atoi(argv[1]);
-    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = 0, mode = MORT_MODE_POOL, bps = 0, tpb = 0, field = 0, fieldcam = 0, pool = 0, refill = 0, gpus = 1, split = MORT_SPLIT_SAMPLE, xflags = 0;
+    int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = 0, mode = MORT_MODE_AUTO, bps = 0, tpb = 0, field = 0, fieldcam = 0, pool = 0, refill = 0, gpus = 1, split = MORT_SPLIT_SAMPLE, xflags = 0;
     float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr, load, dump, ckpt, text_in, text_out;
     bool accumulate = false, resume = false;
     mort_build_opts bo; memset(&bo, 0, sizeof(bo));
@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
         else if (a == "--builder") { std::string m = nx(); bo.builder = m == "host" ? MORT_BUILD_HOST : m == "gpu" ? MORT_BUILD_GPU : MORT_BUILD_AUTO; }
         else if (a == "--motion-bounds") bo.motion_bounds = 1; else if (a == "--gpu-small") bo.gpu_small = atoi(nx()); else if (a == "--gpu-flags") bo.gpu_flags = atoi(nx());
         else if (a == "--pool") pool = atoi(nx()); else if (a == "--xflags") xflags = atoi(nx()); else if (a == "--refill") refill = atoi(nx());
-        else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : m == "mega" ? MORT_MODE_MEGAKERNEL : MORT_MODE_POOL; }
+        else if (a == "--mode") { std::string m = nx(); mode = m == "wave" ? MORT_MODE_WAVEFRONT : m == "mega" ? MORT_MODE_MEGAKERNEL : m == "pool" ? MORT_MODE_POOL : MORT_MODE_AUTO; }
         else return usage();
     }
     if (gpus > 1) {
