@@ -201,7 +201,12 @@ static bool commit_builder(void* user, const std::vector<BuildPrim>& prims, std:
     const int b = ctx->build_opts.builder;
     const bool gpu = b == MORT_BUILD_GPU || (b == MORT_BUILD_AUTO && prims.size() >= 16384);
     if (!gpu) { build_bvh4(prims, nodes, order, stats, opt); return true; }
-    return gpu_build_bvh4(prims, nodes, order, stats, opt, ctx->stream, ctx->build_opts.gpu_flags, err);
+    if (gpu_build_bvh4(prims, nodes, order, stats, opt, ctx->stream, ctx->build_opts.gpu_flags, err)) return true;
+    if (b == MORT_BUILD_GPU) return false;                // asked for explicitly: report
+    cudaGetLastError();                                   // AUTO: e.g. no room for the workspace next to a host framework's pool — same tree from the host builder
+    if (err) err->clear();
+    build_bvh4(prims, nodes, order, stats, opt);
+    return true;
 }
 static BuildOptions build_options(const mort_ctx* ctx) {
     BuildOptions o;

@@ -2,6 +2,7 @@
 // ordering (needed only because it defines primitive ids), dump/load.
 #include "scene.hpp"
 
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -135,9 +136,20 @@ std::string handle_token(Handle h, char category) {
     if (h.type < 1 || h.type >= n || h.idx < 0) return "none";
     return std::string(tab[h.type]) + std::to_string(h.idx);
 }
-static std::string fs(float v) { char b[48]; snprintf(b, sizeof(b), "%.9g", (double)v); return b; }
+// shortest decimal that reads back as the same float (std::to_chars): round-trips like "%.9g", 10x cheaper — a 10^6-sphere field journals 7 floats per sphere
+static std::string fs(float v) { char b[48]; const auto r = std::to_chars(b, b + sizeof(b), v); return std::string(b, r.ptr); }
 static std::string fs3(V3 v) { return fs(v.x) + " " + fs(v.y) + " " + fs(v.z); }
 static void jlog(Scene& s, const std::string& line) { if (s.journal_mute == 0) s.journal.push_back(line); }
+// one buffer per statement for the primitives that come by the million (same text as the concatenations above would give)
+struct JLine {
+    std::string s;
+    explicit JLine(const char* head) { s.reserve(112); s = head; }
+    JLine& f(float v) { char b[48]; const auto r = std::to_chars(b, b + sizeof(b), v); s.push_back(' '); s.append(b, r.ptr); return *this; }
+    JLine& v(V3 p) { return f(p.x).f(p.y).f(p.z); }
+    JLine& h(Handle hd, char cat) { s.push_back(' '); s += handle_token(hd, cat); return *this; }
+    JLine& hidden(bool skip) { if (skip) s += " hidden"; return *this; }
+};
+static void jlog(Scene& s, JLine& l) { if (s.journal_mute == 0) s.journal.push_back(std::move(l.s)); }
 static const char* hid(bool skip) { return skip ? " hidden" : ""; }
 
 // ------------------------------------------------------------------------------------------------
@@ -225,7 +237,7 @@ Handle Scene::add_isotropic(Handle tex) {
 // hittables
 // ------------------------------------------------------------------------------------------------
 Handle Scene::add_sphere(V3 c, float r, Handle mat, bool skip) {
-    jlog(*this, "sphere " + fs3(c) + " " + fs(r) + " " + handle_token(mat, 'm') + hid(skip));
+    if (journal_mute == 0) { JLine l("sphere"); jlog(*this, l.v(c).f(r).h(mat, 'm').hidden(skip)); }
     mscn_sphere s; memset(&s, 0, sizeof(s));
     put3(s.center, c); s.radius = r; s.moves = 0; s.mat_type = mat.type; s.mat_idx = mat.idx; s.skip = skip ? 1 : 0;
     V3 rv(r, r, r);
@@ -234,7 +246,7 @@ Handle Scene::add_sphere(V3 c, float r, Handle mat, bool skip) {
     return Handle{MORT_OBJ_SPHERE, (int)spheres.size() - 1};
 }
 Handle Scene::add_moving_sphere(V3 c1, V3 c2, float r, Handle mat, bool skip) {
-    jlog(*this, "moving_sphere " + fs3(c1) + " " + fs3(c2) + " " + fs(r) + " " + handle_token(mat, 'm') + hid(skip));
+    if (journal_mute == 0) { JLine l("moving_sphere"); jlog(*this, l.v(c1).v(c2).f(r).h(mat, 'm').hidden(skip)); }
     mscn_sphere s; memset(&s, 0, sizeof(s));
     put3(s.center, c1); s.radius = r; s.moves = 1; put3(s.center_vec, c2 - c1);
     s.mat_type = mat.type; s.mat_idx = mat.idx; s.skip = skip ? 1 : 0;
