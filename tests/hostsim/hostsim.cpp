@@ -50,6 +50,17 @@ int main(int argc, char** argv) {
         ImageRec im; if (!s.images.empty() && load_ppm(assets + "/earthmap.ppm", im)) { s.images[0].rgb = im.rgb; }
     } else if (!build_reference_scene(s, atoi(argv[1]), assets)) { fprintf(stderr, "scene: %s\n", s.error.c_str()); return 2; }
     std::string mode = argv[3];
+    if (const char* e = getenv("MORT_EDIT_SPHERES")) {
+        // what mort_update_sphere does to the host scene (Scene::update_sphere), for N pseudo-random spheres: new centres, every
+        // second one moving, new radii — far outside the boxes the reference's own bvh holds for them
+        const int n = atoi(e); uint64_t st = 12345;
+        auto u = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (float)((st >> 40) & 0xFFFFFF) / 16777216.f; };
+        for (int k = 0; k < n && !s.spheres.empty(); k++) {
+            const int idx = (int)(u() * s.spheres.size()) % (int)s.spheres.size();
+            const V3 c0((u() - 0.5f) * 20.f, u() * 3.f, (u() - 0.5f) * 20.f), c1 = c0 + V3(0, u(), 0);
+            s.update_sphere(idx, c0, (k & 1) ? &c1 : nullptr, 0.1f + u() * 0.6f);
+        }
+    }
     if (mode == "dump") { return s.dump(argv[4]) ? 0 : 3; }
     if (mode == "dumptext") { std::string err; if (!dump_scene_text(s, argv[4], &err)) { fprintf(stderr, "%s\n", err.c_str()); return 3; } return 0; }
     if (mode == "rand") { HostRng g(1); int n = atoi(argv[4]); for (int i = 0; i < n; i++) fprintf(stderr, "%d\n", g.next()); return 0; }

@@ -91,3 +91,29 @@ def test_parallel_bvh_build_gives_the_serial_tree(hostsim, tmp_path):
         assert "bvh ok" in p.stderr and "tree hash" in p.stderr
         outs.append(re.sub(r"build [0-9.]+ ms", "build X ms", p.stderr))
     assert outs[0] == outs[1]
+
+
+def test_edited_spheres_flatten_and_trace_like_brute_force(hostsim, tmp_path):
+    """mort_update_sphere's host side (Scene::update_sphere): spheres of scene 1 — whose world is a reference bvh — are moved far outside
+    the boxes that bvh holds for them; the edited scene must still flatten (an edited scene has left the reference's build behind)
+    and the new tree must agree with brute force and with the oracle working from the edited arrays"""
+    import oracle_binding as O
+    from conftest import bits
+    from mort_b200 import formats as F
+    env = dict(os.environ, MORT_EDIT_SPHERES="120")
+    dump = tmp_path / "edited.mscn"
+    subprocess.run([hostsim, "1", ASSETS, "dump", str(dump)], check=True, capture_output=True, env=env)
+    rng = np.random.default_rng(3)
+    n = 3000
+    o, tgt = rng.uniform(-12, 12, (n, 3)), rng.uniform(-10, 10, (n, 3)); o[:, 1] = np.abs(o[:, 1]) + 0.3; tgt[:, 1] = np.abs(tgt[:, 1]) * 0.3
+    rays = np.concatenate([o, tgt - o, rng.random((n, 1))], 1).astype(np.float32)
+    fin, fout, fbr = tmp_path / "in.mhit", tmp_path / "out.mhit", tmp_path / "br.mhit"
+    F.write_hits(fin, rays, np.zeros(n, dtype=F.hit_dt))
+    p = subprocess.run([hostsim, "1", ASSETS, "trace", str(fin), str(fout)], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    subprocess.run([hostsim, "1", ASSETS, "trace", str(fin), str(fbr), "brute"], check=True, capture_output=True, env=env)
+    out, br = F.read_hits(fout)["hits"], F.read_hits(fbr)["hits"]
+    assert (out["hit"] == br["hit"]).all() and (bits(out["t"]) == bits(br["t"])).all() and (out["leaf_idx"] == br["leaf_idx"]).all()
+    # unedited scene: the same rays must hit something else somewhere (the edit is visible)
+    subprocess.run([hostsim, "1", ASSETS, "trace", str(fin), str(tmp_path / "orig.mhit")], check=True, capture_output=True)
+    assert (bits(F.read_hits(tmp_path / "orig.mhit")["hits"]["t"]) != bits(out["t"])).mean() > 0.01
