@@ -5,6 +5,7 @@ import collections
 import glob
 import json
 import os
+import re
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 README = {}
@@ -28,8 +29,12 @@ def main():
            "on the same box.  Raw lines: `profiles/r02_call_*_ab.jsonl`; what each call built: `scripts/r02/gpu_r2_*.sh`.  Tags: `mega` = round-1",
            "megakernel; `pool_TxB_P` = T threads per block, B blocks per SM, P paths per block pool; `refillN` = lanes refill when N of a warp's lanes",
            "are idle; `xN` = `pool_flags` N; a prefix such as `old_` / `new_` / `cold_` / `top_` names the A/B build of that call.", ""]
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_call_*_ab.jsonl"))):
-        call = os.path.basename(f)[len("r02_call_"):-len("_ab.jsonl")]
+    extra = {"final": "closing call L: leaf postponing (`ab_postpone` = `-DMORT_POSTPONE`) against the shipped build", "n_auto": "call N: `MORT_MODE_AUTO` against `--mode pool` and `--mode mega`"}
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_call_*_ab.jsonl"))) + [os.path.join(ROOT, "profiles", "r02_final_ab.jsonl"), os.path.join(ROOT, "profiles", "r02_n_auto_ab.jsonl")]
+    for f in files:
+        call = os.path.basename(f)[len("r02_"):-len("_ab.jsonl")]
+        call = call[len("call_"):] if call.startswith("call_") else call
+        README.update({"gpu_r2_" + k + ".sh": v for k, v in extra.items()})
         lines = open(f).read().splitlines()
         table, cols = collections.OrderedDict(), []
         for i, l in enumerate(lines):
@@ -37,8 +42,8 @@ def main():
                 continue
             try:
                 d = json.loads(l)
-            except ValueError:
-                continue
+            except ValueError:                          # a line cut short by the call's `cut -c`: the leading fields are all this needs
+                d = {k: (float(v) if "." in v else int(v)) for k, v in re.findall(r'"(scene|width|height|spp_eff|msamples_per_s|regs|bps)":([0-9.]+)', l)}
             if "msamples_per_s" not in d or i + 1 >= len(lines) or not lines[i + 1].lstrip().startswith("#"):
                 continue
             tag, _, args = lines[i + 1].strip()[2:].partition("::")
