@@ -351,7 +351,8 @@ class Renderer:
         self._ck(self._L.mort_get_build_info(self._h, C.byref(b)))
         return b.asdict()
 
-    def update_sphere(self, handle, center0, center1=None, radius=1.0):
+    def update_sphere(self, handle, center0, center1, radius):
+        """Move / resize a sphere of the committed scene (center1 = None: static); call refit() (or commit()) before rendering."""
         self._ck(self._L.mort_update_sphere(self._h, handle, _f3(center0), _f3(center1) if center1 is not None else None, float(radius)))
         return self
 
