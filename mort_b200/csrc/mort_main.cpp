@@ -17,7 +17,7 @@ static int usage() { printf("Usage: mort <number_between_1_and_11> [--width W] [
                             "            [--builder auto|host|gpu] [--motion-bounds] [--gpu-small N] [--gpu-flags N]   tree build (GPU from 16384 leaves up by default)\n"
                             "            [--assets DIR] [--out image.ppm|image.png] [--hdr image.pfm] [--device K] [--load scene.mscn] [--dump scene.mscn]\n"
                             "            [--scene-file scene.txt] [--dump-text scene.txt]\n"
-                            "            [--accumulate [--checkpoint FILE [--resume]]]\n"
+                            "            [--accumulate [--checkpoint FILE [--resume]] [--preview K]]   --preview: rewrite --out every K frames while the image converges\n"
                             "            [--gpus N [--split sample|tile]]   N GPUs of this box, one NCCL reduce of the partial frames per frame\n"); return -1; }
 
 int main(int argc, char** argv) {
@@ -25,7 +25,7 @@ int main(int argc, char** argv) {
     int scene = atoi(argv[1]);
     int width = 0, spp = 0, depth = 0, frames = 1, device = 0, stage = 0, mode = MORT_MODE_AUTO, bps = 0, tpb = 0, field = 0, fieldcam = 0, pool = 0, refill = 0, gpus = 1, split = MORT_SPLIT_SAMPLE, xflags = 0;
     float aspect = 0; unsigned seed = 69420; std::string assets = "mort_b200/assets", out, hdr, load, dump, ckpt, text_in, text_out;
-    bool accumulate = false, resume = false;
+    bool accumulate = false, resume = false; int preview = 0;
     mort_build_opts bo; memset(&bo, 0, sizeof(bo));
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
@@ -37,7 +37,7 @@ int main(int argc, char** argv) {
         else if (a == "--stage") stage = atoi(nx());
         else if (a == "--load") load = nx(); else if (a == "--dump") dump = nx();
         else if (a == "--scene-file") text_in = nx(); else if (a == "--dump-text") text_out = nx();
-        else if (a == "--accumulate") accumulate = true; else if (a == "--checkpoint") ckpt = nx(); else if (a == "--resume") resume = true;
+        else if (a == "--accumulate") accumulate = true; else if (a == "--checkpoint") ckpt = nx(); else if (a == "--resume") resume = true; else if (a == "--preview") preview = atoi(nx());
         else if (a == "--bps") bps = atoi(nx()); else if (a == "--tpb") tpb = atoi(nx());
         else if (a == "--field") field = atoi(nx()); else if (a == "--fieldcam") fieldcam = atoi(nx());
         else if (a == "--gpus") gpus = atoi(nx()); else if (a == "--split") { std::string m = nx(); split = m == "tile" ? MORT_SPLIT_TILE : MORT_SPLIT_SAMPLE; }
@@ -106,8 +106,11 @@ int main(int argc, char** argv) {
         // (if any) is read before the first frame and rewritten after every frame
         for (int f = 0; f < frames; f++) {
             const bool last = f + 1 == frames;
-            if (mort_render_progressive(ctx, &o, 1, ckpt.empty() ? nullptr : ckpt.c_str(), (resume || f > 0) ? 1 : 0, last ? img.data() : nullptr,
+            // the headless stand-in for the reference's live window (gpu_anim.h): the running mean is written out every `preview` frames
+            const bool show = last || (preview > 0 && !out.empty() && (f + 1) % preview == 0);
+            if (mort_render_progressive(ctx, &o, 1, ckpt.empty() ? nullptr : ckpt.c_str(), (resume || f > 0) ? 1 : 0, show ? img.data() : nullptr,
                                         (last && !acc.empty()) ? acc.data() : nullptr, &frames_total) != MORT_OK) return die("render");
+            if (show && !last && mort_write_image(out.c_str(), img.data(), st.width, st.height) != MORT_OK) { fprintf(stderr, "mort: cannot write %s (.ppm or .png)\n", out.c_str()); mort_destroy(ctx); return 4; }
             mort_get_stats(ctx, &st);
             total += st.last_render_ms;
             printf("Avg. time per frame: %3.1f ms\n", total / (f + 1));
