@@ -247,13 +247,14 @@ int mort_group_get_stats(mort_group* g, mort_group_stats* out);
 
 /* ---- parity hook: closest hit of arbitrary rays (world::hit with the medium loop disabled) -------------- */
 enum { MORT_TRACE_BVH = 0, MORT_TRACE_BRUTE_FORCE = 1 };
-/* rays7: n x {ox,oy,oz,dx,dy,dz,time} (host).  out: n records (host).  probes: n * n_medium (host) or NULL. */
+/* rays7: n x {ox,oy,oz,dx,dy,dz,time} (host).  out: n records (host).  probes: n * mort_stats.n_media (host) or NULL — the boundary
+ * probes of the media world::hit's own loop reaches (top level, not hidden), in array order. */
 int mort_trace(mort_ctx* ctx, const float* rays7, int n, mhit_record* out, mhit_medium_probe* probes, int flags);
 
 /* ---- stats -------------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t width, height, sqrt_spp, bounce_limit;
-    int32_t n_leaves, n_spheres, n_quads, n_nodes, bvh_depth, n_media, n_instances, n_materials, n_textures;
+    int32_t n_leaves, n_spheres, n_quads, n_nodes, bvh_depth, n_media /* top-level, visible */, n_instances, n_materials, n_textures;
     double sah_cost, build_ms, upload_ms;
     double last_render_ms;             /* CUDA-event time of the render kernels of the last mort_render* call */
     uint64_t last_segments;            /* path segments (top-level closest-hit queries) of that call */
