@@ -125,6 +125,42 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < nodes.size(); i++) { const float* a = nodes[i].lox; const float* b = f.nodes[i].lox; for (int k = 0; k < 24; k++) if (!(a[k] == b[k])) diff++; }
         fprintf(stderr, "refit of the unchanged scene: %zu box words differ from the builder's (pad %g vs %g)\n", diff, c.pad, f.stats.pad);
         if (diff) g_bad++;
+        // (1b) after an edit (what mort_update_sphere + mort_refit do): every 7th sphere record moves and changes size; the refitted
+        // boxes must contain their primitives and nest.  Done on copies: the motion check below wants the unchanged scene.
+        {
+            std::vector<SphereGeom> moved = f.spheres; std::vector<Bvh4Node> en = f.nodes;
+            std::mt19937 g(7); std::uniform_real_distribution<float> U(-1.f, 1.f);
+            for (size_t i = 0; i < moved.size(); i += 7) { moved[i].cx += 3.f * U(g); moved[i].cy += fabsf(U(g)); moved[i].cz += 3.f * U(g); moved[i].r = 0.1f + 0.5f * fabsf(U(g)); moved[i].vy = i % 14 ? 0.f : 0.4f; }
+            rf::Ctx e = c; e.spheres = moved.data(); e.nodes = en.data(); e.node_t1 = nullptr;
+            ext = 0;
+            for (int i = 0; i < n; i++) rf::body_raw(e, i, false);
+            float M; memcpy(&M, &ext, 4);
+            M = fmaxf(M, fmaxf(fabsf(s.cam.center.x), fmaxf(fabsf(s.cam.center.y), fabsf(s.cam.center.z))));
+            e.pad = 2e-6f * M;
+            for (int i = 0; i < n; i++) rf::body_pad(e, i, false);
+            for (int L = (int)f.stats.level_first.size() - 2; L >= 0; L--)
+                for (int node = f.stats.level_first[L]; node < f.stats.level_first[L + 1]; node++) for (int k = 0; k < 4; k++) rf::body_level(e, node, k, false);
+            size_t bad_edit = 0, chk = 0;
+            for (size_t i = 0; i < en.size(); i++) for (int k = 0; k < 4; k++) {
+                const uint32_t w = en[i].child[k];
+                if (w == MORT_CHILD_EMPTY) continue;
+                const float lo[3] = {en[i].lox[k], en[i].loy[k], en[i].loz[k]}, hi[3] = {en[i].hix[k], en[i].hiy[k], en[i].hiz[k]};
+                if (w & MORT_LEAF_BIT) {
+                    const int first = (int)(w & 0x07FFFFFFu), cnt = (int)((w >> 27) & 7u) + 1;
+                    for (int j = 0; j < cnt; j++) {
+                        const rf::Box b = (w & MORT_LEAF_QUAD_BIT) ? rf::quad_raw_box(e, first + j) : rf::sphere_raw_box(e, first + j, rf::TIME_UNION);
+                        for (int a = 0; a < 3; a++) { chk++; if (b.lo[a] < lo[a] || b.hi[a] > hi[a]) bad_edit++; }
+                    }
+                } else for (int j = 0; j < 4; j++) {
+                    if (en[w].child[j] == MORT_CHILD_EMPTY) continue;
+                    const float clo[3] = {en[w].lox[j], en[w].loy[j], en[w].loz[j]}, chi[3] = {en[w].hix[j], en[w].hiy[j], en[w].hiz[j]};
+                    for (int a = 0; a < 3; a++) { chk++; if (clo[a] < lo[a] || chi[a] > hi[a]) bad_edit++; }
+                }
+            }
+            fprintf(stderr, "refit after moving %zu spheres: %zu containment checks, %zu edit-violations\n", (moved.size() + 6) / 7, chk, bad_edit);
+            if (bad_edit) g_bad++;
+            ext = 0;
+        }
         c.node_t1 = t1.data();
         run(true);
         std::vector<Bvh4Node> t1abs = t1;

@@ -24,7 +24,7 @@ def test_emulated_gpu_build_equals_host_build(buildsim, what, k_small):
     assert "order equal, word/box differences 0" in err
     if not what.startswith("dup"):
         assert "refit of the unchanged scene: 0 box words differ" in err
-        assert " 0 violations" in err
+        assert " 0 violations" in err and " 0 edit-violations" in err
 
 
 @pytest.mark.parametrize("seed", range(12))
