@@ -30,14 +30,16 @@ def test_struct_layouts_match_the_header(tmp_path):
     """ctypes mirrors vs the sizes a C compiler derives from include/mort_b200.h (a mismatch would corrupt every call)"""
     import subprocess
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "mort_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mort_render_opts),'
-                   ' sizeof(mort_camera_desc), sizeof(mort_handle), sizeof(mort_stats), sizeof(mhit_record), sizeof(mscn_camera), sizeof(mscn_header));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "mort_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mort_render_opts),'
+                   ' sizeof(mort_camera_desc), sizeof(mort_handle), sizeof(mort_stats), sizeof(mhit_record), sizeof(mscn_camera), sizeof(mscn_header),'
+                   ' sizeof(mort_build_opts), sizeof(mort_build_info), sizeof(mort_group_stats));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     from mort_b200 import formats as F
     assert sizes == [ctypes.sizeof(api.RenderOpts), ctypes.sizeof(api.CameraDesc), ctypes.sizeof(api.Handle), ctypes.sizeof(api.Stats),
-                     F.hit_dt.itemsize, F.camera_dt.itemsize, F.header_dt.itemsize]
+                     F.hit_dt.itemsize, F.camera_dt.itemsize, F.header_dt.itemsize,
+                     ctypes.sizeof(api.BuildOpts), ctypes.sizeof(api.BuildInfo), ctypes.sizeof(api.GroupStats)]
 
 
 def test_no_cpu_fallback():
